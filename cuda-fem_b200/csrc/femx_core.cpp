@@ -1,0 +1,105 @@
+// Context, error reporting and driver-entry-point resolution.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "femx_internal.h"
+
+static thread_local std::string g_err;
+
+void femx_set_global_error(const std::string& s) { g_err = s; }
+
+int femx_fail(const femx_ctx* ctx, int status, const char* fmt, ...) {
+  char buf[4096];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  if (ctx) ctx->err = buf;
+  return status;
+}
+
+const femx_driver* femx_get_driver(std::string* why) {
+  static femx_driver drv;
+  static std::string err;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    struct {
+      const char* name;
+      void** slot;
+    } syms[] = {
+        {"cuModuleLoadData", (void**)&drv.ModuleLoadData},
+        {"cuModuleUnload", (void**)&drv.ModuleUnload},
+        {"cuModuleGetFunction", (void**)&drv.ModuleGetFunction},
+        {"cuLaunchKernel", (void**)&drv.LaunchKernel},
+        {"cuFuncSetAttribute", (void**)&drv.FuncSetAttribute},
+        {"cuGetErrorString", (void**)&drv.GetErrorString},
+    };
+    for (auto& s : syms) {
+      cudaDriverEntryPointQueryResult q;
+      cudaError_t e = cudaGetDriverEntryPoint(s.name, s.slot, cudaEnableDefault, &q);
+      if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !*s.slot) {
+        err = std::string("cudaGetDriverEntryPoint(") + s.name +
+              ") failed: " + cudaGetErrorString(e);
+        (void)cudaGetLastError();
+        return;
+      }
+    }
+    drv.ok = true;
+  });
+  if (!drv.ok) {
+    if (why) *why = err;
+    return nullptr;
+  }
+  return &drv;
+}
+
+extern "C" {
+
+const char* femx_version(void) { return "femx 0.1 (sm_100a)"; }
+
+const char* femx_last_error(const femx_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_err.c_str();
+}
+
+int femx_ctx_create(int device, femx_ctx** out) {
+  if (!out) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    (void)cudaGetLastError();
+    return femx_fail(nullptr, FEMX_ERR_CUDA,
+                     "femx_ctx_create: no CUDA device (%s); this engine has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  if (device < 0 || device >= n)
+    return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_ctx_create: device %d out of range [0,%d)",
+                     device, n);
+  FEMX_CUDA_OK(nullptr, cudaSetDevice(device));
+  FEMX_CUDA_OK(nullptr, cudaFree(0));  // force primary-context creation
+  cudaDeviceProp p;
+  FEMX_CUDA_OK(nullptr, cudaGetDeviceProperties(&p, device));
+  if (p.major < 10)
+    return femx_fail(nullptr, FEMX_ERR_UNSUPPORTED,
+                     "femx_ctx_create: device %d is sm_%d%d; this build targets sm_100a only",
+                     device, p.major, p.minor);
+  std::string why;
+  if (!femx_get_driver(&why))
+    return femx_fail(nullptr, FEMX_ERR_CUDA, "femx_ctx_create: %s", why.c_str());
+  femx_ctx* c = new femx_ctx();
+  c->device = device;
+  c->sm_count = p.multiProcessorCount;
+  c->smem_optin = p.sharedMemPerBlockOptin;
+  *out = c;
+  return FEMX_OK;
+}
+
+void femx_ctx_destroy(femx_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  delete ctx;
+}
+
+}  // extern "C"

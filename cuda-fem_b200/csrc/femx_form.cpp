@@ -1,0 +1,491 @@
+// Integrand emitter (stands in for GiNaC's WeakForm::build), NVRTC compilation
+// to an sm_100a cubin, and the launches of the two JIT kernels.
+#include <nvrtc.h>
+
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+#include "femx_internal.h"
+#include "femx_jit_src.h"
+
+namespace {
+
+struct Variant {
+  std::string source, log;
+  std::vector<char> cubin;
+  CUmodule module = nullptr;
+  CUfunction fn = nullptr;
+  int smem_set = 0;
+};
+
+std::string num(double v) {
+  char b[64];
+  snprintf(b, sizeof b, "%.17g", v);
+  std::string s = b;
+  if (s.find_first_of(".eEn") == std::string::npos) s += ".0";  // keep it a double literal
+  return "real(" + s + ")";
+}
+
+const char* AX[3] = {"x", "y", "z"};
+
+}  // namespace
+
+struct femx_form {
+  femx_ctx* ctx = nullptr;
+  int dim = 2, nn = 3, nd = 1, dtype = FEMX_F64, builtin = 0, fmad = 1;
+  int n = 3;  // nn*nd
+  std::string prologue;
+  std::vector<std::string> entries;  // n*n
+  int nq = 0;
+  std::vector<double> qw, qr, qs, qt, qu;
+  std::map<std::string, Variant> variants;
+  std::string last_source, last_log;
+  mutable std::string err;
+};
+
+namespace {
+
+// ---- built-in forms ---------------------------------------------------------
+// Geometry follows FunctionSpace (fea_symbolic_nvrtc_sparse.cpp:239-289) and the
+// shape-function derivatives sfR_deriv/sfS_deriv (:68-101):
+//   jac = (x1-x3)(y2-y3) - (y1-y3)(x2-x3)
+//   grad r = ((y2-y3), (x3-x2))/jac   grad s = ((y3-y1), (x1-x3))/jac
+// phi = (r, s, 1-r-s); entries are a(u=phi_lj, v=phi_li)*jac (:337, Q6).
+// Unlike GiNaC's fully expanded strings the common sub-expressions live in a
+// prologue evaluated once per element.
+void emit_geometry(int dim, std::string* pro) {
+  std::ostringstream o;
+  if (dim == 2) {
+    o << "const real jac = (x1-x3)*(y2-y3)-(y1-y3)*(x2-x3);\n"
+         "  const real ijac = real(1.0)/jac;\n"
+         "  const real g1x = (y2-y3)*ijac, g1y = (x3-x2)*ijac;\n"
+         "  const real g2x = (y3-y1)*ijac, g2y = (x1-x3)*ijac;\n"
+         "  const real g3x = -(g1x+g2x), g3y = -(g1y+g2y);\n";
+  } else {
+    // X = x1 r + x2 s + x3 t + x4 (1-r-s-t); J[c][a] = dX_c/dref_a; grads = rows of J^-1
+    o << "const real j00 = x1-x4, j01 = x2-x4, j02 = x3-x4;\n"
+         "  const real j10 = y1-y4, j11 = y2-y4, j12 = y3-y4;\n"
+         "  const real j20 = z1-z4, j21 = z2-z4, j22 = z3-z4;\n"
+         "  const real c00 = j11*j22-j12*j21, c01 = j12*j20-j10*j22, c02 = j10*j21-j11*j20;\n"
+         "  const real jac = j00*c00+j01*c01+j02*c02;\n"
+         "  const real ijac = real(1.0)/jac;\n"
+         "  const real g1x = c00*ijac, g1y = (j02*j21-j01*j22)*ijac, g1z = (j01*j12-j02*j11)*ijac;\n"
+         "  const real g2x = c01*ijac, g2y = (j00*j22-j02*j20)*ijac, g2z = (j02*j10-j00*j12)*ijac;\n"
+         "  const real g3x = c02*ijac, g3y = (j01*j20-j00*j21)*ijac, g3z = (j00*j11-j01*j10)*ijac;\n"
+         "  const real g4x = -(g1x+g2x+g3x), g4y = -(g1y+g2y+g3y), g4z = -(g1z+g2z+g3z);\n";
+  }
+  *pro += o.str();
+}
+
+std::string phi(int dim, int a) {
+  if (a == 0) return "r";
+  if (a == 1) return "s";
+  if (dim == 2) return "(real(1.0)-r-s)";
+  if (a == 2) return "t";
+  return "(real(1.0)-r-s-t)";
+}
+
+std::string gg(int dim, int a, int b) {  // grad phi_a . grad phi_b (1-based names)
+  std::ostringstream o;
+  o << "(";
+  for (int k = 0; k < dim; ++k) {
+    if (k) o << "+";
+    o << "g" << a + 1 << AX[k] << "*g" << b + 1 << AX[k];
+  }
+  o << ")";
+  return o.str();
+}
+
+int emit_builtin(femx_form* f, const femx_form_desc* d) {
+  const int dim = f->dim, nn = f->nn, nd = f->nd, n = f->n;
+  emit_geometry(dim, &f->prologue);
+  f->entries.assign((size_t)n * n, "");
+  if (d->builtin == FEMX_FORM_ELASTICITY) {
+    if (nd != dim) return FEMX_ERR_INVALID;
+    std::ostringstream o;
+    for (int a = 0; a < nn; ++a)
+      for (int b = a; b < nn; ++b)
+        o << "  const real gg" << a + 1 << b + 1 << " = " << gg(dim, a, b) << ";\n";
+    o << "  const real LAM = " << num(d->params[0]) << ", MU = " << num(d->params[1]) << ";\n";
+    f->prologue += o.str();
+  }
+  double cm = d->params[0] != 0.0 ? d->params[0] : 1.0;
+  for (int li = 0; li < n; ++li)
+    for (int lj = 0; lj < n; ++lj) {
+      const int a = li / nd, c = li % nd, b = lj / nd, dd = lj % nd;
+      std::ostringstream o;
+      switch (d->builtin) {
+        case FEMX_FORM_POISSON:
+          o << gg(dim, b, a) << "*jac";
+          break;
+        case FEMX_FORM_POISSON_MASS:
+          o << "(" << gg(dim, b, a) << "+";
+          if (cm != 1.0) o << num(cm) << "*";
+          o << phi(dim, b) << "*" << phi(dim, a) << ")*jac";
+          break;
+        case FEMX_FORM_MASS:
+          o << "(" << phi(dim, b) << "*" << phi(dim, a) << ")*jac";
+          break;
+        case FEMX_FORM_ELASTICITY: {
+          const int lo = a < b ? a : b, hi = a < b ? b : a;
+          o << "(LAM*g" << a + 1 << AX[c] << "*g" << b + 1 << AX[dd] << "+MU*(";
+          if (c == dd) o << "gg" << lo + 1 << hi + 1 << "+";
+          o << "g" << a + 1 << AX[dd] << "*g" << b + 1 << AX[c] << "))*jac";
+          break;
+        }
+        default:
+          return FEMX_ERR_INVALID;
+      }
+      f->entries[(size_t)li * n + lj] = o.str();
+    }
+  return FEMX_OK;
+}
+
+void default_rule(femx_form* f) {
+  if (f->dim == 2) {
+    // the reference's literals, fea_symbolic_nvrtc_sparse.cpp:380-383
+    static const double w[7] = {0.06296959, 0.06619708, 0.06296959, 0.06619708,
+                                0.06296959, 0.06619708, 0.11250000};
+    static const double r[7] = {0.10128651, 0.47014206, 0.79742699, 0.47014206,
+                                0.10128651, 0.05971587, 0.33333333};
+    static const double s[7] = {0.10128651, 0.05971587, 0.10128651, 0.47014206,
+                                0.79742699, 0.47014206, 0.33333333};
+    static const double t[7] = {0.79742698, 0.47014207, 0.1012865, 0.05971588,
+                                0.1012865,  0.47014207, 0.33333334};
+    f->nq = 7;
+    f->qw.assign(w, w + 7);
+    f->qr.assign(r, r + 7);
+    f->qs.assign(s, s + 7);
+    f->qt.assign(t, t + 7);
+    f->qu.assign(7, 0.0);
+  } else {
+    const double a = 0.5854101966249685, b = 0.1381966011250105;
+    f->nq = 4;
+    f->qw.assign(4, 1.0 / 24.0);
+    f->qr = {a, b, b, b};
+    f->qs = {b, a, b, b};
+    f->qt = {b, b, a, b};
+    f->qu.resize(4);
+    for (int q = 0; q < 4; ++q) f->qu[q] = 1.0 - f->qr[q] - f->qs[q] - f->qt[q];
+  }
+}
+
+// One macro per matrix row: FEMX_ROW_<li>(R,S,T,U,W) adds one quadrature point.
+std::string build_defines(const femx_form* f) {
+  std::ostringstream o;
+  const int n = f->n;
+  o << "#define FEMX_REAL " << (f->dtype == FEMX_F32 ? "float" : "double") << "\n";
+  o << "#define NN " << f->nn << "\n#define ND " << f->nd << "\n#define DIM " << f->dim
+    << "\n#define FEMX_TILE_NODES " << femx_tile_nodes_for(f->nd) << "\n";
+  std::string pro = f->prologue;
+  // a multi-line prologue becomes one macro body
+  std::string esc;
+  for (char ch : pro) {
+    if (ch == '\n') esc += " \\\n"; else esc += ch;
+  }
+  o << "#define FEMX_PROLOGUE " << esc << "\n";
+  for (int li = 0; li < n; ++li) {
+    o << "#define FEMX_ROW_" << li << "(R,S,T,U,W) { const real r = (R), s = (S), t = (T), u = (U), w = (W); "
+         "(void)r; (void)s; (void)t; (void)u;";
+    for (int lj = 0; lj < n; ++lj)
+      o << " \\\n    out[" << lj << "] += w*(" << f->entries[(size_t)li * n + lj] << ");";
+    o << " }\n";
+  }
+  o << "#define FEMX_QUAD(M)";
+  for (int q = 0; q < f->nq; ++q)
+    o << " \\\n    M(" << num(f->qr[q]) << "," << num(f->qs[q]) << "," << num(f->qt[q]) << ","
+      << num(f->qu[q]) << "," << num(f->qw[q]) << ")";
+  o << "\n#define FEMX_ROW_CASES";
+  for (int li = 0; li < n; ++li)
+    o << " \\\n    case " << li << ": FEMX_QUAD(FEMX_ROW_" << li << ") break;";
+  o << "\n";
+  return o.str();
+}
+
+int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, bool load) {
+  auto it = f->variants.find(kernel);
+  if (it == f->variants.end()) {
+    Variant v;
+    const char* body = nullptr;
+    const char* entry = nullptr;
+    if (kernel == "coo") { body = kFemxJitCoo; entry = "femx_coo"; }
+    else if (kernel == "csr") { body = kFemxJitCsr; entry = "femx_csr"; }
+    else return femx_fail(f->ctx, FEMX_ERR_INVALID, "unknown kernel variant '%s'", kernel.c_str());
+    (void)entry;
+    v.source = "// femx JIT kernel '" + kernel + "' (generated)\n" + build_defines(f) +
+               kFemxJitCommon + body;
+    nvrtcProgram prog;
+    std::string fname = "femx_" + kernel + ".cu";
+    nvrtcResult r = nvrtcCreateProgram(&prog, v.source.c_str(), fname.c_str(), 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS)
+      return femx_fail(f->ctx, FEMX_ERR_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
+                                     f->fmad ? "--fmad=true" : "--fmad=false"};
+    r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+    size_t ls = 0;
+    nvrtcGetProgramLogSize(prog, &ls);
+    v.log.resize(ls);
+    if (ls) nvrtcGetProgramLog(prog, &v.log[0]);
+    f->last_source = v.source;
+    f->last_log = v.log;
+    if (r != NVRTC_SUCCESS) {
+      nvrtcDestroyProgram(&prog);
+      f->err = "NVRTC compilation of kernel '" + kernel + "' failed:\n" + v.log;
+      return femx_fail(f->ctx, FEMX_ERR_NVRTC, "%s", f->err.c_str());
+    }
+    size_t cs = 0;
+    r = nvrtcGetCUBINSize(prog, &cs);
+    if (r != NVRTC_SUCCESS || cs == 0) {
+      nvrtcDestroyProgram(&prog);
+      return femx_fail(f->ctx, FEMX_ERR_NVRTC, "nvrtcGetCUBINSize: %s", nvrtcGetErrorString(r));
+    }
+    v.cubin.resize(cs);
+    nvrtcGetCUBIN(prog, v.cubin.data());
+    nvrtcDestroyProgram(&prog);
+    it = f->variants.emplace(kernel, std::move(v)).first;
+  }
+  Variant& v = it->second;
+  if (load && !v.fn) {
+    if (!f->ctx)
+      return femx_fail(nullptr, FEMX_ERR_CUDA,
+                       "form was compiled offline (no device context); cannot launch");
+    const femx_driver* drv = femx_get_driver(nullptr);
+    if (!drv) return femx_fail(f->ctx, FEMX_ERR_CUDA, "CUDA driver entry points unavailable");
+    cudaSetDevice(f->ctx->device);
+    CUresult cr = drv->ModuleLoadData(&v.module, v.cubin.data());
+    const char* es = nullptr;
+    if (cr != CUDA_SUCCESS) {
+      drv->GetErrorString(cr, &es);
+      return femx_fail(f->ctx, FEMX_ERR_CUDA, "cuModuleLoadData: %s", es ? es : "?");
+    }
+    std::string entry = "femx_" + kernel;
+    cr = drv->ModuleGetFunction(&v.fn, v.module, entry.c_str());
+    if (cr != CUDA_SUCCESS) {
+      drv->GetErrorString(cr, &es);
+      return femx_fail(f->ctx, FEMX_ERR_CUDA, "cuModuleGetFunction(%s): %s", entry.c_str(),
+                       es ? es : "?");
+    }
+  }
+  if (outv) *outv = &v;
+  return FEMX_OK;
+}
+
+int make_form(femx_ctx* ctx, const femx_form_desc* d, femx_form** out) {
+  if (!d || !out) return femx_fail(ctx, FEMX_ERR_INVALID, "femx_form_compile: NULL argument");
+  *out = nullptr;
+  if (!((d->dim == 2 && d->nn == 3) || (d->dim == 3 && d->nn == 4)))
+    return femx_fail(ctx, FEMX_ERR_UNSUPPORTED,
+                     "femx_form_compile: only P1 simplices (dim=2,nn=3 / dim=3,nn=4), got dim=%d nn=%d",
+                     d->dim, d->nn);
+  if (d->nd < 1 || d->nd > 3)
+    return femx_fail(ctx, FEMX_ERR_INVALID, "femx_form_compile: nd=%d out of range", d->nd);
+  if (d->dtype != FEMX_F64 && d->dtype != FEMX_F32)
+    return femx_fail(ctx, FEMX_ERR_INVALID, "femx_form_compile: bad dtype %d", d->dtype);
+  femx_form* f = new femx_form();
+  f->ctx = ctx;
+  f->dim = d->dim; f->nn = d->nn; f->nd = d->nd; f->dtype = d->dtype;
+  f->builtin = d->builtin; f->fmad = d->fmad ? 1 : 0;
+  f->n = d->nn * d->nd;
+  if (d->builtin == FEMX_FORM_CUSTOM) {
+    if (!d->entries) {
+      delete f;
+      return femx_fail(ctx, FEMX_ERR_INVALID, "femx_form_compile: custom form without entries");
+    }
+    for (int k = 0; k < f->n * f->n; ++k) {
+      if (!d->entries[k]) {
+        delete f;
+        return femx_fail(ctx, FEMX_ERR_INVALID, "femx_form_compile: entries[%d] is NULL", k);
+      }
+      std::string s = d->entries[k];
+      while (!s.empty() && (s.back() == '\n' || s.back() == ';' || s.back() == ' ')) s.pop_back();
+      f->entries.push_back(s);
+    }
+    if (d->prologue) f->prologue = d->prologue;
+  } else {
+    if (d->builtin != FEMX_FORM_ELASTICITY && d->nd != 1) {
+      delete f;
+      return femx_fail(ctx, FEMX_ERR_INVALID, "femx_form_compile: scalar form needs nd=1");
+    }
+    int st = emit_builtin(f, d);
+    if (st != FEMX_OK) {
+      delete f;
+      return femx_fail(ctx, st, "femx_form_compile: bad built-in form %d (nd=%d, dim=%d)",
+                       d->builtin, d->nd, d->dim);
+    }
+  }
+  if (d->nq > 0) {
+    if (!d->qw || !d->qr || !d->qs || (d->dim == 3 && !d->qt)) {
+      delete f;
+      return femx_fail(ctx, FEMX_ERR_INVALID, "femx_form_compile: incomplete quadrature rule");
+    }
+    f->nq = d->nq;
+    f->qw.assign(d->qw, d->qw + d->nq);
+    f->qr.assign(d->qr, d->qr + d->nq);
+    f->qs.assign(d->qs, d->qs + d->nq);
+    f->qt.resize(d->nq);
+    f->qu.assign(d->nq, 0.0);
+    for (int q = 0; q < d->nq; ++q) {
+      if (d->dim == 2) {
+        f->qt[q] = d->qt ? d->qt[q] : 1.0 - d->qr[q] - d->qs[q];
+      } else {
+        f->qt[q] = d->qt[q];
+        f->qu[q] = d->qu ? d->qu[q] : 1.0 - d->qr[q] - d->qs[q] - d->qt[q];
+      }
+    }
+  } else {
+    default_rule(f);
+  }
+  int st = compile_variant(f, "coo", nullptr, ctx != nullptr);
+  if (st != FEMX_OK) {
+    if (ctx) ctx->err = f->err.empty() ? ctx->err : f->err;
+    delete f;
+    return st;
+  }
+  *out = f;
+  return FEMX_OK;
+}
+
+int check_mesh(const femx_form* f, const femx_mesh_view* m, bool* expanded) {
+  if (!m) return femx_fail(f->ctx, FEMX_ERR_INVALID, "mesh view is NULL");
+  if (m->dim != f->dim || m->nn != f->nn)
+    return femx_fail(f->ctx, FEMX_ERR_INVALID, "mesh (dim=%d,nn=%d) does not match form (dim=%d,nn=%d)",
+                     m->dim, m->nn, f->dim, f->nn);
+  bool ex = m->d_elem_xyz[0] != nullptr;
+  const void* const* c = ex ? m->d_elem_xyz : m->d_node_xyz;
+  for (int k = 0; k < f->dim; ++k)
+    if (!c[k]) return femx_fail(f->ctx, FEMX_ERR_INVALID, "mesh view: coordinate array %d is NULL", k);
+  if (m->n_elems < 0 || m->n_nodes < 0)
+    return femx_fail(f->ctx, FEMX_ERR_INVALID, "mesh view: negative size");
+  *expanded = ex;
+  return FEMX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int femx_form_compile(femx_ctx* ctx, const femx_form_desc* desc, femx_form** out) {
+  if (!ctx) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_form_compile: ctx is NULL");
+  return make_form(ctx, desc, out);
+}
+
+int femx_form_compile_offline(const femx_form_desc* desc, femx_form** out) {
+  return make_form(nullptr, desc, out);
+}
+
+void femx_form_destroy(femx_form* form) {
+  if (!form) return;
+  const femx_driver* drv = femx_get_driver(nullptr);
+  for (auto& kv : form->variants)
+    if (kv.second.module && drv) drv->ModuleUnload(kv.second.module);
+  delete form;
+}
+
+const char* femx_form_source(const femx_form* form) { return form ? form->last_source.c_str() : ""; }
+const char* femx_form_log(const femx_form* form) { return form ? form->last_log.c_str() : ""; }
+const char* femx_form_prologue(const femx_form* form) { return form ? form->prologue.c_str() : ""; }
+
+const char* femx_form_entry(const femx_form* form, int li, int lj) {
+  if (!form || li < 0 || lj < 0 || li >= form->n || lj >= form->n) return nullptr;
+  return form->entries[(size_t)li * form->n + lj].c_str();
+}
+
+int femx_form_cubin(femx_form* form, const char* kernel, const void** cubin, size_t* size) {
+  if (!form || !kernel) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_form_cubin: NULL argument");
+  Variant* v = nullptr;
+  int st = compile_variant(form, kernel, &v, false);
+  if (st != FEMX_OK) return st;
+  form->last_source = v->source;
+  form->last_log = v->log;
+  if (cubin) *cubin = v->cubin.data();
+  if (size) *size = v->cubin.size();
+  return FEMX_OK;
+}
+
+int femx_assemble_coo(femx_form* form, const femx_mesh_view* mesh, void* d_A, int32_t* d_rowA,
+                      int32_t* d_colA, void* stream) {
+  if (!form) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_assemble_coo: form is NULL");
+  bool expanded = false;
+  int st = check_mesh(form, mesh, &expanded);
+  if (st != FEMX_OK) return st;
+  if (!mesh->d_conn && (!expanded || d_rowA || d_colA))
+    return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_coo: connectivity is NULL");
+  if (mesh->n_elems == 0) return FEMX_OK;
+  Variant* v = nullptr;
+  st = compile_variant(form, "coo", &v, true);
+  if (st != FEMX_OK) return st;
+  const femx_driver* drv = femx_get_driver(nullptr);
+  const void* const* c = expanded ? mesh->d_elem_xyz : mesh->d_node_xyz;
+  const void* X = c[0]; const void* Y = c[1]; const void* Z = c[2];
+  long long cs = mesh->node_stride ? mesh->node_stride : 1;
+  int ex = expanded ? 1 : 0;
+  long long ne = mesh->n_elems;
+  const int32_t* conn = mesh->d_conn;
+  void* args[] = {&conn, &X, &Y, &Z, &cs, &ex, &d_A, &d_rowA, &d_colA, &ne};
+  long long threads = ne * form->n;
+  long long blocks = (threads + 255) / 256;
+  if (blocks > 2147483647LL)
+    return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED, "femx_assemble_coo: %lld blocks exceed grid limit", blocks);
+  CUresult cr = drv->LaunchKernel(v->fn, (unsigned)blocks, 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr);
+  if (cr != CUDA_SUCCESS) {
+    const char* es = nullptr;
+    drv->GetErrorString(cr, &es);
+    return femx_fail(form->ctx, FEMX_ERR_CUDA, "femx_assemble_coo: launch failed: %s", es ? es : "?");
+  }
+  return FEMX_OK;
+}
+
+int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_view* mesh,
+                      void* d_values, void* stream) {
+  if (!form || !pat) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_assemble_csr: NULL argument");
+  bool expanded = false;
+  int st = check_mesh(form, mesh, &expanded);
+  if (st != FEMX_OK) return st;
+  if (pat->nn != form->nn || pat->nd != form->nd)
+    return femx_fail(form->ctx, FEMX_ERR_INVALID,
+                     "femx_assemble_csr: pattern (nn=%d,nd=%d) does not match form (nn=%d,nd=%d)",
+                     pat->nn, pat->nd, form->nn, form->nd);
+  if (mesh->n_nodes != pat->n_nodes || mesh->n_elems != pat->n_elems)
+    return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_csr: mesh sizes differ from the pattern's");
+  if (!d_values && pat->nnz_node > 0)
+    return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_csr: d_values is NULL");
+  if (pat->n_rows == 0) return FEMX_OK;
+  Variant* v = nullptr;
+  st = compile_variant(form, "csr", &v, true);
+  if (st != FEMX_OK) return st;
+  const femx_driver* drv = femx_get_driver(nullptr);
+  const size_t rs = form->dtype == FEMX_F32 ? 4 : 8;
+  size_t smem = (size_t)pat->max_tile_nnz * form->nd * form->nd * rs;
+  if (smem > form->ctx->smem_optin)
+    return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED,
+                     "femx_assemble_csr: a %d-row tile needs %zu B of shared memory (> %zu)",
+                     pat->tile_nodes, smem, form->ctx->smem_optin);
+  if ((int)smem > v->smem_set && smem > 48 * 1024) {
+    CUresult cr = drv->FuncSetAttribute(v->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
+    if (cr != CUDA_SUCCESS) return femx_fail(form->ctx, FEMX_ERR_CUDA, "cuFuncSetAttribute(smem=%zu) failed", smem);
+    v->smem_set = (int)smem;
+  }
+  const void* const* c = expanded ? mesh->d_elem_xyz : mesh->d_node_xyz;
+  const void* X = c[0]; const void* Y = c[1]; const void* Z = c[2];
+  long long cs = mesh->node_stride ? mesh->node_stride : 1;
+  int ex = expanded ? 1 : 0;
+  int n_rows = (int)pat->n_rows;
+  int col_base = (int)pat->col_base;
+  const int2* rowinfo = pat->d_rowinfo;
+  const int32_t* col = pat->d_col_idx;
+  const uint32_t* code = pat->d_pair_code;
+  const int32_t* pelem = pat->d_pair_elem;
+  void* args[] = {&rowinfo, &col, &code, &pelem, &X, &Y, &Z, &cs, &ex, &d_values, &n_rows, &col_base};
+  unsigned blocks = (unsigned)((pat->n_rows + pat->tile_nodes - 1) / pat->tile_nodes);
+  unsigned threads = (unsigned)(pat->tile_nodes * form->nd);
+  CUresult cr = drv->LaunchKernel(v->fn, blocks, 1, 1, threads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
+  if (cr != CUDA_SUCCESS) {
+    const char* es = nullptr;
+    drv->GetErrorString(cr, &es);
+    return femx_fail(form->ctx, FEMX_ERR_CUDA, "femx_assemble_csr: launch failed: %s", es ? es : "?");
+  }
+  return FEMX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// Internal declarations shared by the translation units of libfemx.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "femx.h"
+
+struct femx_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  double* d_scratch = nullptr;  // partial sums of femx_dot2 (2 * FEMX_DOT_BLOCKS doubles)
+  mutable std::string err;
+};
+
+// Driver entry points resolved through cudaGetDriverEntryPoint so that the
+// library has no link-time dependency on libcuda.so (it must load, and its
+// symbols be listable, on a box without a driver).
+struct femx_driver {
+  CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned,
+                           unsigned, unsigned, CUstream, void**, void**) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  bool ok = false;
+};
+const femx_driver* femx_get_driver(std::string* why);
+
+int femx_fail(const femx_ctx* ctx, int status, const char* fmt, ...);
+void femx_set_global_error(const std::string& s);
+
+#define FEMX_CUDA_OK(ctx, call)                                                    \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess)                                                        \
+      return femx_fail((ctx), FEMX_ERR_CUDA, "%s failed: %s (%s:%d)", #call,      \
+                       cudaGetErrorString(e__), __FILE__, __LINE__);               \
+  } while (0)
+
+// ---- pattern object (femx_pattern.cu) -------------------------------------
+// Node-level CSR + scatter map.  All arrays are device memory owned by the
+// object.  "pair" = (owned row node, adjacent element) incidence.
+struct femx_pattern {
+  femx_ctx* ctx = nullptr;
+  int nn = 0, nd = 1;
+  int64_t n_nodes = 0, n_elems = 0;
+  int64_t row_begin = 0, row_end = 0, col_base = 0;
+  int64_t n_rows = 0;    // node rows owned
+  int64_t nnz_node = 0;  // node-level nonzeros
+  int64_t n_pairs = 0;
+  int max_row = 0;       // longest node-level row
+  int tile_nodes = 0;    // node rows per CTA in the numeric pass
+  int64_t max_tile_nnz = 0;
+  int2* d_rowinfo = nullptr;       // [n_rows+1] {row_ptr, pair_ptr}
+  int32_t* d_col_idx = nullptr;    // [nnz_node] local node id + col_base, ascending per row
+  uint32_t* d_pair_code = nullptr; // [n_pairs] 7-bit row positions of the element's nodes | li<<28
+  int32_t* d_pair_elem = nullptr;  // [n_pairs] e*nn + li, ascending per row
+  int64_t bytes = 0;
+};
+
+#define FEMX_DOT_BLOCKS 1024
+
+static inline int femx_tile_nodes_for(int nd) { return nd == 1 ? 256 : (nd == 2 ? 128 : 64); }

@@ -1,0 +1,143 @@
+// Validation layer: CSR SpMV on the pattern's native layout and the fused
+// vector kernels of an unpreconditioned CG (no reference counterpart).
+// All reductions use a fixed grid and a fixed tree → bitwise reproducible.
+#include "femx_internal.h"
+
+namespace {
+
+// One thread per dof row (i, c).  values are laid out as the dof-level CSR:
+// row start = nd*nd*row_ptr[i] + c*nd*len, entry (p, d) at p*nd + d.
+template <class T>
+__global__ void spmv_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx, int n_rows, int nd,
+                       const T* __restrict__ vals, const T* __restrict__ x, long long x_base, T* __restrict__ y) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n_rows * nd) return;
+  int i = (int)(t / nd), c = (int)(t - (int64_t)i * nd);
+  int lo = rowinfo[i].x, len = rowinfo[i + 1].x - lo;
+  const T* v = vals + (long long)lo * nd * nd + (long long)c * nd * len;
+  double s = 0.0;
+  for (int p = 0; p < len; ++p) {
+    long long col = (long long)col_idx[lo + p] * nd - x_base;
+    for (int d = 0; d < nd; ++d) s += (double)v[p * nd + d] * (double)x[col + d];
+  }
+  y[t] = (T)s;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) dot2_partial(int64_t n, const T* __restrict__ a, const T* __restrict__ b,
+                                                    const T* __restrict__ c, const T* __restrict__ d,
+                                                    double* __restrict__ part) {
+  double s0 = 0.0, s1 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    s0 += (double)a[i] * (double)b[i];
+    if (c) s1 += (double)c[i] * (double)d[i];
+  }
+  __shared__ double sh0[256], sh1[256];
+  sh0[threadIdx.x] = s0; sh1[threadIdx.x] = s1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh0[threadIdx.x] += sh0[threadIdx.x + o]; sh1[threadIdx.x] += sh1[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { part[blockIdx.x] = sh0[0]; part[FEMX_DOT_BLOCKS + blockIdx.x] = sh1[0]; }
+}
+
+__global__ void __launch_bounds__(256) dot2_final(const double* __restrict__ part, int nblocks, double* __restrict__ out) {
+  __shared__ double sh0[256], sh1[256];
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) { s0 += part[i]; s1 += part[FEMX_DOT_BLOCKS + i]; }
+  sh0[threadIdx.x] = s0; sh1[threadIdx.x] = s1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh0[threadIdx.x] += sh0[threadIdx.x + o]; sh1[threadIdx.x] += sh1[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = sh0[0]; out[1] = sh1[0]; }
+}
+
+template <class T>
+__global__ void axpy_ratio_k(int64_t n, const double* __restrict__ num, const double* __restrict__ den, double sign,
+                             const T* __restrict__ x, T* __restrict__ y) {
+  const double alpha = sign * (*num) / (*den);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = (T)((double)y[i] + alpha * (double)x[i]);
+}
+
+template <class T>
+__global__ void xpby_ratio_k(int64_t n, const double* __restrict__ num, const double* __restrict__ den,
+                             const T* __restrict__ r, T* __restrict__ p) {
+  const double beta = (*num) / (*den);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (T)((double)r[i] + beta * (double)p[i]);
+}
+
+inline unsigned nb(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+}  // namespace
+
+extern "C" {
+
+int femx_spmv(const femx_pattern* p, int dtype, const void* d_values, const void* d_x, int64_t x_base, void* d_y,
+              void* stream) {
+  if (!p || !d_values || !d_x || !d_y) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_spmv: NULL argument");
+  if (p->n_rows == 0) return FEMX_OK;
+  FEMX_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
+  int64_t n = p->n_rows * p->nd;
+  if (dtype == FEMX_F64)
+    spmv_k<double><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
+                                                            (const double*)d_values, (const double*)d_x,
+                                                            (long long)x_base, (double*)d_y);
+  else
+    spmv_k<float><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
+                                                           (const float*)d_values, (const float*)d_x,
+                                                           (long long)x_base, (float*)d_y);
+  FEMX_CUDA_OK(p->ctx, cudaGetLastError());
+  return FEMX_OK;
+}
+
+int femx_dot2(femx_ctx* ctx, int dtype, int64_t n, const void* d_a, const void* d_b, const void* d_c, const void* d_d,
+              double* d_out, void* stream) {
+  if (!ctx || !d_a || !d_b || !d_out || (d_c && !d_d))
+    return femx_fail(ctx, FEMX_ERR_INVALID, "femx_dot2: NULL argument");
+  FEMX_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->d_scratch) FEMX_CUDA_OK(ctx, cudaMalloc(&ctx->d_scratch, sizeof(double) * 2 * FEMX_DOT_BLOCKS));
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)std::min<int64_t>(FEMX_DOT_BLOCKS, std::max<int64_t>(1, (n + 255) / 256));
+  if (dtype == FEMX_F64)
+    dot2_partial<double><<<blocks, 256, 0, st>>>(n, (const double*)d_a, (const double*)d_b, (const double*)d_c,
+                                                 (const double*)d_d, ctx->d_scratch);
+  else
+    dot2_partial<float><<<blocks, 256, 0, st>>>(n, (const float*)d_a, (const float*)d_b, (const float*)d_c,
+                                                (const float*)d_d, ctx->d_scratch);
+  dot2_final<<<1, 256, 0, st>>>(ctx->d_scratch, blocks, d_out);
+  FEMX_CUDA_OK(ctx, cudaGetLastError());
+  return FEMX_OK;
+}
+
+int femx_axpy_ratio(femx_ctx* ctx, int dtype, int64_t n, const double* d_num, const double* d_den, double sign,
+                    const void* d_x, void* d_y, void* stream) {
+  if (!ctx || !d_num || !d_den || !d_x || !d_y) return femx_fail(ctx, FEMX_ERR_INVALID, "femx_axpy_ratio: NULL argument");
+  if (n == 0) return FEMX_OK;
+  FEMX_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  if (dtype == FEMX_F64)
+    axpy_ratio_k<double><<<nb(n), 256, 0, (cudaStream_t)stream>>>(n, d_num, d_den, sign, (const double*)d_x, (double*)d_y);
+  else
+    axpy_ratio_k<float><<<nb(n), 256, 0, (cudaStream_t)stream>>>(n, d_num, d_den, sign, (const float*)d_x, (float*)d_y);
+  FEMX_CUDA_OK(ctx, cudaGetLastError());
+  return FEMX_OK;
+}
+
+int femx_xpby_ratio(femx_ctx* ctx, int dtype, int64_t n, const double* d_num, const double* d_den, const void* d_r,
+                    void* d_p, void* stream) {
+  if (!ctx || !d_num || !d_den || !d_r || !d_p) return femx_fail(ctx, FEMX_ERR_INVALID, "femx_xpby_ratio: NULL argument");
+  if (n == 0) return FEMX_OK;
+  FEMX_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  if (dtype == FEMX_F64)
+    xpby_ratio_k<double><<<nb(n), 256, 0, (cudaStream_t)stream>>>(n, d_num, d_den, (const double*)d_r, (double*)d_p);
+  else
+    xpby_ratio_k<float><<<nb(n), 256, 0, (cudaStream_t)stream>>>(n, d_num, d_den, (const float*)d_r, (float*)d_p);
+  FEMX_CUDA_OK(ctx, cudaGetLastError());
+  return FEMX_OK;
+}
+
+}  // extern "C"

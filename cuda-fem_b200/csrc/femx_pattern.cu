@@ -1,0 +1,495 @@
+// The symbolic pass: CSR pattern + scatter map on the device.
+//
+// Replaces the reference's host-side Mesh::getNeighborNodesList
+// (fea_symbolic_nvrtc_sparse2.cpp:181-210: one std::set<int> per node, 9*NE
+// red-black-tree inserts) with
+//   1. histogram of node incidences            (integer atomics: result exact)
+//   2. exclusive scan                          → pair_ptr
+//   3. bucket fill + per-row sort by element   → pair_elem   (ascending ⇒ deterministic)
+//   4. per-row merge of the incident elements' nodes into a sorted unique list → row length
+//   5. exclusive scan                          → row_ptr
+//   6. column fill + per-incidence position codes (the element-slot → CSR-offset map)
+// The output is bit-identical to the reference's sorted std::set rows.
+#include <algorithm>
+#include <cstdio>
+
+#include "femx_internal.h"
+
+#define FEMX_MAX_ROW 128  // node-level row length limit (7-bit positions in pair_code)
+
+namespace {
+
+// ------------------------------------------------------------------ scan ---
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+  __shared__ int warp_sums[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    int s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    if (lane < SCAN_THREADS / 32) warp_sums[lane] = s;
+  }
+  __syncthreads();
+  const int woff = wid ? warp_sums[wid - 1] : 0;
+  *total = warp_sums[SCAN_THREADS / 32 - 1];
+  __syncthreads();
+  return woff + x - v;
+}
+
+// phase 1: per-tile sums (64-bit so that overflow of the grand total is detected)
+__global__ void scan_tile_sums(const int* __restrict__ in, int64_t n, long long* __restrict__ sums) {
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  int s = 0;
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    int64_t i = base + k * SCAN_THREADS + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+  int tot;
+  block_exclusive_scan(s, &tot);
+  if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+// phase 2: one block scans the tile sums in place (exclusive), writes the total
+__global__ void scan_sums(long long* __restrict__ sums, int nt, long long* __restrict__ total) {
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b = 0; b < nt; b += SCAN_THREADS) {
+    int i = b + threadIdx.x;
+    long long v = i < nt ? sums[i] : 0;
+    // simple Hillis-Steele in shared memory (nt is small)
+    __shared__ long long buf[SCAN_THREADS];
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < SCAN_THREADS; o <<= 1) {
+      long long y = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += y;
+      __syncthreads();
+    }
+    if (i < nt) sums[i] = carry + buf[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == SCAN_THREADS - 1) carry += buf[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+// phase 3: exclusive scan inside each tile + tile offset; out has n+1 entries
+__global__ void scan_apply(const int* __restrict__ in, int64_t n, const long long* __restrict__ sums,
+                           int* __restrict__ out) {
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS], s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = base + k < n ? in[base + k] : 0;
+    s += v[k];
+  }
+  int tot;
+  int ex = block_exclusive_scan(s, &tot) + (int)sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+  }
+  if (base <= n - 1 && n - 1 < base + SCAN_ITEMS) out[n] = ex;
+}
+
+// out[0..n] = exclusive scan of in[0..n); *h_total = grand total (host)
+int exclusive_scan(femx_ctx* ctx, const int* d_in, int64_t n, int* d_out, long long* h_total,
+                   cudaStream_t st) {
+  if (n == 0) {
+    FEMX_CUDA_OK(ctx, cudaMemsetAsync(d_out, 0, sizeof(int), st));
+    *h_total = 0;
+    return FEMX_OK;
+  }
+  int nt = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+  long long* d_sums = nullptr;
+  FEMX_CUDA_OK(ctx, cudaMalloc(&d_sums, sizeof(long long) * (nt + 1)));
+  scan_tile_sums<<<nt, SCAN_THREADS, 0, st>>>(d_in, n, d_sums);
+  scan_sums<<<1, SCAN_THREADS, 0, st>>>(d_sums, nt, d_sums + nt);
+  scan_apply<<<nt, SCAN_THREADS, 0, st>>>(d_in, n, d_sums, d_out);
+  cudaError_t e = cudaMemcpyAsync(h_total, d_sums + nt, sizeof(long long), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_sums);
+  FEMX_CUDA_OK(ctx, e);
+  return FEMX_OK;
+}
+
+// ------------------------------------------------------------ incidences ---
+__global__ void count_pairs(const int* __restrict__ conn, int64_t total, int row_begin, int row_end,
+                            int n_nodes, int* __restrict__ cnt, int* __restrict__ err) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= total) return;
+  int node = conn[k];
+  if (node < 0 || node >= n_nodes) { atomicOr(err, 1); return; }
+  if (node >= row_begin && node < row_end) atomicAdd(&cnt[node - row_begin], 1);
+}
+
+__global__ void fill_pairs(const int* __restrict__ conn, int64_t total, int row_begin, int row_end,
+                           const int* __restrict__ pair_ptr, int* __restrict__ cursor,
+                           int* __restrict__ pair_elem) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= total) return;
+  int node = conn[k];
+  if (node >= row_begin && node < row_end) {
+    int r = node - row_begin;
+    int slot = atomicAdd(&cursor[r], 1);
+    pair_elem[pair_ptr[r] + slot] = (int)k;  // k = e*nn + li
+  }
+}
+
+// per row: insertion sort of its incidences (ascending e*nn+li) — the bucket
+// order left by the atomics is arbitrary, the sorted order is not.
+__global__ void sort_pairs(const int* __restrict__ pair_ptr, int n_rows, int* __restrict__ pair_elem) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int lo = pair_ptr[r], hi = pair_ptr[r + 1];
+  for (int i = lo + 1; i < hi; ++i) {
+    int v = pair_elem[i], j = i - 1;
+    while (j >= lo && pair_elem[j] > v) { pair_elem[j + 1] = pair_elem[j]; --j; }
+    pair_elem[j + 1] = v;
+  }
+}
+
+// Sorted duplicate-free union of the nodes of a row's incident elements
+// (= the std::set of getNeighborNodesList).  Returns the length, or -1 if it
+// exceeds FEMX_MAX_ROW.
+template <int NN>
+__device__ __forceinline__ int build_row(const int* __restrict__ conn, const int* __restrict__ pair_elem,
+                                         int lo, int hi, int* list) {
+  int len = 0;
+  for (int k = lo; k < hi; ++k) {
+    const int e = pair_elem[k] / NN;
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+      const int node = conn[(int64_t)e * NN + a];
+      int p = len;
+      while (p > 0 && list[p - 1] > node) --p;
+      if (p > 0 && list[p - 1] == node) continue;
+      if (len == FEMX_MAX_ROW) return -1;
+      for (int q = len; q > p; --q) list[q] = list[q - 1];
+      list[p] = node;
+      ++len;
+    }
+  }
+  return len;
+}
+
+template <int NN>
+__global__ void row_lengths(const int* __restrict__ conn, const int* __restrict__ pair_ptr,
+                            const int* __restrict__ pair_elem, int n_rows, int* __restrict__ rowlen,
+                            int* __restrict__ err, int* __restrict__ max_row) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int list[FEMX_MAX_ROW];
+  int len = build_row<NN>(conn, pair_elem, pair_ptr[r], pair_ptr[r + 1], list);
+  if (len < 0) { atomicOr(err, 2); len = 0; }
+  rowlen[r] = len;
+  atomicMax(max_row, len);
+}
+
+template <int NN>
+__global__ void row_fill(const int* __restrict__ conn, const int* __restrict__ pair_ptr,
+                         const int* __restrict__ pair_elem, const int* __restrict__ row_ptr, int n_rows,
+                         int col_base, int* __restrict__ col_idx, unsigned* __restrict__ pair_code,
+                         int2* __restrict__ rowinfo) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_rows) return;
+  rowinfo[r] = make_int2(row_ptr[r], pair_ptr[r]);
+  if (r == n_rows) return;
+  int list[FEMX_MAX_ROW];
+  const int lo = pair_ptr[r], hi = pair_ptr[r + 1];
+  const int len = build_row<NN>(conn, pair_elem, lo, hi, list);
+  const int rp = row_ptr[r];
+  for (int p = 0; p < len; ++p) col_idx[rp + p] = list[p] + col_base;
+  for (int k = lo; k < hi; ++k) {
+    const int pe = pair_elem[k];
+    const int e = pe / NN, li = pe - e * NN;
+    unsigned code = (unsigned)li << 28;
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+      const int node = conn[(int64_t)e * NN + a];
+      int a0 = 0, b0 = len;  // binary search in the sorted list
+      while (a0 < b0) {
+        int m = (a0 + b0) >> 1;
+        if (list[m] < node) a0 = m + 1; else b0 = m;
+      }
+      code |= (unsigned)a0 << (7 * a);
+    }
+    pair_code[k] = code;
+  }
+}
+
+__global__ void tile_max(const int2* __restrict__ rowinfo, int n_rows, int tile, int* __restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i0 = (int64_t)t * tile;
+  if (i0 >= n_rows) return;
+  int i1 = (int)min((int64_t)n_rows, i0 + tile);
+  atomicMax(out, rowinfo[i1].x - rowinfo[i0].x);
+}
+
+// ---------------------------------------------------------------- exports ---
+__global__ void export_csr_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx, int n_rows,
+                             int nd, long long* __restrict__ rp64, int* __restrict__ rp32,
+                             int* __restrict__ dcol) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // dof row
+  int64_t nrows_d = (int64_t)n_rows * nd;
+  if (t > nrows_d) return;
+  if (t == nrows_d) {
+    long long tot = (long long)rowinfo[n_rows].x * nd * nd;
+    if (rp64) rp64[t] = tot;
+    if (rp32) rp32[t] = (int)tot;
+    return;
+  }
+  int i = (int)(t / nd), c = (int)(t - (int64_t)i * nd);
+  int lo = rowinfo[i].x, len = rowinfo[i + 1].x - lo;
+  long long start = (long long)lo * nd * nd + (long long)c * nd * len;
+  if (rp64) rp64[t] = start;
+  if (rp32) rp32[t] = (int)start;
+  if (dcol)
+    for (int p = 0; p < len; ++p) {
+      int col = col_idx[lo + p];
+      for (int d = 0; d < nd; ++d) dcol[start + (long long)p * nd + d] = col * nd + d;
+    }
+}
+
+__global__ void export_ell_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx, int n_rows,
+                             int width, int* __restrict__ len_out, int* __restrict__ idx) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int lo = rowinfo[r].x, len = rowinfo[r + 1].x - lo;
+  if (len_out) len_out[r] = len;
+  if (idx)
+    for (int j = 0; j < width; ++j) idx[(int64_t)r * width + j] = j < len ? col_idx[lo + j] : 0;
+}
+
+template <class T>
+__global__ void csr_to_ell_k(const int2* __restrict__ rowinfo, int n_rows, int width,
+                             const T* __restrict__ vals, T* __restrict__ ell) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int lo = rowinfo[r].x, len = rowinfo[r + 1].x - lo;
+  for (int j = 0; j < width; ++j) ell[(int64_t)r * width + j] = j < len ? vals[lo + j] : T(0);
+}
+
+template <class T>
+int dev_alloc(femx_ctx* ctx, T** p, int64_t n, int64_t* bytes) {
+  size_t b = sizeof(T) * (size_t)(n > 0 ? n : 1);
+  cudaError_t e = cudaMalloc((void**)p, b);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return femx_fail(ctx, FEMX_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", b, cudaGetErrorString(e));
+  }
+  if (bytes) *bytes += (int64_t)b;
+  return FEMX_OK;
+}
+
+inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+extern "C" {
+
+int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n_elems,
+                       const int32_t* d_conn, int64_t row_begin, int64_t row_end, int64_t col_base,
+                       void* stream, femx_pattern** out) {
+  if (!ctx || !out) return femx_fail(ctx, FEMX_ERR_INVALID, "femx_pattern_build: NULL argument");
+  *out = nullptr;
+  if (nn != 3 && nn != 4)
+    return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: nn=%d (only 3 or 4)", nn);
+  if (nd < 1 || nd > 3) return femx_fail(ctx, FEMX_ERR_INVALID, "femx_pattern_build: nd=%d", nd);
+  if (n_nodes < 0 || n_elems < 0 || row_begin < 0 || row_end < row_begin || row_end > n_nodes)
+    return femx_fail(ctx, FEMX_ERR_INVALID,
+                     "femx_pattern_build: bad sizes (n_nodes=%lld n_elems=%lld rows=[%lld,%lld))",
+                     (long long)n_nodes, (long long)n_elems, (long long)row_begin, (long long)row_end);
+  if (n_elems > 0 && !d_conn) return femx_fail(ctx, FEMX_ERR_INVALID, "femx_pattern_build: d_conn is NULL");
+  if (n_nodes >= (1LL << 31) - 1 || n_elems * nn >= (1LL << 31) - 1 ||
+      (col_base + n_nodes) * nd >= (1LL << 31) - 1)
+    return femx_fail(ctx, FEMX_ERR_UNSUPPORTED,
+                     "femx_pattern_build: sizes exceed 32-bit indexing on one device; shard the mesh");
+  cudaStream_t st = (cudaStream_t)stream;
+  FEMX_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+
+  femx_pattern* p = new femx_pattern();
+  p->ctx = ctx; p->nn = nn; p->nd = nd; p->n_nodes = n_nodes; p->n_elems = n_elems;
+  p->row_begin = row_begin; p->row_end = row_end; p->col_base = col_base;
+  p->n_rows = row_end - row_begin;
+  p->tile_nodes = femx_tile_nodes_for(nd);
+  const int64_t nr = p->n_rows, total = n_elems * nn;
+  int *d_cnt = nullptr, *d_pair_ptr = nullptr, *d_row_ptr = nullptr, *d_flags = nullptr;
+  int st_code = FEMX_OK;
+  auto cleanup = [&]() {
+    cudaFree(d_cnt); cudaFree(d_pair_ptr); cudaFree(d_row_ptr); cudaFree(d_flags);
+  };
+#define PB_TRY(x)                                   \
+  do {                                              \
+    st_code = (x);                                  \
+    if (st_code != FEMX_OK) { cleanup(); femx_pattern_destroy(p); return st_code; } \
+  } while (0)
+#define PB_CUDA(call)                                                                  \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      cleanup(); femx_pattern_destroy(p);                                              \
+      return femx_fail(ctx, FEMX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+    }                                                                                  \
+  } while (0)
+
+  PB_TRY(dev_alloc(ctx, &d_cnt, nr + 1, nullptr));
+  PB_TRY(dev_alloc(ctx, &d_pair_ptr, nr + 1, nullptr));
+  PB_TRY(dev_alloc(ctx, &d_row_ptr, nr + 1, nullptr));
+  PB_TRY(dev_alloc(ctx, &d_flags, 4, nullptr));  // [0] err, [1] max_row, [2] max tile nnz
+  PB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (nr + 1), st));
+  PB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, st));
+
+  // 1-2: incidence histogram + scan
+  if (total > 0)
+    count_pairs<<<nblocks(total, 256), 256, 0, st>>>(d_conn, total, (int)row_begin, (int)row_end,
+                                                     (int)n_nodes, d_cnt, d_flags);
+  long long n_pairs = 0;
+  PB_TRY(exclusive_scan(ctx, d_cnt, nr, d_pair_ptr, &n_pairs, st));
+  int h_flags[4];
+  PB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  if (h_flags[0] & 1) {
+    cleanup(); femx_pattern_destroy(p);
+    return femx_fail(ctx, FEMX_ERR_INVALID, "femx_pattern_build: connectivity holds a node id outside [0,%lld)",
+                     (long long)n_nodes);
+  }
+  p->n_pairs = n_pairs;
+  PB_TRY(dev_alloc(ctx, &p->d_pair_elem, n_pairs, &p->bytes));
+  PB_TRY(dev_alloc(ctx, &p->d_pair_code, n_pairs, &p->bytes));
+  PB_TRY(dev_alloc(ctx, &p->d_rowinfo, nr + 1, &p->bytes));
+
+  // 3: bucket fill + sort
+  PB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (nr + 1), st));
+  if (total > 0) {
+    fill_pairs<<<nblocks(total, 256), 256, 0, st>>>(d_conn, total, (int)row_begin, (int)row_end,
+                                                    d_pair_ptr, d_cnt, p->d_pair_elem);
+    if (nr > 0) sort_pairs<<<nblocks(nr, 128), 128, 0, st>>>(d_pair_ptr, (int)nr, p->d_pair_elem);
+  }
+  // 4-5: row lengths + scan
+  if (nr > 0) {
+    if (nn == 3)
+      row_lengths<3><<<nblocks(nr, 128), 128, 0, st>>>(d_conn, d_pair_ptr, p->d_pair_elem, (int)nr, d_cnt,
+                                                       d_flags, d_flags + 1);
+    else
+      row_lengths<4><<<nblocks(nr, 128), 128, 0, st>>>(d_conn, d_pair_ptr, p->d_pair_elem, (int)nr, d_cnt,
+                                                       d_flags, d_flags + 1);
+  }
+  long long nnz = 0;
+  PB_TRY(exclusive_scan(ctx, d_cnt, nr, d_row_ptr, &nnz, st));
+  PB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  if (h_flags[0] & 2) {
+    cleanup(); femx_pattern_destroy(p);
+    return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: a row has more than %d columns", FEMX_MAX_ROW);
+  }
+  if (nnz >= (1LL << 31) - 1) {
+    cleanup(); femx_pattern_destroy(p);
+    return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: %lld node-level nonzeros exceed 32-bit offsets", nnz);
+  }
+  p->nnz_node = nnz;
+  p->max_row = h_flags[1];
+  PB_TRY(dev_alloc(ctx, &p->d_col_idx, nnz, &p->bytes));
+  // 6: columns + scatter map
+  if (nn == 3)
+    row_fill<3><<<nblocks(nr + 1, 128), 128, 0, st>>>(d_conn, d_pair_ptr, p->d_pair_elem, d_row_ptr, (int)nr,
+                                                      (int)col_base, p->d_col_idx, p->d_pair_code, p->d_rowinfo);
+  else
+    row_fill<4><<<nblocks(nr + 1, 128), 128, 0, st>>>(d_conn, d_pair_ptr, p->d_pair_elem, d_row_ptr, (int)nr,
+                                                      (int)col_base, p->d_col_idx, p->d_pair_code, p->d_rowinfo);
+  if (nr > 0) {
+    int64_t ntiles = (nr + p->tile_nodes - 1) / p->tile_nodes;
+    tile_max<<<nblocks(ntiles, 128), 128, 0, st>>>(p->d_rowinfo, (int)nr, p->tile_nodes, d_flags + 2);
+  }
+  PB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  PB_CUDA(cudaGetLastError());
+  p->max_tile_nnz = h_flags[2];
+  cleanup();
+  *out = p;
+  return FEMX_OK;
+#undef PB_TRY
+#undef PB_CUDA
+}
+
+void femx_pattern_destroy(femx_pattern* p) {
+  if (!p) return;
+  cudaFree(p->d_rowinfo);
+  cudaFree(p->d_col_idx);
+  cudaFree(p->d_pair_code);
+  cudaFree(p->d_pair_elem);
+  delete p;
+}
+
+int femx_pattern_info(const femx_pattern* p, int64_t* n_rows, int64_t* nnz, int64_t* max_row) {
+  if (!p) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_pattern_info: pattern is NULL");
+  if (n_rows) *n_rows = p->n_rows * p->nd;
+  if (nnz) *nnz = p->nnz_node * p->nd * p->nd;
+  if (max_row) *max_row = (int64_t)p->max_row * p->nd;
+  return FEMX_OK;
+}
+
+int64_t femx_pattern_bytes(const femx_pattern* p) { return p ? p->bytes : 0; }
+
+int femx_pattern_export_csr(const femx_pattern* p, int64_t* d_rp64, int32_t* d_rp32, int32_t* d_col,
+                            void* stream) {
+  if (!p) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_pattern_export_csr: pattern is NULL");
+  if (d_rp32 && p->nnz_node * p->nd * p->nd >= (1LL << 31) - 1)
+    return femx_fail(p->ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_export_csr: nnz does not fit a 32-bit row_ptr");
+  FEMX_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
+  int64_t n = p->n_rows * p->nd + 1;
+  export_csr_k<<<nblocks(n, 128), 128, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
+                                                                  (long long*)d_rp64, d_rp32, d_col);
+  FEMX_CUDA_OK(p->ctx, cudaGetLastError());
+  return FEMX_OK;
+}
+
+int femx_pattern_export_ell(const femx_pattern* p, int width, int32_t* d_len, int32_t* d_idx, void* stream) {
+  if (!p) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_pattern_export_ell: pattern is NULL");
+  if (p->nd != 1) return femx_fail(p->ctx, FEMX_ERR_INVALID, "femx_pattern_export_ell: nd must be 1");
+  if (width < p->max_row)
+    return femx_fail(p->ctx, FEMX_ERR_INVALID, "femx_pattern_export_ell: width %d < longest row %d", width, p->max_row);
+  if (p->n_rows == 0) return FEMX_OK;
+  FEMX_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
+  export_ell_k<<<nblocks(p->n_rows, 128), 128, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows,
+                                                                          width, d_len, d_idx);
+  FEMX_CUDA_OK(p->ctx, cudaGetLastError());
+  return FEMX_OK;
+}
+
+int femx_csr_to_ell(const femx_pattern* p, int dtype, int width, const void* d_values, void* d_ell, void* stream) {
+  if (!p || !d_values || !d_ell) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_csr_to_ell: NULL argument");
+  if (p->nd != 1) return femx_fail(p->ctx, FEMX_ERR_INVALID, "femx_csr_to_ell: nd must be 1");
+  if (width < p->max_row)
+    return femx_fail(p->ctx, FEMX_ERR_INVALID, "femx_csr_to_ell: width %d < longest row %d", width, p->max_row);
+  if (p->n_rows == 0) return FEMX_OK;
+  FEMX_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
+  if (dtype == FEMX_F64)
+    csr_to_ell_k<double><<<nblocks(p->n_rows, 128), 128, 0, (cudaStream_t)stream>>>(
+        p->d_rowinfo, (int)p->n_rows, width, (const double*)d_values, (double*)d_ell);
+  else
+    csr_to_ell_k<float><<<nblocks(p->n_rows, 128), 128, 0, (cudaStream_t)stream>>>(
+        p->d_rowinfo, (int)p->n_rows, width, (const float*)d_values, (float*)d_ell);
+  FEMX_CUDA_OK(p->ctx, cudaGetLastError());
+  return FEMX_OK;
+}
+
+}  // extern "C"

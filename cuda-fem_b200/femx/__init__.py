@@ -1,0 +1,375 @@
+"""Python host-side mirror of the femx C ABI (include/femx.h), via ctypes.
+
+This is plumbing for tests and bench.py: torch supplies device memory and
+streams, every compute call goes straight through libfemx.so.  There is no CPU
+fallback — if the library is missing or no device is present the calls raise.
+
+Names follow the reference's vocabulary (fea_symbolic_nvrtc_sparse*.cpp):
+RectangleMesh, WeakForm (→ Form), getNeighborNodesList (→ Pattern), rowA/colA/A.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libfemx.so")
+
+F64, F32 = 0, 1
+CUSTOM, POISSON, POISSON_MASS, MASS, ELASTICITY = 0, 1, 2, 3, 4
+
+_STATUS = {1: "INVALID", 2: "CUDA", 3: "NVRTC", 4: "UNSUPPORTED", 5: "NOMEM"}
+
+
+class FemxError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"femx error {status} ({_STATUS.get(status, '?')}): {msg}")
+        self.status = status
+
+
+class _FormDesc(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int), ("nn", C.c_int), ("nd", C.c_int), ("dtype", C.c_int),
+        ("builtin", C.c_int), ("params", C.c_double * 4),
+        ("entries", C.POINTER(C.c_char_p)), ("prologue", C.c_char_p),
+        ("nq", C.c_int), ("qw", C.POINTER(C.c_double)), ("qr", C.POINTER(C.c_double)),
+        ("qs", C.POINTER(C.c_double)), ("qt", C.POINTER(C.c_double)),
+        ("qu", C.POINTER(C.c_double)), ("fmad", C.c_int),
+    ]
+
+
+class _MeshView(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int), ("nn", C.c_int), ("n_nodes", C.c_int64), ("n_elems", C.c_int64),
+        ("d_conn", C.c_void_p), ("d_node_xyz", C.c_void_p * 3), ("node_stride", C.c_int64),
+        ("d_elem_xyz", C.c_void_p * 3),
+    ]
+
+
+# every symbol include/femx.h declares (tests check the library exports them all)
+SYMBOLS = [
+    "femx_ctx_create", "femx_ctx_destroy", "femx_last_error", "femx_version",
+    "femx_form_compile", "femx_form_compile_offline", "femx_form_destroy", "femx_form_source",
+    "femx_form_log", "femx_form_entry", "femx_form_prologue", "femx_form_cubin",
+    "femx_mesh_rectangle", "femx_mesh_expand", "femx_mesh_box",
+    "femx_assemble_coo", "femx_pattern_build", "femx_pattern_destroy", "femx_pattern_info",
+    "femx_pattern_bytes", "femx_pattern_export_csr", "femx_pattern_export_ell",
+    "femx_assemble_csr", "femx_csr_to_ell", "femx_spmv", "femx_dot2", "femx_axpy_ratio",
+    "femx_xpby_ratio",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libfemx.so (raises if it has not been built: no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FemxError(2, f"{LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        L.femx_last_error.restype = C.c_char_p
+        L.femx_version.restype = C.c_char_p
+        L.femx_form_source.restype = C.c_char_p
+        L.femx_form_log.restype = C.c_char_p
+        L.femx_form_entry.restype = C.c_char_p
+        L.femx_form_prologue.restype = C.c_char_p
+        L.femx_pattern_bytes.restype = C.c_int64
+        for n in ("femx_form_source", "femx_form_log", "femx_form_prologue", "femx_last_error",
+                  "femx_form_destroy", "femx_pattern_destroy", "femx_ctx_destroy", "femx_pattern_bytes"):
+            getattr(L, n).argtypes = [C.c_void_p]
+        L.femx_form_entry.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _vp(x):
+    """device pointer of a torch tensor / int / None → c_void_p"""
+    if x is None:
+        return C.c_void_p(None)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(int(x))
+
+
+def _stream(stream):
+    if stream is None:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if hasattr(stream, "cuda_stream"):
+        return C.c_void_p(stream.cuda_stream)
+    return C.c_void_p(int(stream))
+
+
+def _i64(v):
+    return C.c_int64(int(v))
+
+
+def _dbl(v):
+    return C.c_double(float(v))
+
+
+class Context:
+    """One per device (replaces cuInit/cuCtxCreate, fea_symbolic_nvrtc_sparse.cpp:557-559)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        st = lib().femx_ctx_create(int(device), C.byref(self.h))
+        if st:
+            raise FemxError(st, lib().femx_last_error(None).decode())
+        self.device = device
+
+    def check(self, st):
+        if st:
+            raise FemxError(st, lib().femx_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            lib().femx_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    # ---- structured generators (RectangleMesh::generate on the device)
+    def rectangle_mesh(self, x0, x1, y0, y1, n_row, n_col, row_lo=0, row_hi=None, dtype=F64,
+                       flags=False, stream=None):
+        import torch
+        row_hi = n_row if row_hi is None else row_hi
+        nl = (row_hi - row_lo + 1) * (n_col + 1)
+        ne = 2 * (row_hi - row_lo) * n_col
+        dev = torch.device("cuda", self.device)
+        tdt = torch.float64 if dtype == F64 else torch.float32
+        X = torch.empty(nl, dtype=tdt, device=dev)
+        Y = torch.empty(nl, dtype=tdt, device=dev)
+        flag = torch.empty(nl, dtype=torch.int32, device=dev) if flags else None
+        conn = torch.empty((ne, 3), dtype=torch.int32, device=dev)
+        self.check(lib().femx_mesh_rectangle(self.h, _dbl(x0), _dbl(x1), _dbl(y0), _dbl(y1), _i64(n_row),
+                                             _i64(n_col), _i64(row_lo), _i64(row_hi), dtype, _vp(X), _vp(Y),
+                                             _vp(flag), _vp(conn), _stream(stream)))
+        m = Mesh(2, conn, (X, Y))
+        m.flag = flag
+        return m
+
+    def box_mesh(self, nx, ny, nz, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), k_lo=0, k_hi=None, dtype=F64,
+                 stream=None):
+        import torch
+        k_hi = nz if k_hi is None else k_hi
+        nl = (k_hi - k_lo + 1) * (nx + 1) * (ny + 1)
+        ne = 6 * (k_hi - k_lo) * nx * ny
+        dev = torch.device("cuda", self.device)
+        tdt = torch.float64 if dtype == F64 else torch.float32
+        X, Y, Z = (torch.empty(nl, dtype=tdt, device=dev) for _ in range(3))
+        conn = torch.empty((ne, 4), dtype=torch.int32, device=dev)
+        self.check(lib().femx_mesh_box(self.h, _dbl(lo[0]), _dbl(hi[0]), _dbl(lo[1]), _dbl(hi[1]), _dbl(lo[2]),
+                                       _dbl(hi[2]), _i64(nx), _i64(ny), _i64(nz), _i64(k_lo), _i64(k_hi), dtype,
+                                       _vp(X), _vp(Y), _vp(Z), _vp(conn), _stream(stream)))
+        return Mesh(3, conn, (X, Y, Z))
+
+
+class Mesh:
+    """Device mesh: conn[NE, nn] int32 (gIdx layout) + node coordinates (SoA) and/or
+    element-expanded coordinates X[nn*e+k] (the reference's layout)."""
+
+    def __init__(self, dim, conn, node_xyz=None, elem_xyz=None, n_nodes=None):
+        self.dim = dim
+        self.nn = dim + 1
+        self.conn = conn
+        self.node_xyz = node_xyz
+        self.elem_xyz = elem_xyz
+        self.n_elems = 0 if conn is None else int(conn.shape[0])
+        if conn is None and elem_xyz is not None:
+            self.n_elems = int(elem_xyz[0].numel()) // self.nn
+        self.n_nodes = int(n_nodes) if n_nodes is not None else (
+            int(node_xyz[0].numel()) if node_xyz is not None else 0)
+        self.flag = None
+
+    def expanded(self, ctx, stream=None):
+        """Element-expanded copy (replaces the host loop fea_symbolic_nvrtc_sparse.cpp:571-583)."""
+        import torch
+        out = []
+        for c in self.node_xyz:
+            e = torch.empty(self.n_elems * self.nn, dtype=c.dtype, device=c.device)
+            dt = F64 if c.dtype == torch.float64 else F32
+            ctx.check(lib().femx_mesh_expand(ctx.h, dt, self.nn, _i64(self.n_elems), _vp(self.conn), _vp(c),
+                                             _vp(e), _stream(stream)))
+            out.append(e)
+        return Mesh(self.dim, self.conn, None, tuple(out), n_nodes=self.n_nodes)
+
+    def view(self):
+        v = _MeshView()
+        v.dim, v.nn = self.dim, self.nn
+        v.n_nodes, v.n_elems = self.n_nodes, self.n_elems
+        v.d_conn = None if self.conn is None else self.conn.data_ptr()
+        v.node_stride = 1
+        for k in range(3):
+            v.d_node_xyz[k] = None
+            v.d_elem_xyz[k] = None
+        if self.elem_xyz is not None:
+            for k, c in enumerate(self.elem_xyz):
+                v.d_elem_xyz[k] = c.data_ptr()
+        elif self.node_xyz is not None:
+            for k, c in enumerate(self.node_xyz):
+                v.d_node_xyz[k] = c.data_ptr()
+        return v
+
+
+class Form:
+    """A JIT-compiled element integrand (WeakForm::build + NVRTC + module load,
+    fea_symbolic_nvrtc_sparse.cpp:307-356, 506-561)."""
+
+    def __init__(self, ctx, dim, builtin=POISSON, nd=1, dtype=F64, params=(), entries=None, prologue=None,
+                 rule=None, fmad=True, offline=False):
+        self.ctx = ctx
+        self.dim, self.nn, self.nd, self.dtype = dim, dim + 1, nd, dtype
+        self.n = self.nn * nd
+        d = _FormDesc()
+        d.dim, d.nn, d.nd, d.dtype, d.builtin = dim, dim + 1, nd, dtype, builtin
+        for i in range(4):
+            d.params[i] = float(params[i]) if i < len(params) else 0.0
+        keep = []
+        if entries is not None:
+            flat = [e for row in entries for e in row] if isinstance(entries[0], (list, tuple)) else list(entries)
+            arr = (C.c_char_p * len(flat))(*[s.encode() for s in flat])
+            keep.append(arr)
+            d.entries = C.cast(arr, C.POINTER(C.c_char_p))
+            d.builtin = CUSTOM
+        d.prologue = prologue.encode() if prologue else None
+        if rule is not None:
+            cols = [list(map(float, c)) if c is not None else None for c in rule]
+            while len(cols) < 5:
+                cols.append(None)
+            d.nq = len(cols[0])
+            ptrs = []
+            for c in cols:
+                if c is None:
+                    ptrs.append(None)
+                else:
+                    a = (C.c_double * len(c))(*c)
+                    keep.append(a)
+                    ptrs.append(C.cast(a, C.POINTER(C.c_double)))
+            d.qw, d.qr, d.qs, d.qt, d.qu = ptrs
+        d.fmad = 1 if fmad else 0
+        self.h = C.c_void_p()
+        if offline:
+            st = lib().femx_form_compile_offline(C.byref(d), C.byref(self.h))
+            if st:
+                raise FemxError(st, lib().femx_last_error(None).decode())
+        else:
+            ctx.check(lib().femx_form_compile(ctx.h, C.byref(d), C.byref(self.h)))
+
+    def _check(self, st):
+        if st:
+            raise FemxError(st, lib().femx_last_error(self.ctx.h if self.ctx else None).decode())
+
+    @property
+    def source(self):
+        return lib().femx_form_source(self.h).decode()
+
+    @property
+    def log(self):
+        return lib().femx_form_log(self.h).decode()
+
+    @property
+    def prologue(self):
+        return lib().femx_form_prologue(self.h).decode()
+
+    def entry(self, li, lj):
+        s = lib().femx_form_entry(self.h, li, lj)
+        return None if s is None else s.decode()
+
+    def cubin(self, kernel="csr"):
+        p = C.c_void_p()
+        n = C.c_size_t()
+        self._check(lib().femx_form_cubin(self.h, kernel.encode(), C.byref(p), C.byref(n)))
+        return C.string_at(p.value, n.value)
+
+    def _tdtype(self):
+        import torch
+        return torch.float64 if self.dtype == F64 else torch.float32
+
+    def assemble_coo(self, mesh, A=None, rowA=None, colA=None, stream=None, indices=True):
+        """COO triplets, slot e*n*n + li*n + lj (kernel ABI #1)."""
+        import torch
+        n2 = mesh.n_elems * self.n * self.n
+        dev = torch.device("cuda", self.ctx.device)
+        if A is None:
+            A = torch.empty(n2, dtype=self._tdtype(), device=dev)
+        if indices and rowA is None:
+            rowA = torch.empty(n2, dtype=torch.int32, device=dev)
+        if indices and colA is None:
+            colA = torch.empty(n2, dtype=torch.int32, device=dev)
+        v = mesh.view()
+        self._check(lib().femx_assemble_coo(self.h, C.byref(v), _vp(A), _vp(rowA), _vp(colA), _stream(stream)))
+        return A, rowA, colA
+
+    def assemble_csr(self, pattern, mesh, values=None, stream=None):
+        """Deterministic numeric pass into the pattern's CSR (kernel ABI #2)."""
+        import torch
+        if values is None:
+            values = torch.empty(pattern.nnz, dtype=self._tdtype(), device=torch.device("cuda", self.ctx.device))
+        v = mesh.view()
+        self._check(lib().femx_assemble_csr(self.h, pattern.h, C.byref(v), _vp(values), _stream(stream)))
+        return values
+
+    def close(self):
+        if self.h:
+            lib().femx_form_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Pattern:
+    """CSR pattern + scatter map (the symbolic pass; replaces getNeighborNodesList,
+    fea_symbolic_nvrtc_sparse2.cpp:181-210)."""
+
+    def __init__(self, ctx, mesh, nd=1, row_begin=0, row_end=None, col_base=0, stream=None):
+        self.ctx = ctx
+        self.nd = nd
+        row_end = mesh.n_nodes if row_end is None else row_end
+        self.h = C.c_void_p()
+        ctx.check(lib().femx_pattern_build(ctx.h, mesh.nn, nd, _i64(mesh.n_nodes), _i64(mesh.n_elems),
+                                           _vp(mesh.conn), _i64(row_begin), _i64(row_end), _i64(col_base),
+                                           _stream(stream), C.byref(self.h)))
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        ctx.check(lib().femx_pattern_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        self.n_rows, self.nnz, self.max_row = a.value, b.value, c.value
+
+    @property
+    def bytes(self):
+        return lib().femx_pattern_bytes(self.h)
+
+    def csr(self, index_dtype="int32", stream=None):
+        import torch
+        dev = torch.device("cuda", self.ctx.device)
+        col = torch.empty(self.nnz, dtype=torch.int32, device=dev)
+        if index_dtype == "int64":
+            rp = torch.empty(self.n_rows + 1, dtype=torch.int64, device=dev)
+            self.ctx.check(lib().femx_pattern_export_csr(self.h, _vp(rp), _vp(None), _vp(col), _stream(stream)))
+        else:
+            rp = torch.empty(self.n_rows + 1, dtype=torch.int32, device=dev)
+            self.ctx.check(lib().femx_pattern_export_csr(self.h, _vp(None), _vp(rp), _vp(col), _stream(stream)))
+        return rp, col
+
+    def ell(self, width, stream=None):
+        """gNbrNodeLen / gNbrNodeIdx in the reference's padded layout."""
+        import torch
+        dev = torch.device("cuda", self.ctx.device)
+        ln = torch.empty(self.n_rows, dtype=torch.int32, device=dev)
+        idx = torch.empty((self.n_rows, width), dtype=torch.int32, device=dev)
+        self.ctx.check(lib().femx_pattern_export_ell(self.h, int(width), _vp(ln), _vp(idx), _stream(stream)))
+        return ln, idx
+
+    def values_to_ell(self, values, width, stream=None):
+        import torch
+        out = torch.empty((self.n_rows, width), dtype=values.dtype, device=values.device)
+        dt = F64 if values.dtype == torch.float64 else F32
+        self.ctx.check(lib().femx_csr_to_ell(self.h, dt, int(width), _vp(values), _vp(out), _stream(stream)))
+        return out
+
+    def spmv(self, values, x, x_base=0, y=None, stream=None):
+        import torch
+        if y is None:
+            y = torch.empty(self.n_rows, dtype=values.dtype, device=values.device)
+        dt = F64 if values.dtype == torch.float64 else F32
+        self.ctx.check(lib().femx_spmv(self.h, dt, _vp(values), _vp(x), _i64(x_base), _vp(y), _stream(stream)))
+        return y
+
+    def close(self):
+        if self.h:
+            lib().femx_pattern_destroy(self.h)
+            self.h = C.c_void_p()

@@ -1,0 +1,253 @@
+/*
+ * femx.h — C ABI of the B200-native finite-element assembly engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of yuemingl/cuda-fem:
+ *   mesh coordinates + connectivity  →  NVRTC-compiled symbolic element
+ *   integrand  →  assembled global sparse matrix (COO triplets or CSR).
+ *
+ * The reference has no FFI: every program is a main().  Each entry point below
+ * therefore cites the stretch of reference host/device code it replaces
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every pointer named d_* is a DEVICE pointer
+ *     owned by the caller; h_* is a host pointer.
+ *   - every call returns a femx_status (0 = ok); it never exits, aborts or
+ *     throws across the ABI (the reference's NVRTC_SAFE_CALL/CUDA_SAFE_CALL
+ *     macros call exit(1): fea_symbolic_nvrtc_sparse.cpp:16-35).
+ *   - calls are stream-ordered on the cudaStream_t passed as `void* stream`
+ *     (NULL = legacy default stream, what the reference uses:
+ *     fea_symbolic_nvrtc_sparse.cpp:614).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     returns FEMX_ERR_CUDA.
+ */
+#ifndef FEMX_H
+#define FEMX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEMX_VERSION_MAJOR 0
+#define FEMX_VERSION_MINOR 1
+
+typedef enum femx_status {
+  FEMX_OK = 0,
+  FEMX_ERR_INVALID = 1,     /* bad argument                                  */
+  FEMX_ERR_CUDA = 2,        /* CUDA runtime/driver error, or no device       */
+  FEMX_ERR_NVRTC = 3,       /* integrand failed to compile; see femx_last_error */
+  FEMX_ERR_UNSUPPORTED = 4, /* size/shape outside what this build handles    */
+  FEMX_ERR_NOMEM = 5
+} femx_status;
+
+typedef enum femx_dtype { FEMX_F64 = 0, FEMX_F32 = 1 } femx_dtype;
+
+/* Built-in weak forms (the emitter that stands in for GiNaC's
+ * WeakForm::build, fea_symbolic_nvrtc_sparse.cpp:307-356). FEMX_FORM_CUSTOM
+ * takes the (nn*nd)^2 C-expression strings directly, i.e. the reference's
+ * $integrand{li}{lj}$ placeholders (fea_symbolic_nvrtc_sparse.cpp:384-414). */
+typedef enum femx_builtin {
+  FEMX_FORM_CUSTOM = 0,
+  FEMX_FORM_POISSON = 1,      /* grad u . grad v                  (nd = 1) */
+  FEMX_FORM_POISSON_MASS = 2, /* grad u . grad v + c * u v        (nd = 1), c = params[0] (0 → 1) */
+  FEMX_FORM_MASS = 3,         /* u v                               (nd = 1) */
+  FEMX_FORM_ELASTICITY = 4    /* lambda div u div v + 2 mu eps(u):eps(v), nd = dim;
+                                 params[0] = lambda, params[1] = mu          */
+} femx_builtin;
+
+typedef struct femx_ctx femx_ctx;         /* one per device                     */
+typedef struct femx_form femx_form;       /* a JIT-compiled element integrand   */
+typedef struct femx_pattern femx_pattern; /* CSR pattern + scatter map          */
+
+/* ------------------------------------------------------------------ context */
+
+/* Replaces cuInit/cuDeviceGet/cuCtxCreate (fea_symbolic_nvrtc_sparse.cpp:557-559);
+ * binds to the device's primary context instead of creating a new one. */
+int femx_ctx_create(int device, femx_ctx** out);
+void femx_ctx_destroy(femx_ctx* ctx);
+/* Message of the last failing call on this ctx (includes the NVRTC log for
+ * FEMX_ERR_NVRTC, which the reference prints to stdout before exit(1):
+ * fea_symbolic_nvrtc_sparse.cpp:534-542).  ctx == NULL → last global error. */
+const char* femx_last_error(const femx_ctx* ctx);
+const char* femx_version(void);
+
+/* -------------------------------------------------------------------- forms */
+
+typedef struct femx_form_desc {
+  int dim;     /* 2 (P1 triangle, nn = 3) or 3 (P1 tetrahedron, nn = 4)          */
+  int nn;      /* nodes per element                                               */
+  int nd;      /* dofs per node (1 scalar, dim for elasticity)                    */
+  int dtype;   /* femx_dtype of coordinates and matrix values                     */
+  int builtin; /* femx_builtin                                                    */
+  double params[4];
+  /* FEMX_FORM_CUSTOM: n*n strings, n = nn*nd, entries[li*n + lj] is the
+   * integrand of matrix entry (row = dof li, col = dof lj) = a(u=phi_lj, v=phi_li) * jac
+   * as a C expression over x1..x{nn}, y1.., z1.., and the quadrature point
+   * r, s, t (and u in 3-D) — the names the reference's integrand() unpacks from
+   * params[] (fea_symbolic_nvrtc_sparse.cpp:386-394).  Use the type `real`
+   * for casts; pow(x,2.0) is accepted. */
+  const char* const* entries;
+  /* optional C statements evaluated once per element before the quadrature
+   * loop (common sub-expressions such as the Jacobian); may be NULL. */
+  const char* prologue;
+  /* quadrature rule; nq == 0 → default: the reference's 7-point triangle
+   * literals (fea_symbolic_nvrtc_sparse.cpp:380-383) in 2-D, the 4-point
+   * degree-2 rule in 3-D.  qt (2-D: third barycentric; 3-D: third reference
+   * coordinate) and qu (3-D: fourth barycentric) may be NULL → 1 - sum. */
+  int nq;
+  const double* qw;
+  const double* qr;
+  const double* qs;
+  const double* qt;
+  const double* qu;
+  int fmad; /* 1 (default build) allows FMA contraction; 0 = the reference's
+               --fmad=false (fea_symbolic_nvrtc_sparse.cpp:529)              */
+} femx_form_desc;
+
+/* Replaces WeakForm::build + nvrtcCreateProgram … cuModuleGetFunction
+ * (fea_symbolic_nvrtc_sparse.cpp:307-356, 506-561).  Compiles with NVRTC
+ * straight to an sm_100a cubin.  The COO kernel is compiled eagerly (so a bad
+ * expression fails here); other kernel variants on first use. */
+int femx_form_compile(femx_ctx* ctx, const femx_form_desc* desc, femx_form** out);
+void femx_form_destroy(femx_form* form);
+/* Generated CUDA source of the last compiled kernel variant (what the
+ * reference prints at fea_symbolic_nvrtc_sparse.cpp:354) and its NVRTC log. */
+const char* femx_form_source(const femx_form* form);
+const char* femx_form_log(const femx_form* form);
+/* The n*n entry strings actually used (for built-ins: what the emitter
+ * produced; the analogue of the csrc_float output of WeakForm::build).
+ * Returns a pointer valid for the life of the form. */
+const char* femx_form_entry(const femx_form* form, int li, int lj);
+const char* femx_form_prologue(const femx_form* form);
+/* Compile only (no device needed): emits source + cubin for inspection with
+ * cuobjdump.  kernel: "coo", "csr", "csr_expanded".  cubin buffer is owned by the
+ * form. */
+int femx_form_cubin(femx_form* form, const char* kernel, const void** cubin, size_t* size);
+/* As femx_form_compile but never touches the device (ctx may be NULL):
+ * used by the CPU-only test tier and for offline SASS inspection. */
+int femx_form_compile_offline(const femx_form_desc* desc, femx_form** out);
+
+/* --------------------------------------------------------------------- mesh */
+
+typedef struct femx_mesh_view {
+  int dim;
+  int nn;
+  int64_t n_nodes;
+  int64_t n_elems;
+  /* connectivity, reference layout gIdx[nn*e + k]
+   * (fea_symbolic_nvrtc_sparse.cpp:580-582) */
+  const int32_t* d_conn;
+  /* node-indexed coordinates (SoA, dtype of the form), d_node_xyz[c][node*node_stride];
+   * NULL when element-expanded coordinates are given instead */
+  const void* d_node_xyz[3];
+  int64_t node_stride; /* in elements; 0 → 1 */
+  /* element-expanded coordinates, reference layout X[nn*e + k], Y[nn*e + k]
+   * (fea_symbolic_nvrtc_sparse.cpp:574-579); NULL when node-indexed */
+  const void* d_elem_xyz[3];
+} femx_mesh_view;
+
+/* Device-side structured generators (replace RectangleMesh::generate,
+ * fea_symbolic_nvrtc_sparse.cpp:170-216, whose per-node `new` cannot reach
+ * 10^8 elements).  Node index i*(nCol+1)+j, two CCW triangles per cell
+ * (n, n+1, n+nCol+1) and (n+1, n+nCol+2, n+nCol+1) — exactly the reference.
+ * Only node rows [row_lo, row_hi] and cell rows [row_lo, row_hi) are produced
+ * (a slab for multi-GPU); local node index = global - row_lo*(nCol+1).
+ * Any output pointer may be NULL. d_flag gets the boundary flag
+ * (fea_test.cu:100-103). */
+int femx_mesh_rectangle(femx_ctx* ctx, double x0, double x1, double y0, double y1,
+                        int64_t nRow, int64_t nCol, int64_t row_lo, int64_t row_hi,
+                        int dtype, void* d_x, void* d_y, int32_t* d_flag,
+                        int32_t* d_conn, void* stream);
+/* Element-expanded coordinates from node coordinates (replaces the host
+ * flattening loop fea_symbolic_nvrtc_sparse.cpp:571-583). */
+int femx_mesh_expand(femx_ctx* ctx, int dtype, int nn, int64_t n_elems,
+                     const int32_t* d_conn, const void* d_node, void* d_elem,
+                     void* stream);
+/* Unit-box Kuhn mesh: (nx,ny,nz) cells, 6 positively oriented tets per cell
+ * around the (0,0,0)-(1,1,1) diagonal, node index (k*(ny+1)+j)*(nx+1)+i.
+ * No reference counterpart (the reference is 2-D only). Slab in k:
+ * node planes [k_lo, k_hi], cell layers [k_lo, k_hi). */
+int femx_mesh_box(femx_ctx* ctx, double x0, double x1, double y0, double y1,
+                  double z0, double z1, int64_t nx, int64_t ny, int64_t nz,
+                  int64_t k_lo, int64_t k_hi, int dtype, void* d_x, void* d_y,
+                  void* d_z, int32_t* d_conn, void* stream);
+
+/* ---------------------------------------------------------- kernel ABI #1: COO */
+
+/* Replaces fea_kernel (COO variant) + its launch
+ * (fea_symbolic_nvrtc_sparse.cpp:415-480, 604-615): slot = e*n*n + li*n + lj,
+ * rowA = dof of local row li, colA = dof of local col lj, A = sum_q w_q *
+ * integrand(li,lj).  Duplicates are NOT merged (as in the reference). */
+int femx_assemble_coo(femx_form* form, const femx_mesh_view* mesh, void* d_A,
+                      int32_t* d_rowA, int32_t* d_colA, void* stream);
+
+/* ------------------------------------- kernel ABI #2: pattern + numeric pass */
+
+/* The symbolic pass.  Replaces Mesh::getNeighborNodesList
+ * (fea_symbolic_nvrtc_sparse2.cpp:181-210): per row the ascending, duplicate-free
+ * list of all nodes sharing an element with it, diagonal included.  Runs on the
+ * device (histogram + scan + per-row sort/unique) and also builds the
+ * element-slot → CSR-offset scatter map used by femx_assemble_csr.
+ *
+ * Rows are built for local nodes [row_begin, row_end) only (0, n_nodes for the
+ * whole mesh); column indices are local node ids + col_base, so a slab of a
+ * partitioned mesh yields rows of the GLOBAL matrix.  Every element touching
+ * an owned row must be present in d_conn (ghost elements). */
+int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes,
+                       int64_t n_elems, const int32_t* d_conn, int64_t row_begin,
+                       int64_t row_end, int64_t col_base, void* stream,
+                       femx_pattern** out);
+void femx_pattern_destroy(femx_pattern* pat);
+/* n_rows = nd*(row_end-row_begin) dof rows; nnz of the dof-level CSR;
+ * max_row = longest dof row.  Any out pointer may be NULL. */
+int femx_pattern_info(const femx_pattern* pat, int64_t* n_rows, int64_t* nnz,
+                      int64_t* max_row);
+/* Bytes of device memory held by the pattern object (scatter map included). */
+int64_t femx_pattern_bytes(const femx_pattern* pat);
+/* CSR of the dof-level matrix into caller buffers: row_ptr has n_rows+1
+ * entries (give either the 64- or the 32-bit buffer, or both), col_idx nnz. */
+int femx_pattern_export_csr(const femx_pattern* pat, int64_t* d_row_ptr64,
+                            int32_t* d_row_ptr32, int32_t* d_col_idx, void* stream);
+/* The reference's padded layout (fea_symbolic_nvrtc_sparse2.cpp:181-210, 437):
+ * len[i] = row length, idx[i*width + j] = j-th column; entries j >= len[i]
+ * are set to 0 as the reference's host zero-fill does (:644).  nd must be 1.
+ * Fails with FEMX_ERR_INVALID if width < max_row. */
+int femx_pattern_export_ell(const femx_pattern* pat, int width, int32_t* d_len,
+                            int32_t* d_idx, void* stream);
+
+/* The numeric pass.  Replaces fea_kernel (ELL + global atomicAdd variant,
+ * fea_symbolic_nvrtc_sparse2.cpp:475-547): d_values[k] is the sum of all element
+ * contributions to CSR slot k, accumulated in ascending element order by the
+ * one thread that owns the row — no atomics, bitwise reproducible.
+ * d_values has nnz entries of the form's dtype and is fully overwritten. */
+int femx_assemble_csr(femx_form* form, const femx_pattern* pat,
+                      const femx_mesh_view* mesh, void* d_values, void* stream);
+/* CSR values → the reference's ELL value layout A[i*width + j] (zero padded). */
+int femx_csr_to_ell(const femx_pattern* pat, int dtype, int width,
+                    const void* d_values, void* d_ell, void* stream);
+
+/* ------------------------------------------------- validation: SpMV and CG */
+
+/* y = A x for the rows of this pattern; x is indexed by (column - x_base). */
+int femx_spmv(const femx_pattern* pat, int dtype, const void* d_values,
+              const void* d_x, int64_t x_base, void* d_y, void* stream);
+/* Fused vector kernels used by the CG driver (all length n, fp64 partial sums
+ * reduced in a fixed order → deterministic):
+ *   dot2:  out[0] = <a,b>, out[1] = <c,d>                       */
+int femx_dot2(femx_ctx* ctx, int dtype, int64_t n, const void* d_a, const void* d_b,
+              const void* d_c, const void* d_d, double* d_out, void* stream);
+/*   axpy:  y += alpha[0]/alpha[1] * sign * x   (alpha read on device, no host sync) */
+int femx_axpy_ratio(femx_ctx* ctx, int dtype, int64_t n, const double* d_num,
+                    const double* d_den, double sign, const void* d_x, void* d_y,
+                    void* stream);
+/*   xpby:  p = r + (num/den) p */
+int femx_xpby_ratio(femx_ctx* ctx, int dtype, int64_t n, const double* d_num,
+                    const double* d_den, const void* d_r, void* d_p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMX_H */

@@ -1,0 +1,336 @@
+"""GPU tier: the CUDA path through the C ABI against the CPU oracle and the golden
+fixtures.  Pattern / index work must be bit-exact; values within the north-star
+tolerance  ||A - A_ref||_F / ||A_ref||_F <= 1e-12 (fp64), 1e-5 (fp32)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import femx
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-12
+TOL32 = 1e-5
+FORM_IDS = {femx.POISSON: orc.POISSON, femx.POISSON_MASS: orc.POISSON_MASS, femx.MASS: orc.MASS,
+            femx.ELASTICITY: orc.ELASTICITY}
+
+
+def relF(a, b):
+    return np.linalg.norm(np.asarray(a, np.float64) - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def to_dev(a, dtype=None):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def host_mesh_to_dev(dim, conn, coords, dtype=femx.F64):
+    import torch
+    tdt = torch.float64 if dtype == femx.F64 else torch.float32
+    return femx.Mesh(dim, to_dev(conn), tuple(to_dev(c, tdt) for c in coords))
+
+
+# ------------------------------------------------------------------ meshes ---
+def test_device_rectangle_mesh_matches_reference_semantics(ctx):
+    m = ctx.rectangle_mesh(-3.0, 3.0, -3.0, 3.0, 10, 7, flags=True)
+    X, Y, flag, conn = orc.rect_mesh(-3.0, 3.0, -3.0, 3.0, 10, 7)
+    assert np.array_equal(m.conn.cpu().numpy(), conn)
+    assert np.array_equal(m.node_xyz[0].cpu().numpy(), X)
+    assert np.array_equal(m.node_xyz[1].cpu().numpy(), Y)
+    assert np.array_equal(m.flag.cpu().numpy(), flag)
+
+
+def test_device_box_mesh_matches_oracle(ctx):
+    m = ctx.box_mesh(5, 4, 3, hi=(1.0, 2.0, 3.0))
+    X, Y, Z, conn = orc.box_mesh(5, 4, 3, hi=(1.0, 2.0, 3.0))
+    assert np.array_equal(m.conn.cpu().numpy(), conn)
+    for a, b in zip(m.node_xyz, (X, Y, Z)):
+        assert np.array_equal(a.cpu().numpy(), b)
+
+
+# ------------------------------------------------- kernel ABI #1: COO triplets ---
+@pytest.mark.parametrize("case", ["ref_poisson2d_2x2.npz", "ref_poisson2d_4x4.npz", "ref_poisson2d_10x7.npz",
+                                  "ref_poisson2d_jitter12.npz"])
+def test_coo_against_reference_golden(ctx, golden_dir, case):
+    g = np.load(os.path.join(golden_dir, case))
+    mesh = host_mesh_to_dev(2, g["conn"], (g["X"], g["Y"]))
+    form = femx.Form(ctx, 2, femx.POISSON)
+    A, r, c = form.assemble_coo(mesh)
+    assert np.array_equal(r.cpu().numpy(), g["rowA"]) and np.array_equal(c.cpu().numpy(), g["colA"])
+    assert relF(A.cpu().numpy(), g["A"]) <= TOL64
+    # element-expanded coordinates (the reference's X[3e+k] layout)
+    A2, _, _ = form.assemble_coo(mesh.expanded(ctx))
+    assert np.array_equal(A2.cpu().numpy(), A.cpu().numpy())
+    form.close()
+
+
+def test_coo_reference_strings_through_nvrtc(ctx, golden_dir):
+    """The reference's own GiNaC output strings, compiled at run time (operator surface #1)."""
+    j = json.load(open(os.path.join(golden_dir, "ref_integrand_strings.json")))
+    g = np.load(os.path.join(golden_dir, "ref_poisson2d_jitter12.npz"))
+    mesh = host_mesh_to_dev(2, g["conn"], (g["X"], g["Y"]))
+    for fmad in (True, False):  # the reference compiles with --fmad=false
+        form = femx.Form(ctx, 2, entries=j["integrand"], fmad=fmad)
+        A, r, c = form.assemble_coo(mesh)
+        assert relF(A.cpu().numpy(), g["A"]) <= TOL64
+        assert np.array_equal(r.cpu().numpy(), g["rowA"])
+        form.close()
+    # fp32, as the reference runs it: tolerance 1e-5
+    mesh32 = host_mesh_to_dev(2, g["conn"], (g["X"], g["Y"]), femx.F32)
+    form = femx.Form(ctx, 2, entries=j["integrand"], dtype=femx.F32, fmad=False)
+    A, _, _ = form.assemble_coo(mesh32)
+    assert relF(A.cpu().numpy(), g["A"]) <= TOL32
+    form.close()
+
+
+@pytest.mark.parametrize("dim,builtin,nd", [(2, femx.POISSON_MASS, 1), (2, femx.MASS, 1), (3, femx.POISSON, 1),
+                                           (3, femx.POISSON_MASS, 1), (2, femx.ELASTICITY, 2),
+                                           (3, femx.ELASTICITY, 3)])
+def test_coo_builtin_forms(ctx, dim, builtin, nd):
+    rng = np.random.RandomState(12345)
+    params = (0.5769, 0.3846) if builtin == femx.ELASTICITY else (2.5,)
+    if dim == 2:
+        X, Y, _, conn = orc.rect_mesh(0, 1, 0, 2, 9, 6)
+        X = X + rng.uniform(-0.03, 0.03, X.shape)
+        coords = (X, Y)
+        oc = (X, Y, None)
+    else:
+        X, Y, Z, conn = orc.box_mesh(4, 3, 5)
+        Z = Z + rng.uniform(-0.02, 0.02, Z.shape)
+        coords = (X, Y, Z)
+        oc = coords
+    mesh = host_mesh_to_dev(dim, conn, coords)
+    form = femx.Form(ctx, dim, builtin, nd=nd, params=params)
+    A, r, c = form.assemble_coo(mesh)
+    oA, orow, ocol = orc.assemble_coo(FORM_IDS[builtin], dim, nd, conn, *oc, params=params)
+    assert np.array_equal(r.cpu().numpy(), orow) and np.array_equal(c.cpu().numpy(), ocol)
+    assert relF(A.cpu().numpy(), oA) <= TOL64
+    form.close()
+
+
+# ------------------------------------------- kernel ABI #2: pattern + numeric ---
+@pytest.mark.parametrize("case", ["ref_poisson2d_2x2.npz", "ref_poisson2d_4x4.npz", "ref_poisson2d_10x7.npz",
+                                  "ref_poisson2d_jitter12.npz"])
+def test_pattern_and_ell_against_reference_golden(ctx, golden_dir, case):
+    g = np.load(os.path.join(golden_dir, case))
+    mesh = host_mesh_to_dev(2, g["conn"], (g["X"], g["Y"]))
+    pat = femx.Pattern(ctx, mesh)
+    ln, idx = pat.ell(7)
+    assert np.array_equal(ln.cpu().numpy(), g["ell_len"])
+    assert np.array_equal(idx.cpu().numpy(), g["ell_idx"])
+    form = femx.Form(ctx, 2, femx.POISSON)
+    vals = form.assemble_csr(pat, mesh)
+    ell = pat.values_to_ell(vals, 7).cpu().numpy()
+    assert relF(ell, g["ell_val"]) <= TOL64
+    with pytest.raises(femx.FemxError):
+        pat.ell(pat.max_row - 1)
+    form.close(); pat.close()
+
+
+def _csr_case(ctx, dim, builtin, nd, conn, coords, params=(), dtype=femx.F64, tol=TOL64):
+    n = len(coords[0])
+    mesh = host_mesh_to_dev(dim, conn, coords, dtype)
+    pat = femx.Pattern(ctx, mesh, nd=nd)
+    rp, ci = pat.csr("int64")
+    orp, oci = orc.pattern(conn, n)
+    drp, dci = orc.expand_pattern(nd, orp, oci) if nd > 1 else (orp, oci)
+    assert pat.nnz == drp[-1] and pat.n_rows == n * nd
+    assert np.array_equal(rp.cpu().numpy(), drp), "row_ptr not bit-exact"
+    assert np.array_equal(ci.cpu().numpy(), dci), "col_idx not bit-exact"
+    rp32, _ = pat.csr("int32")
+    assert np.array_equal(rp32.cpu().numpy().astype(np.int64), drp)
+    form = femx.Form(ctx, dim, builtin, nd=nd, params=params, dtype=dtype)
+    vals = form.assemble_csr(pat, mesh)
+    oc = coords if dim == 3 else (coords[0], coords[1], None)
+    ov = orc.assemble_csr(FORM_IDS[builtin], dim, nd, conn, *oc, drp, dci, params=params)
+    assert relF(vals.cpu().numpy(), ov) <= tol
+    # bitwise run-to-run determinism
+    vals2 = form.assemble_csr(pat, mesh)
+    assert np.array_equal(vals.cpu().numpy(), vals2.cpu().numpy())
+    # element-expanded coordinate layout gives the same bits
+    vals3 = form.assemble_csr(pat, mesh.expanded(ctx))
+    assert np.array_equal(vals.cpu().numpy(), vals3.cpu().numpy())
+    # SpMV against the oracle
+    x = np.random.RandomState(7).uniform(-1, 1, n * nd)
+    y = pat.spmv(vals, to_dev(x, vals.dtype)).cpu().numpy()
+    assert relF(y, orc.spmv(drp, dci, ov, x)) <= max(tol, 1e-13) * 10
+    form.close(); pat.close()
+
+
+def test_csr_config1_poisson_64x64(ctx):
+    """BASELINE config 1: 2-D P1 Poisson, 64x64 unit square, 8,192 triangles, 29,057 nnz."""
+    X, Y, _, conn = orc.rect_mesh(0, 1, 0, 1, 64, 64)
+    _csr_case(ctx, 2, femx.POISSON, 1, conn, (X, Y))
+
+
+def test_csr_reference_config_1000x100(ctx):
+    """The reference's configured sparse2 run (fea_test_sm_sym_sparse2.cu:16-17, 302): 703,301 nnz."""
+    X, Y, _, conn = orc.rect_mesh(-3, 3, -3, 3, 1000, 100)
+    _csr_case(ctx, 2, femx.POISSON, 1, conn, (X, Y))
+
+
+def test_csr_fp32(ctx):
+    X, Y, _, conn = orc.rect_mesh(-3, 3, -3, 3, 40, 30)
+    _csr_case(ctx, 2, femx.POISSON, 1, conn, (X, Y), dtype=femx.F32, tol=TOL32)
+
+
+@pytest.mark.parametrize("builtin", [femx.POISSON, femx.POISSON_MASS])
+def test_csr_tets(ctx, builtin):
+    X, Y, Z, conn = orc.box_mesh(9, 7, 8)
+    rng = np.random.RandomState(3)
+    X = X + rng.uniform(-0.01, 0.01, X.shape)
+    _csr_case(ctx, 3, builtin, 1, conn, (X, Y, Z), params=(1.0,))
+
+
+def test_csr_elasticity_3d(ctx):
+    X, Y, Z, conn = orc.box_mesh(6, 5, 4)
+    _csr_case(ctx, 3, femx.ELASTICITY, 3, conn, (X, Y, Z), params=(0.5769, 0.3846))
+
+
+def test_csr_elasticity_2d(ctx):
+    X, Y, _, conn = orc.rect_mesh(0, 2, 0, 1, 12, 17)
+    _csr_case(ctx, 2, femx.ELASTICITY, 2, conn, (X, Y), params=(1.2, 0.7))
+
+
+def test_csr_unstructured_shuffled_numbering(ctx):
+    """Random node renumbering + random element order + random local rotations:
+    nothing in the engine may rely on the structured numbering."""
+    rng = np.random.RandomState(12345)
+    X, Y, _, conn = orc.rect_mesh(0, 1, 0, 1, 23, 31)
+    n = len(X)
+    perm = rng.permutation(n)            # new id of old node
+    X2 = np.empty(n); Y2 = np.empty(n)
+    X2[perm] = X; Y2[perm] = Y
+    conn2 = perm[conn].astype(np.int32)
+    conn2 = conn2[rng.permutation(len(conn2))]
+    rot = rng.randint(0, 3, len(conn2))
+    conn2 = np.stack([np.roll(c, k) for c, k in zip(conn2, rot)]).astype(np.int32)
+    # flip a few elements to clockwise: the reference's signed jac gives negated entries
+    conn2[::7] = conn2[::7][:, [0, 2, 1]]
+    _csr_case(ctx, 2, femx.POISSON_MASS, 1, conn2, (X2, Y2))
+
+
+def test_csr_high_valence_fan(ctx):
+    """A fan of 40 triangles around one node: row length 41 (> the structured 7)."""
+    k = 40
+    ang = np.linspace(0, 2 * np.pi, k, endpoint=False)
+    X = np.concatenate([[0.0], np.cos(ang)]); Y = np.concatenate([[0.0], np.sin(ang)])
+    conn = np.array([[0, 1 + i, 1 + (i + 1) % k] for i in range(k)], np.int32)
+    _csr_case(ctx, 2, femx.POISSON, 1, conn, (X, Y))
+
+
+def test_pattern_rejects_bad_connectivity(ctx):
+    conn = np.array([[0, 1, 5]], np.int32)
+    mesh = host_mesh_to_dev(2, conn, (np.zeros(3), np.zeros(3)))
+    with pytest.raises(femx.FemxError) as ei:
+        femx.Pattern(ctx, mesh)
+    assert ei.value.status == 1
+
+
+def test_empty_mesh(ctx):
+    import torch
+    mesh = femx.Mesh(2, torch.empty((0, 3), dtype=torch.int32, device="cuda"),
+                     (torch.zeros(4, dtype=torch.float64, device="cuda"),) * 2)
+    pat = femx.Pattern(ctx, mesh)
+    assert pat.nnz == 0 and pat.n_rows == 4
+    rp, ci = pat.csr("int64")
+    assert rp.cpu().tolist() == [0] * 5
+    form = femx.Form(ctx, 2, femx.POISSON)
+    A, r, c = form.assemble_coo(mesh)
+    assert A.numel() == 0
+    v = form.assemble_csr(pat, mesh)
+    assert v.numel() == 0
+    form.close(); pat.close()
+
+
+def test_form_pattern_mismatch_is_an_error(ctx):
+    m = ctx.rectangle_mesh(0, 1, 0, 1, 4, 4)
+    pat = femx.Pattern(ctx, m)
+    f3 = femx.Form(ctx, 3, femx.POISSON)
+    with pytest.raises(femx.FemxError):
+        f3.assemble_csr(pat, m)
+    f3.close(); pat.close()
+
+
+# --------------------------------------------------- slabs (multi-GPU layout) ---
+@pytest.mark.parametrize("parts", [2, 3])
+def test_slab_rows_concatenate_to_global_matrix_2d(ctx, parts):
+    """Owned-row slabs with ghost elements: concatenation == single-device matrix, bitwise."""
+    import torch
+    nR, nC = 24, 13
+    whole = ctx.rectangle_mesh(0, 1, 0, 1, nR, nC)
+    form = femx.Form(ctx, 2, femx.POISSON_MASS)
+    pw = femx.Pattern(ctx, whole)
+    vw = form.assemble_csr(pw, whole)
+    rpw, ciw = pw.csr("int64")
+    vals, cols, lens = [], [], []
+    bounds = [round(p * (nR + 1) / parts) for p in range(parts + 1)]  # owned node rows
+    for p in range(parts):
+        r0, r1 = bounds[p], bounds[p + 1]          # owned grid rows [r0, r1)
+        lo, hi = max(r0 - 1, 0), min(r1, nR)       # slab incl. ghost rows: node rows [lo, hi]
+        slab = ctx.rectangle_mesh(0, 1, 0, 1, nR, nC, row_lo=lo, row_hi=hi)
+        base = lo * (nC + 1)
+        pat = femx.Pattern(ctx, slab, row_begin=(r0 - lo) * (nC + 1), row_end=(r1 - lo) * (nC + 1), col_base=base)
+        v = form.assemble_csr(pat, slab)
+        rp, ci = pat.csr("int64")
+        vals.append(v); cols.append(ci); lens.append(torch.diff(rp))
+        pat.close()
+    assert torch.equal(torch.cat(lens), torch.diff(rpw))
+    assert torch.equal(torch.cat(cols), ciw)
+    assert torch.equal(torch.cat(vals), vw)
+    form.close(); pw.close()
+
+
+def test_slab_rows_concatenate_to_global_matrix_3d(ctx):
+    import torch
+    n = 6
+    whole = ctx.box_mesh(n, n, n)
+    form = femx.Form(ctx, 3, femx.POISSON_MASS)
+    pw = femx.Pattern(ctx, whole)
+    vw = form.assemble_csr(pw, whole)
+    rpw, ciw = pw.csr("int64")
+    plane = (n + 1) * (n + 1)
+    vals, cols = [], []
+    for (k0, k1) in [(0, 3), (3, 7)]:              # owned node planes [k0, k1)
+        lo, hi = max(k0 - 1, 0), min(k1, n)
+        slab = ctx.box_mesh(n, n, n, k_lo=lo, k_hi=hi)
+        pat = femx.Pattern(ctx, slab, row_begin=(k0 - lo) * plane, row_end=(k1 - lo) * plane, col_base=lo * plane)
+        vals.append(form.assemble_csr(pat, slab)); cols.append(pat.csr("int64")[1])
+        pat.close()
+    assert torch.equal(torch.cat(cols), ciw)
+    assert torch.equal(torch.cat(vals), vw)
+    form.close(); pw.close()
+
+
+# ------------------------------------------- size-independent properties ---
+def test_large_mesh_properties(ctx):
+    """1024x1024 (2.1M elements): closed-form nnz, zero row sums, symmetry via x^T A y = y^T A x,
+    COO and CSR agree (sum of triplets == sum of CSR values), determinism."""
+    import torch
+    n = 1024
+    mesh = ctx.rectangle_mesh(0, 1, 0, 1, n, n)
+    pat = femx.Pattern(ctx, mesh)
+    assert pat.nnz == (n + 1) ** 2 + 2 * (2 * n * (n + 1) + n * n) and pat.max_row == 7
+    form = femx.Form(ctx, 2, femx.POISSON)
+    v = form.assemble_csr(pat, mesh)
+    ones = torch.ones(pat.n_rows, dtype=torch.float64, device="cuda")
+    assert pat.spmv(v, ones).abs().max().item() < 1e-10
+    g = torch.Generator(device="cuda"); g.manual_seed(12345)
+    x = torch.rand(pat.n_rows, dtype=torch.float64, device="cuda", generator=g)
+    y = torch.rand(pat.n_rows, dtype=torch.float64, device="cuda", generator=g)
+    a = torch.dot(x, pat.spmv(v, y)).item(); b = torch.dot(y, pat.spmv(v, x)).item()
+    assert abs(a - b) <= 1e-11 * abs(a)
+    A, r, c = form.assemble_coo(mesh)
+    # scatter the triplets with index_add (order-dependent, so compare with tolerance)
+    rp, ci = pat.csr("int64")
+    dense_rows = torch.zeros(pat.n_rows, dtype=torch.float64, device="cuda")
+    dense_rows.index_add_(0, r.long(), A * x[c.long()])
+    assert (dense_rows - pat.spmv(v, x)).norm().item() <= 1e-12 * dense_rows.norm().item()
+    assert torch.equal(v, form.assemble_csr(pat, mesh))
+    form.close(); pat.close()
