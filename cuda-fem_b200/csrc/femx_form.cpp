@@ -17,6 +17,7 @@ struct Variant {
   CUmodule module = nullptr;
   CUfunction fn = nullptr;
   int smem_set = 0;
+  int carveout_set = 0;
 };
 
 std::string num(double v) {
@@ -35,6 +36,7 @@ struct femx_form {
   femx_ctx* ctx = nullptr;
   int dim = 2, nn = 3, nd = 1, dtype = FEMX_F64, builtin = 0, fmad = 1;
   int n = 3;  // nn*nd
+  int integrated = 0;  // entries are final element-matrix expressions (no quadrature applied)
   std::string prologue;
   std::vector<std::string> entries;  // n*n
   int nq = 0;
@@ -54,84 +56,98 @@ namespace {
 // phi = (r, s, 1-r-s); entries are a(u=phi_lj, v=phi_li)*jac (:337, Q6).
 // Unlike GiNaC's fully expanded strings the common sub-expressions live in a
 // prologue evaluated once per element.
+// The emitter pre-integrates: for P1 simplices the Jacobian is constant, so
+//   sum_q w_q (grad phi_b . grad phi_a) jac = (d_b . d_a) * (W / jac),   W = sum_q w_q,
+//   sum_q w_q  phi_b phi_a jac             = M_ab * jac,                 M_ab = sum_q w_q phi_a phi_b
+// with d_a = jac * grad phi_a (no division) and W, M_ab folded on the host from the
+// SAME quadrature rule (the reference's 8-digit literals in 2-D), so the values
+// equal the reference's quadrature sums up to rounding.
 void emit_geometry(int dim, std::string* pro) {
   std::ostringstream o;
   if (dim == 2) {
-    o << "const real jac = (x1-x3)*(y2-y3)-(y1-y3)*(x2-x3);\n"
-         "  const real ijac = real(1.0)/jac;\n"
-         "  const real g1x = (y2-y3)*ijac, g1y = (x3-x2)*ijac;\n"
-         "  const real g2x = (y3-y1)*ijac, g2y = (x1-x3)*ijac;\n"
-         "  const real g3x = -(g1x+g2x), g3y = -(g1y+g2y);\n";
+    o << "const real d1x = y2-y3, d1y = x3-x2;\n"
+         "  const real d2x = y3-y1, d2y = x1-x3;\n"
+         "  const real d3x = -(d1x+d2x), d3y = -(d1y+d2y);\n"
+         "  const real jac = d2y*d1x-d2x*d1y;\n"   // (x1-x3)(y2-y3)-(y1-y3)(x2-x3)
+         "  const real ijac = real(1.0)/jac;\n";
   } else {
-    // X = x1 r + x2 s + x3 t + x4 (1-r-s-t); J[c][a] = dX_c/dref_a; grads = rows of J^-1
+    // X = x1 r + x2 s + x3 t + x4 (1-r-s-t); J[c][a] = dX_c/dref_a; d_a = jac * (row a of J^-1)
     o << "const real j00 = x1-x4, j01 = x2-x4, j02 = x3-x4;\n"
          "  const real j10 = y1-y4, j11 = y2-y4, j12 = y3-y4;\n"
          "  const real j20 = z1-z4, j21 = z2-z4, j22 = z3-z4;\n"
-         "  const real c00 = j11*j22-j12*j21, c01 = j12*j20-j10*j22, c02 = j10*j21-j11*j20;\n"
-         "  const real jac = j00*c00+j01*c01+j02*c02;\n"
-         "  const real ijac = real(1.0)/jac;\n"
-         "  const real g1x = c00*ijac, g1y = (j02*j21-j01*j22)*ijac, g1z = (j01*j12-j02*j11)*ijac;\n"
-         "  const real g2x = c01*ijac, g2y = (j00*j22-j02*j20)*ijac, g2z = (j02*j10-j00*j12)*ijac;\n"
-         "  const real g3x = c02*ijac, g3y = (j01*j20-j00*j21)*ijac, g3z = (j00*j11-j01*j10)*ijac;\n"
-         "  const real g4x = -(g1x+g2x+g3x), g4y = -(g1y+g2y+g3y), g4z = -(g1z+g2z+g3z);\n";
+         "  const real d1x = j11*j22-j12*j21, d1y = j02*j21-j01*j22, d1z = j01*j12-j02*j11;\n"
+         "  const real d2x = j12*j20-j10*j22, d2y = j00*j22-j02*j20, d2z = j02*j10-j00*j12;\n"
+         "  const real d3x = j10*j21-j11*j20, d3y = j01*j20-j00*j21, d3z = j00*j11-j01*j10;\n"
+         "  const real d4x = -(d1x+d2x+d3x), d4y = -(d1y+d2y+d3y), d4z = -(d1z+d2z+d3z);\n"
+         "  const real jac = j00*d1x+j01*d2x+j02*d3x;\n"
+         "  const real ijac = real(1.0)/jac;\n";
   }
   *pro += o.str();
 }
 
-std::string phi(int dim, int a) {
-  if (a == 0) return "r";
-  if (a == 1) return "s";
-  if (dim == 2) return "(real(1.0)-r-s)";
-  if (a == 2) return "t";
-  return "(real(1.0)-r-s-t)";
-}
-
-std::string gg(int dim, int a, int b) {  // grad phi_a . grad phi_b (1-based names)
+std::string dd(int dim, int a, int b) {  // d_a . d_b (1-based names)
   std::ostringstream o;
   o << "(";
   for (int k = 0; k < dim; ++k) {
     if (k) o << "+";
-    o << "g" << a + 1 << AX[k] << "*g" << b + 1 << AX[k];
+    o << "d" << a + 1 << AX[k] << "*d" << b + 1 << AX[k];
   }
   o << ")";
   return o.str();
 }
 
+double phi_at(const femx_form* f, int a, int q) {
+  if (a == 0) return f->qr[q];
+  if (a == 1) return f->qs[q];
+  if (f->dim == 2) return 1.0 - f->qr[q] - f->qs[q];
+  if (a == 2) return f->qt[q];
+  return 1.0 - f->qr[q] - f->qs[q] - f->qt[q];
+}
+
 int emit_builtin(femx_form* f, const femx_form_desc* d) {
   const int dim = f->dim, nn = f->nn, nd = f->nd, n = f->n;
   emit_geometry(dim, &f->prologue);
+  f->integrated = 1;
   f->entries.assign((size_t)n * n, "");
+  double W = 0.0;
+  for (int q = 0; q < f->nq; ++q) W += f->qw[q];
+  double M[4][4];
+  for (int a = 0; a < nn; ++a)
+    for (int b = 0; b < nn; ++b) {
+      double m = 0.0;
+      for (int q = 0; q < f->nq; ++q) m += f->qw[q] * (phi_at(f, b, q) * phi_at(f, a, q));
+      M[a][b] = m;
+    }
+  std::ostringstream pro;
+  pro << "  const real kq = " << num(W) << "*ijac;\n";
   if (d->builtin == FEMX_FORM_ELASTICITY) {
     if (nd != dim) return FEMX_ERR_INVALID;
-    std::ostringstream o;
     for (int a = 0; a < nn; ++a)
       for (int b = a; b < nn; ++b)
-        o << "  const real gg" << a + 1 << b + 1 << " = " << gg(dim, a, b) << ";\n";
-    o << "  const real LAM = " << num(d->params[0]) << ", MU = " << num(d->params[1]) << ";\n";
-    f->prologue += o.str();
+        pro << "  const real dd" << a + 1 << b + 1 << " = " << dd(dim, a, b) << ";\n";
+    pro << "  const real LAMq = " << num(d->params[0]) << "*kq, MUq = " << num(d->params[1]) << "*kq;\n";
   }
+  f->prologue += pro.str();
   double cm = d->params[0] != 0.0 ? d->params[0] : 1.0;
   for (int li = 0; li < n; ++li)
     for (int lj = 0; lj < n; ++lj) {
-      const int a = li / nd, c = li % nd, b = lj / nd, dd = lj % nd;
+      const int a = li / nd, c = li % nd, b = lj / nd, e = lj % nd;
       std::ostringstream o;
       switch (d->builtin) {
         case FEMX_FORM_POISSON:
-          o << gg(dim, b, a) << "*jac";
+          o << dd(dim, b, a) << "*kq";
           break;
         case FEMX_FORM_POISSON_MASS:
-          o << "(" << gg(dim, b, a) << "+";
-          if (cm != 1.0) o << num(cm) << "*";
-          o << phi(dim, b) << "*" << phi(dim, a) << ")*jac";
+          o << dd(dim, b, a) << "*kq+" << num(cm * M[a][b]) << "*jac";
           break;
         case FEMX_FORM_MASS:
-          o << "(" << phi(dim, b) << "*" << phi(dim, a) << ")*jac";
+          o << num(M[a][b]) << "*jac";
           break;
         case FEMX_FORM_ELASTICITY: {
           const int lo = a < b ? a : b, hi = a < b ? b : a;
-          o << "(LAM*g" << a + 1 << AX[c] << "*g" << b + 1 << AX[dd] << "+MU*(";
-          if (c == dd) o << "gg" << lo + 1 << hi + 1 << "+";
-          o << "g" << a + 1 << AX[dd] << "*g" << b + 1 << AX[c] << "))*jac";
+          o << "LAMq*(d" << a + 1 << AX[c] << "*d" << b + 1 << AX[e] << ")+MUq*(";
+          if (c == e) o << "dd" << lo + 1 << hi + 1 << "+";
+          o << "d" << a + 1 << AX[e] << "*d" << b + 1 << AX[c] << ")";
           break;
         }
         default:
@@ -171,34 +187,78 @@ void default_rule(femx_form* f) {
   }
 }
 
-// One macro per matrix row: FEMX_ROW_<li>(R,S,T,U,W) adds one quadrature point.
-std::string build_defines(const femx_form* f) {
+// Does a C expression mention the quadrature point (identifiers r, s, t, u)?
+bool depends_on_q(const std::string& e) {
+  size_t i = 0;
+  while (i < e.size()) {
+    unsigned char ch = (unsigned char)e[i];
+    if (isalpha(ch) || ch == '_') {
+      size_t j = i;
+      while (j < e.size() && (isalnum((unsigned char)e[j]) || e[j] == '_')) ++j;
+      std::string id = e.substr(i, j - i);
+      if (id == "r" || id == "s" || id == "t" || id == "u") return true;
+      i = j;
+    } else if (isdigit(ch) || (ch == '.' && i + 1 < e.size() && isdigit((unsigned char)e[i + 1]))) {
+      // skip a numeric literal incl. exponent / suffix so that "1.0f" or "2e3" is not an identifier
+      size_t j = i;
+      while (j < e.size() && (isalnum((unsigned char)e[j]) || e[j] == '.' ||
+                              ((e[j] == '+' || e[j] == '-') && (e[j - 1] == 'e' || e[j - 1] == 'E'))))
+        ++j;
+      i = j;
+    } else {
+      ++i;
+    }
+  }
+  return false;
+}
+
+// Per matrix row li:
+//   FEMX_ROWC_<li>              entries that do not depend on the quadrature point:
+//                               out[lj] = E (pre-integrated) or out[lj] = (sum_q w_q) * E
+//   FEMX_ROWQ_<li>(R,S,T,U,W)   one quadrature-point update of the entries that do
+std::string build_defines(const femx_form* f, const std::string& kernel) {
   std::ostringstream o;
   const int n = f->n;
   o << "#define FEMX_REAL " << (f->dtype == FEMX_F32 ? "float" : "double") << "\n";
   o << "#define NN " << f->nn << "\n#define ND " << f->nd << "\n#define DIM " << f->dim
     << "\n#define FEMX_TILE_NODES " << femx_tile_nodes_for(f->nd) << "\n";
-  std::string pro = f->prologue;
-  // a multi-line prologue becomes one macro body
+  o << "#define FEMX_EXPANDED " << (kernel == "csr_x" ? 1 : 0) << "\n";
+  o << "#define FEMX_UNIT_STRIDE " << (kernel == "csr" ? 1 : 0) << "\n";
   std::string esc;
-  for (char ch : pro) {
+  for (char ch : f->prologue) {
     if (ch == '\n') esc += " \\\n"; else esc += ch;
   }
   o << "#define FEMX_PROLOGUE " << esc << "\n";
+  double W = 0.0;
+  for (int q = 0; q < f->nq; ++q) W += f->qw[q];
+  std::vector<int> has_q(n, 0);
   for (int li = 0; li < n; ++li) {
-    o << "#define FEMX_ROW_" << li << "(R,S,T,U,W) { const real r = (R), s = (S), t = (T), u = (U), w = (W); "
-         "(void)r; (void)s; (void)t; (void)u;";
-    for (int lj = 0; lj < n; ++lj)
-      o << " \\\n    out[" << lj << "] += w*(" << f->entries[(size_t)li * n + lj] << ");";
-    o << " }\n";
+    std::ostringstream c, qd;
+    for (int lj = 0; lj < n; ++lj) {
+      const std::string& e = f->entries[(size_t)li * n + lj];
+      if (f->integrated)
+        c << " \\\n    out[" << lj << "] = (" << e << ");";
+      else if (!depends_on_q(e))
+        c << " \\\n    out[" << lj << "] = " << num(W) << "*(" << e << ");";
+      else {
+        qd << " \\\n    out[" << lj << "] += w*(" << e << ");";
+        has_q[li] = 1;
+      }
+    }
+    o << "#define FEMX_ROWC_" << li << c.str() << "\n";
+    o << "#define FEMX_ROWQ_" << li << "(R,S,T,U,W) { const real r = (R), s = (S), t = (T), u = (U), w = (W); "
+         "(void)r; (void)s; (void)t; (void)u; (void)w;" << qd.str() << " }\n";
   }
   o << "#define FEMX_QUAD(M)";
   for (int q = 0; q < f->nq; ++q)
     o << " \\\n    M(" << num(f->qr[q]) << "," << num(f->qs[q]) << "," << num(f->qt[q]) << ","
       << num(f->qu[q]) << "," << num(f->qw[q]) << ")";
   o << "\n#define FEMX_ROW_CASES";
-  for (int li = 0; li < n; ++li)
-    o << " \\\n    case " << li << ": FEMX_QUAD(FEMX_ROW_" << li << ") break;";
+  for (int li = 0; li < n; ++li) {
+    o << " \\\n    case " << li << ": FEMX_ROWC_" << li;
+    if (has_q[li]) o << " FEMX_QUAD(FEMX_ROWQ_" << li << ")";
+    o << " break;";
+  }
   o << "\n";
   return o.str();
 }
@@ -208,19 +268,21 @@ int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, boo
   if (it == f->variants.end()) {
     Variant v;
     const char* body = nullptr;
-    const char* entry = nullptr;
-    if (kernel == "coo") { body = kFemxJitCoo; entry = "femx_coo"; }
-    else if (kernel == "csr") { body = kFemxJitCsr; entry = "femx_csr"; }
+    if (kernel == "coo") body = kFemxJitCoo;
+    else if (kernel == "csr" || kernel == "csr_x" || kernel == "csr_s") body = kFemxJitCsr;
     else return femx_fail(f->ctx, FEMX_ERR_INVALID, "unknown kernel variant '%s'", kernel.c_str());
-    (void)entry;
-    v.source = "// femx JIT kernel '" + kernel + "' (generated)\n" + build_defines(f) +
+    v.source = "// femx JIT kernel '" + kernel + "' (generated)\n" + build_defines(f, kernel) +
                kFemxJitCommon + body;
     nvrtcProgram prog;
     std::string fname = "femx_" + kernel + ".cu";
+    if (const char* dump = getenv("FEMX_JIT_DUMP")) {  // keep the source on disk (ncu --import-source)
+      fname = std::string(dump) + "/" + fname;
+      if (FILE* fp = fopen(fname.c_str(), "w")) { fwrite(v.source.data(), 1, v.source.size(), fp); fclose(fp); }
+    }
     nvrtcResult r = nvrtcCreateProgram(&prog, v.source.c_str(), fname.c_str(), 0, nullptr, nullptr);
     if (r != NVRTC_SUCCESS)
       return femx_fail(f->ctx, FEMX_ERR_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
-    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--diag-suppress=550", "--diag-suppress=177",
                                      f->fmad ? "--fmad=true" : "--fmad=false"};
     r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
     size_t ls = 0;
@@ -259,7 +321,7 @@ int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, boo
       drv->GetErrorString(cr, &es);
       return femx_fail(f->ctx, FEMX_ERR_CUDA, "cuModuleLoadData: %s", es ? es : "?");
     }
-    std::string entry = "femx_" + kernel;
+    std::string entry = kernel == "coo" ? "femx_coo" : "femx_csr";
     cr = drv->ModuleGetFunction(&v.fn, v.module, entry.c_str());
     if (cr != CUDA_SUCCESS) {
       drv->GetErrorString(cr, &es);
@@ -287,6 +349,29 @@ int make_form(femx_ctx* ctx, const femx_form_desc* d, femx_form** out) {
   f->dim = d->dim; f->nn = d->nn; f->nd = d->nd; f->dtype = d->dtype;
   f->builtin = d->builtin; f->fmad = d->fmad ? 1 : 0;
   f->n = d->nn * d->nd;
+  f->integrated = d->integrated ? 1 : 0;
+  if (d->nq > 0) {
+    if (!d->qw || !d->qr || !d->qs || (d->dim == 3 && !d->qt)) {
+      delete f;
+      return femx_fail(ctx, FEMX_ERR_INVALID, "femx_form_compile: incomplete quadrature rule");
+    }
+    f->nq = d->nq;
+    f->qw.assign(d->qw, d->qw + d->nq);
+    f->qr.assign(d->qr, d->qr + d->nq);
+    f->qs.assign(d->qs, d->qs + d->nq);
+    f->qt.resize(d->nq);
+    f->qu.assign(d->nq, 0.0);
+    for (int q = 0; q < d->nq; ++q) {
+      if (d->dim == 2) {
+        f->qt[q] = d->qt ? d->qt[q] : 1.0 - d->qr[q] - d->qs[q];
+      } else {
+        f->qt[q] = d->qt[q];
+        f->qu[q] = d->qu ? d->qu[q] : 1.0 - d->qr[q] - d->qs[q] - d->qt[q];
+      }
+    }
+  } else {
+    default_rule(f);
+  }
   if (d->builtin == FEMX_FORM_CUSTOM) {
     if (!d->entries) {
       delete f;
@@ -313,28 +398,6 @@ int make_form(femx_ctx* ctx, const femx_form_desc* d, femx_form** out) {
       return femx_fail(ctx, st, "femx_form_compile: bad built-in form %d (nd=%d, dim=%d)",
                        d->builtin, d->nd, d->dim);
     }
-  }
-  if (d->nq > 0) {
-    if (!d->qw || !d->qr || !d->qs || (d->dim == 3 && !d->qt)) {
-      delete f;
-      return femx_fail(ctx, FEMX_ERR_INVALID, "femx_form_compile: incomplete quadrature rule");
-    }
-    f->nq = d->nq;
-    f->qw.assign(d->qw, d->qw + d->nq);
-    f->qr.assign(d->qr, d->qr + d->nq);
-    f->qs.assign(d->qs, d->qs + d->nq);
-    f->qt.resize(d->nq);
-    f->qu.assign(d->nq, 0.0);
-    for (int q = 0; q < d->nq; ++q) {
-      if (d->dim == 2) {
-        f->qt[q] = d->qt ? d->qt[q] : 1.0 - d->qr[q] - d->qs[q];
-      } else {
-        f->qt[q] = d->qt[q];
-        f->qu[q] = d->qu ? d->qu[q] : 1.0 - d->qr[q] - d->qs[q] - d->qt[q];
-      }
-    }
-  } else {
-    default_rule(f);
   }
   int st = compile_variant(f, "coo", nullptr, ctx != nullptr);
   if (st != FEMX_OK) {
@@ -409,9 +472,9 @@ int femx_assemble_coo(femx_form* form, const femx_mesh_view* mesh, void* d_A, in
   bool expanded = false;
   int st = check_mesh(form, mesh, &expanded);
   if (st != FEMX_OK) return st;
+  if (mesh->n_elems == 0) return FEMX_OK;
   if (!mesh->d_conn && (!expanded || d_rowA || d_colA))
     return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_coo: connectivity is NULL");
-  if (mesh->n_elems == 0) return FEMX_OK;
   Variant* v = nullptr;
   st = compile_variant(form, "coo", &v, true);
   if (st != FEMX_OK) return st;
@@ -450,17 +513,24 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
     return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_csr: mesh sizes differ from the pattern's");
   if (!d_values && pat->nnz_node > 0)
     return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_csr: d_values is NULL");
-  if (pat->n_rows == 0) return FEMX_OK;
+  if (pat->n_rows == 0 || pat->nnz_node == 0) return FEMX_OK;
+  long long cs = mesh->node_stride ? mesh->node_stride : 1;
   Variant* v = nullptr;
-  st = compile_variant(form, "csr", &v, true);
+  st = compile_variant(form, expanded ? "csr_x" : (cs == 1 ? "csr" : "csr_s"), &v, true);
   if (st != FEMX_OK) return st;
   const femx_driver* drv = femx_get_driver(nullptr);
   const size_t rs = form->dtype == FEMX_F32 ? 4 : 8;
-  size_t smem = (size_t)pat->max_tile_nnz * form->nd * form->nd * rs;
+  size_t smem = (size_t)pat->max_tile_nnz * (form->nd * form->nd * rs + 4) + (size_t)pat->max_tile_codes * 4;
   if (smem > form->ctx->smem_optin)
     return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED,
                      "femx_assemble_csr: a %d-row tile needs %zu B of shared memory (> %zu)",
                      pat->tile_nodes, smem, form->ctx->smem_optin);
+  if (!v->carveout_set) {
+    // prefer shared memory over L1 up to what full occupancy needs (experiment knob: FEMX_CARVEOUT=percent)
+    if (const char* cv = getenv("FEMX_CARVEOUT"))
+      drv->FuncSetAttribute(v->fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, atoi(cv));
+    v->carveout_set = 1;
+  }
   if ((int)smem > v->smem_set && smem > 48 * 1024) {
     CUresult cr = drv->FuncSetAttribute(v->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
     if (cr != CUDA_SUCCESS) return femx_fail(form->ctx, FEMX_ERR_CUDA, "cuFuncSetAttribute(smem=%zu) failed", smem);
@@ -468,15 +538,14 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   }
   const void* const* c = expanded ? mesh->d_elem_xyz : mesh->d_node_xyz;
   const void* X = c[0]; const void* Y = c[1]; const void* Z = c[2];
-  long long cs = mesh->node_stride ? mesh->node_stride : 1;
-  int ex = expanded ? 1 : 0;
   int n_rows = (int)pat->n_rows;
   int col_base = (int)pat->col_base;
   const int2* rowinfo = pat->d_rowinfo;
   const int32_t* col = pat->d_col_idx;
-  const uint32_t* code = pat->d_pair_code;
-  const int32_t* pelem = pat->d_pair_elem;
-  void* args[] = {&rowinfo, &col, &code, &pelem, &X, &Y, &Z, &cs, &ex, &d_values, &n_rows, &col_base};
+  const int32_t* slice_ptr = pat->d_slice_ptr;
+  const uint32_t* code = pat->d_sell_code;
+  const int32_t* pelem = pat->d_sell_elem;
+  void* args[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &n_rows, &col_base};
   unsigned blocks = (unsigned)((pat->n_rows + pat->tile_nodes - 1) / pat->tile_nodes);
   unsigned threads = (unsigned)(pat->tile_nodes * form->nd);
   CUresult cr = drv->LaunchKernel(v->fn, blocks, 1, 1, threads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);

@@ -59,10 +59,15 @@ struct femx_pattern {
   int max_row = 0;       // longest node-level row
   int tile_nodes = 0;    // node rows per CTA in the numeric pass
   int64_t max_tile_nnz = 0;
-  int2* d_rowinfo = nullptr;       // [n_rows+1] {row_ptr, pair_ptr}
+  int64_t max_tile_codes = 0;  // most padded incidences (SELL entries) in one tile
+  int2* d_rowinfo = nullptr;       // [n_rows+1] {row_ptr, number of incidences}
   int32_t* d_col_idx = nullptr;    // [nnz_node] local node id + col_base, ascending per row
-  uint32_t* d_pair_code = nullptr; // [n_pairs] 7-bit row positions of the element's nodes | li<<28
-  int32_t* d_pair_elem = nullptr;  // [n_pairs] e*nn + li, ascending per row
+  // SELL-32 scatter map: slice s = rows [32s, 32s+32); incidence `it` of row r sits at
+  // slice_ptr[s] + 32*it + r%32 (rows padded to the slice's longest incidence list)
+  int32_t* d_slice_ptr = nullptr;  // [n_slices+1]
+  uint32_t* d_sell_code = nullptr; // 7-bit row positions of the element's nodes | li<<28
+  int32_t* d_sell_elem = nullptr;  // e*nn + li, ascending element order per row
+  int64_t n_sell = 0;              // padded incidence count
   int64_t bytes = 0;
 };
 

@@ -102,71 +102,171 @@ femx_coo(const int* __restrict__ conn, const real* __restrict__ X,
 // reproducible (replaces the linear search + global atomicAdd of
 // fea_symbolic_nvrtc_sparse2.cpp:533-544).
 //
-// Scatter map: pair_code[k] holds, for incidence k of the row, the positions
-// (7 bits each) of the element's NN nodes inside the row's sorted column list
-// and the local index li (bits 28-29).  The node ids themselves come from the
-// column list, so connectivity is not re-read.
+// Scatter map (built once by the symbolic pass): for incidence `it` of a row,
+// code = positions (7 bits each) of the element's NN nodes inside the row's
+// sorted column list | li << 28.  Codes are stored SELL-32: slice s = rows
+// [32s, 32s+32), entry (row, it) at slice_ptr[s] + 32*it + row%32, so a warp
+// reads one contiguous 128-byte line per incidence.  Node ids come from the
+// tile's column list staged in shared memory, so connectivity is not re-read.
 static const char* const kFemxJitCsr = R"FEMX(
+// predicated read-only global load (keeps the gathers of the software pipeline
+// branch-free so that they are issued before the current incidence is evaluated)
+__device__ __forceinline__ void femx_ldg_if(double& v, const double* p, int pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.f64 %0, [%1];\n\t}"
+               : "+d"(v) : "l"(p), "r"(pred));
+}
+__device__ __forceinline__ void femx_ldg_if(float& v, const float* p, int pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.f32 %0, [%1];\n\t}"
+               : "+f"(v) : "l"(p), "r"(pred));
+}
+#if FEMX_UNIT_STRIDE
+#define FEMX_CS 1
+#else
+#define FEMX_CS cs
+#endif
+
 extern "C" __global__ void __launch_bounds__(FEMX_TILE_NODES * ND)
-femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx,
-         const unsigned* __restrict__ pair_code, const int* __restrict__ pair_elem,
-         const real* __restrict__ X, const real* __restrict__ Y,
-         const real* __restrict__ Z, const i64 cs, const int expanded,
+femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
+         const int* __restrict__ col_idx, const unsigned* __restrict__ sell_code,
+         const int* __restrict__ sell_elem, const real* __restrict__ X,
+         const real* __restrict__ Y, const real* __restrict__ Z, const i64 cs,
          real* __restrict__ vals, const int n_rows, const int col_base) {
-  extern __shared__ __align__(16) unsigned char femx_smem[];
-  real* s_vals = reinterpret_cast<real*>(femx_smem);
+  extern __shared__ __align__(128) unsigned char femx_smem[];
   const int i0 = blockIdx.x * FEMX_TILE_NODES;
   const int nt = min(FEMX_TILE_NODES, n_rows - i0);
   const int base = __ldg(&rowinfo[i0].x);
-  const int cnt = (__ldg(&rowinfo[i0 + nt].x) - base) * (ND * ND);
+  const int cntn = __ldg(&rowinfo[i0 + nt].x) - base;  // node-level nonzeros of the tile
+  const int cnt = cntn * (ND * ND);
+  const int sbase = __ldg(slice_ptr + (i0 >> 5));      // the tile's slices are contiguous
+  const int ncode = __ldg(slice_ptr + ((i0 + nt + 31) >> 5)) - sbase;
+  // smem: [codes | values | columns]; codes first so that 16-byte async copies are aligned
+  unsigned* s_code = reinterpret_cast<unsigned*>(femx_smem);
+  real* s_vals = reinterpret_cast<real*>(s_code + ncode);
+  int* s_cols = reinterpret_cast<int*>(s_vals + cnt);
+  // Stage the tile's streamed inputs (scatter codes, column list) with asynchronous
+  // global->shared copies: every copy of the tile is in flight at once, no register
+  // staging, one memory latency per tile instead of one per loop trip.
+  {
+    const unsigned sdst = (unsigned)__cvta_generic_to_shared(s_code);
+    const unsigned* gsrc = sell_code + sbase;  // 128-byte aligned (slices are 32-entry multiples)
+    for (int j = threadIdx.x * 4; j < ncode; j += blockDim.x * 4)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + j * 4), "l"(gsrc + j) : "memory");
+    const unsigned cdst = (unsigned)__cvta_generic_to_shared(s_cols);
+    const int* csrc = col_idx + base;
+    for (int j = threadIdx.x; j < cntn; j += blockDim.x)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cdst + j * 4), "l"(csrc + j) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (int j = threadIdx.x; j < cnt; j += blockDim.x) s_vals[j] = real(0);
+  // column ids are local node id + col_base: fold the offset into the coordinate bases
+#if !FEMX_EXPANDED
+  X -= (i64)col_base * FEMX_CS;
+  Y -= (i64)col_base * FEMX_CS;
+  if (DIM == 3) Z -= (i64)col_base * FEMX_CS;
+#endif
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   const int ln = threadIdx.x / ND;
   const int c = threadIdx.x - ln * ND;
   if (ln < nt) {
-    const int2 r0 = __ldg(&rowinfo[i0 + ln]);
-    const int2 r1 = __ldg(&rowinfo[i0 + ln + 1]);
-    const int rlen = r1.x - r0.x;
-    real* srow = s_vals + (r0.x - base) * (ND * ND) + c * rlen * ND;
-    const int* cols = col_idx + r0.x;
-    for (int k = r0.y; k < r1.y; ++k) {
-      const unsigned code = __ldg(pair_code + k);
-      int pos[NN];
-#pragma unroll
-      for (int a = 0; a < NN; ++a) pos[a] = (code >> (7 * a)) & 127;
-      const int li = (code >> 28) & 3;
+    const int row = i0 + ln;
+    const int2 r0 = __ldg(&rowinfo[row]);
+    const int rlen = __ldg(&rowinfo[row + 1].x) - r0.x;
+    const int off = r0.x - base;
+    real* srow = s_vals + off * (ND * ND) + c * rlen * ND;
+    const int* scol = s_cols + off;
+    const int sp = __ldg(slice_ptr + (row >> 5)) + (row & 31);
+    const unsigned* sc = s_code + (sp - sbase);
+    const int np = r0.y;
+    if (np > 0) {
+      unsigned code = sc[0];
+#if FEMX_EXPANDED
+      // element-expanded coordinates X[NN*e + a] (the reference's layout): plain pipelined loads
+      const int* pelem = sell_elem + sp;
       real cx[NN], cy[NN], cz[NN];
-      if (expanded) {
-        const i64 e = __ldg(pair_elem + k) / NN;
+      {
+        const i64 p0 = (i64)(__ldg(pelem) / NN) * NN;
 #pragma unroll
         for (int a = 0; a < NN; ++a) {
-          cx[a] = __ldg(X + e * NN + a);
-          cy[a] = __ldg(Y + e * NN + a);
-#if DIM == 3
-          cz[a] = __ldg(Z + e * NN + a);
-#else
-          cz[a] = real(0);
-#endif
-        }
-      } else {
-#pragma unroll
-        for (int a = 0; a < NN; ++a) {
-          const i64 p = (i64)(__ldg(cols + pos[a]) - col_base) * cs;
-          cx[a] = __ldg(X + p);
-          cy[a] = __ldg(Y + p);
-#if DIM == 3
-          cz[a] = __ldg(Z + p);
-#else
-          cz[a] = real(0);
-#endif
+          cx[a] = __ldg(X + p0 + a); cy[a] = __ldg(Y + p0 + a);
+          cz[a] = DIM == 3 ? __ldg(Z + p0 + a) : real(0);
         }
       }
-      real out[NDOF];
-      femx_row(li * ND + c, cx, cy, cz, out);
+#else
+      // the row's own node is a vertex of every incident element: keep it in registers
+      const int self_pos = (code >> (7 * ((code >> 28) & 3))) & 127;
+      const i64 pself = (i64)scol[self_pos] * FEMX_CS;
+      const real xs = __ldg(X + pself), ys = __ldg(Y + pself), zs = DIM == 3 ? __ldg(Z + pself) : real(0);
+      real cx[NN], cy[NN], cz[NN];
+      {
+        const int li = (code >> 28) & 3;
 #pragma unroll
-      for (int a = 0; a < NN; ++a)
+        for (int a = 0; a < NN; ++a) {
+          const i64 p = (i64)scol[(code >> (7 * a)) & 127] * FEMX_CS;
+          cx[a] = xs; cy[a] = ys; cz[a] = zs;
+          femx_ldg_if(cx[a], X + p, a != li);
+          femx_ldg_if(cy[a], Y + p, a != li);
+          if (DIM == 3) femx_ldg_if(cz[a], Z + p, a != li);
+        }
+      }
+#endif
+      real dacc[ND];  // the diagonal block row (self column) accumulates in registers
 #pragma unroll
-        for (int d = 0; d < ND; ++d) srow[pos[a] * ND + d] += out[a * ND + d];
+      for (int d = 0; d < ND; ++d) dacc[d] = real(0);
+      for (int it = 0; it < np; ++it) {
+        // ---- software pipeline: gathers of incidence it+1 are issued first
+        const int more = it + 1 < np;
+        const unsigned ncd = sc[(it + more) * 32];
+        real nx[NN], ny[NN], nz[NN];
+#if FEMX_EXPANDED
+        {
+          const i64 p0 = (i64)(__ldg(pelem + (it + more) * 32) / NN) * NN;
+#pragma unroll
+          for (int a = 0; a < NN; ++a) {
+            nx[a] = cx[a]; ny[a] = cy[a]; nz[a] = cz[a];
+            femx_ldg_if(nx[a], X + p0 + a, more);
+            femx_ldg_if(ny[a], Y + p0 + a, more);
+            if (DIM == 3) femx_ldg_if(nz[a], Z + p0 + a, more);
+          }
+        }
+#else
+        {
+          const int nli = (ncd >> 28) & 3;
+#pragma unroll
+          for (int a = 0; a < NN; ++a) {
+            const i64 p = (i64)scol[(ncd >> (7 * a)) & 127] * FEMX_CS;
+            const int pr = more & (a != nli);
+            nx[a] = xs; ny[a] = ys; nz[a] = zs;
+            femx_ldg_if(nx[a], X + p, pr);
+            femx_ldg_if(ny[a], Y + p, pr);
+            if (DIM == 3) femx_ldg_if(nz[a], Z + p, pr);
+          }
+        }
+#endif
+        // ---- evaluate incidence it
+        const int li = (code >> 28) & 3;
+        real out[NDOF];
+        femx_row(li * ND + c, cx, cy, cz, out);
+#pragma unroll
+        for (int a = 0; a < NN; ++a) {
+          if (a == li) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) dacc[d] += out[a * ND + d];
+          } else {
+            const int pa = ((code >> (7 * a)) & 127) * ND;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) srow[pa + d] += out[a * ND + d];
+          }
+        }
+        if (!more) {
+          const int pa = ((code >> (7 * li)) & 127) * ND;
+#pragma unroll
+          for (int d = 0; d < ND; ++d) srow[pa + d] = dacc[d];
+        }
+        code = ncd;
+#pragma unroll
+        for (int a = 0; a < NN; ++a) { cx[a] = nx[a]; cy[a] = ny[a]; cz[a] = nz[a]; }
+      }
     }
   }
   __syncthreads();

@@ -12,8 +12,9 @@ __global__ void rect_nodes(double x0, double y0, double stepx, double stepy, int
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_local) return;
   int64_t i = row_lo + n / (nCol + 1), j = n % (nCol + 1);
-  if (X) X[n] = (T)(x0 + (double)j * stepx);
-  if (Y) Y[n] = (T)(y0 + (double)i * stepy);
+  // mul then add, no FMA contraction: bit-identical to the reference's host arithmetic
+  if (X) X[n] = (T)__dadd_rn(x0, __dmul_rn((double)j, stepx));
+  if (Y) Y[n] = (T)__dadd_rn(y0, __dmul_rn((double)i, stepy));
   if (flag) flag[n] = (i == 0 || i == nRow || j == 0 || j == nCol) ? 1 : 0;
 }
 
@@ -35,9 +36,9 @@ __global__ void box_nodes(double x0, double y0, double z0, double hx, double hy,
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_local) return;
   int64_t i = n % (nx + 1), j = (n / (nx + 1)) % (ny + 1), k = k_lo + n / ((nx + 1) * (ny + 1));
-  if (X) X[n] = (T)(x0 + (double)i * hx);
-  if (Y) Y[n] = (T)(y0 + (double)j * hy);
-  if (Z) Z[n] = (T)(z0 + (double)k * hz);
+  if (X) X[n] = (T)__dadd_rn(x0, __dmul_rn((double)i, hx));
+  if (Y) Y[n] = (T)__dadd_rn(y0, __dmul_rn((double)j, hy));
+  if (Z) Z[n] = (T)__dadd_rn(z0, __dmul_rn((double)k, hz));
 }
 
 // Kuhn split, one thread per tet; permutation table and orientation fix as in

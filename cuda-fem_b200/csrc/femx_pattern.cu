@@ -211,7 +211,7 @@ __global__ void row_fill(const int* __restrict__ conn, const int* __restrict__ p
                          int2* __restrict__ rowinfo) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r > n_rows) return;
-  rowinfo[r] = make_int2(row_ptr[r], pair_ptr[r]);
+  rowinfo[r] = make_int2(row_ptr[r], r < n_rows ? pair_ptr[r + 1] - pair_ptr[r] : 0);
   if (r == n_rows) return;
   int list[FEMX_MAX_ROW];
   const int lo = pair_ptr[r], hi = pair_ptr[r + 1];
@@ -236,12 +236,39 @@ __global__ void row_fill(const int* __restrict__ conn, const int* __restrict__ p
   }
 }
 
-__global__ void tile_max(const int2* __restrict__ rowinfo, int n_rows, int tile, int* __restrict__ out) {
+// SELL-32 layout of the scatter map: slice = 32 consecutive rows, padded to the
+// slice's longest incidence list.
+__global__ void slice_sizes(const int* __restrict__ pair_ptr, int n_rows, int n_slices, int* __restrict__ size) {
+  int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= n_slices) return;
+  int r = s * 32 + (threadIdx.x & 31);
+  int np = r < n_rows ? pair_ptr[r + 1] - pair_ptr[r] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) np = max(np, __shfl_xor_sync(0xffffffffu, np, o));
+  if ((threadIdx.x & 31) == 0) size[s] = np * 32;
+}
+
+__global__ void to_sell(const int* __restrict__ pair_ptr, const int* __restrict__ slice_ptr, int n_rows,
+                        const int* __restrict__ pair_elem, const unsigned* __restrict__ pair_code,
+                        int* __restrict__ sell_elem, unsigned* __restrict__ sell_code) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int lo = pair_ptr[r], np = pair_ptr[r + 1] - lo;
+  const int sp = slice_ptr[r >> 5] + (r & 31);
+  for (int it = 0; it < np; ++it) {
+    sell_elem[sp + it * 32] = pair_elem[lo + it];
+    sell_code[sp + it * 32] = pair_code[lo + it];
+  }
+}
+
+__global__ void tile_max(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr, int n_rows, int tile,
+                         int* __restrict__ out) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int64_t i0 = (int64_t)t * tile;
   if (i0 >= n_rows) return;
   int i1 = (int)min((int64_t)n_rows, i0 + tile);
   atomicMax(out, rowinfo[i1].x - rowinfo[i0].x);
+  atomicMax(out + 1, slice_ptr[(i1 + 31) >> 5] - slice_ptr[i0 >> 5]);
 }
 
 // ---------------------------------------------------------------- exports ---
@@ -333,9 +360,12 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
   p->tile_nodes = femx_tile_nodes_for(nd);
   const int64_t nr = p->n_rows, total = n_elems * nn;
   int *d_cnt = nullptr, *d_pair_ptr = nullptr, *d_row_ptr = nullptr, *d_flags = nullptr;
+  int* d_pair_elem = nullptr;       // CSR-style incidence lists (temporary)
+  unsigned* d_pair_code = nullptr;
   int st_code = FEMX_OK;
   auto cleanup = [&]() {
     cudaFree(d_cnt); cudaFree(d_pair_ptr); cudaFree(d_row_ptr); cudaFree(d_flags);
+    cudaFree(d_pair_elem); cudaFree(d_pair_code);
   };
 #define PB_TRY(x)                                   \
   do {                                              \
@@ -373,24 +403,24 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
                      (long long)n_nodes);
   }
   p->n_pairs = n_pairs;
-  PB_TRY(dev_alloc(ctx, &p->d_pair_elem, n_pairs, &p->bytes));
-  PB_TRY(dev_alloc(ctx, &p->d_pair_code, n_pairs, &p->bytes));
+  PB_TRY(dev_alloc(ctx, &d_pair_elem, n_pairs, nullptr));
+  PB_TRY(dev_alloc(ctx, &d_pair_code, n_pairs, nullptr));
   PB_TRY(dev_alloc(ctx, &p->d_rowinfo, nr + 1, &p->bytes));
 
   // 3: bucket fill + sort
   PB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (nr + 1), st));
   if (total > 0) {
     fill_pairs<<<nblocks(total, 256), 256, 0, st>>>(d_conn, total, (int)row_begin, (int)row_end,
-                                                    d_pair_ptr, d_cnt, p->d_pair_elem);
-    if (nr > 0) sort_pairs<<<nblocks(nr, 128), 128, 0, st>>>(d_pair_ptr, (int)nr, p->d_pair_elem);
+                                                    d_pair_ptr, d_cnt, d_pair_elem);
+    if (nr > 0) sort_pairs<<<nblocks(nr, 128), 128, 0, st>>>(d_pair_ptr, (int)nr, d_pair_elem);
   }
   // 4-5: row lengths + scan
   if (nr > 0) {
     if (nn == 3)
-      row_lengths<3><<<nblocks(nr, 128), 128, 0, st>>>(d_conn, d_pair_ptr, p->d_pair_elem, (int)nr, d_cnt,
+      row_lengths<3><<<nblocks(nr, 128), 128, 0, st>>>(d_conn, d_pair_ptr, d_pair_elem, (int)nr, d_cnt,
                                                        d_flags, d_flags + 1);
     else
-      row_lengths<4><<<nblocks(nr, 128), 128, 0, st>>>(d_conn, d_pair_ptr, p->d_pair_elem, (int)nr, d_cnt,
+      row_lengths<4><<<nblocks(nr, 128), 128, 0, st>>>(d_conn, d_pair_ptr, d_pair_elem, (int)nr, d_cnt,
                                                        d_flags, d_flags + 1);
   }
   long long nnz = 0;
@@ -410,19 +440,47 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
   PB_TRY(dev_alloc(ctx, &p->d_col_idx, nnz, &p->bytes));
   // 6: columns + scatter map
   if (nn == 3)
-    row_fill<3><<<nblocks(nr + 1, 128), 128, 0, st>>>(d_conn, d_pair_ptr, p->d_pair_elem, d_row_ptr, (int)nr,
-                                                      (int)col_base, p->d_col_idx, p->d_pair_code, p->d_rowinfo);
+    row_fill<3><<<nblocks(nr + 1, 128), 128, 0, st>>>(d_conn, d_pair_ptr, d_pair_elem, d_row_ptr, (int)nr,
+                                                      (int)col_base, p->d_col_idx, d_pair_code, p->d_rowinfo);
   else
-    row_fill<4><<<nblocks(nr + 1, 128), 128, 0, st>>>(d_conn, d_pair_ptr, p->d_pair_elem, d_row_ptr, (int)nr,
-                                                      (int)col_base, p->d_col_idx, p->d_pair_code, p->d_rowinfo);
+    row_fill<4><<<nblocks(nr + 1, 128), 128, 0, st>>>(d_conn, d_pair_ptr, d_pair_elem, d_row_ptr, (int)nr,
+                                                      (int)col_base, p->d_col_idx, d_pair_code, p->d_rowinfo);
+  // SELL-32 transposition of the scatter map
+  {
+    const int64_t n_slices = (nr + 31) / 32;
+    int* d_ssize = nullptr;
+    PB_TRY(dev_alloc(ctx, &d_ssize, n_slices + 1, nullptr));
+    st_code = dev_alloc(ctx, &p->d_slice_ptr, n_slices + 1, &p->bytes);
+    long long n_sell = 0;
+    if (st_code == FEMX_OK) {
+      if (n_slices > 0) slice_sizes<<<nblocks(n_slices, 8), 256, 0, st>>>(d_pair_ptr, (int)nr, (int)n_slices, d_ssize);
+      st_code = exclusive_scan(ctx, d_ssize, n_slices, p->d_slice_ptr, &n_sell, st);
+    }
+    cudaFree(d_ssize);
+    if (st_code != FEMX_OK) { cleanup(); femx_pattern_destroy(p); return st_code; }
+    if (n_sell >= (1LL << 31) - 1) {
+      cleanup(); femx_pattern_destroy(p);
+      return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: padded scatter map (%lld) exceeds 32-bit offsets", n_sell);
+    }
+    p->n_sell = n_sell;
+    PB_TRY(dev_alloc(ctx, &p->d_sell_code, n_sell, &p->bytes));
+    PB_TRY(dev_alloc(ctx, &p->d_sell_elem, n_sell, &p->bytes));
+    if (n_sell > 0) {
+      PB_CUDA(cudaMemsetAsync(p->d_sell_code, 0, sizeof(unsigned) * n_sell, st));
+      PB_CUDA(cudaMemsetAsync(p->d_sell_elem, 0, sizeof(int) * n_sell, st));
+      to_sell<<<nblocks(nr, 128), 128, 0, st>>>(d_pair_ptr, p->d_slice_ptr, (int)nr, d_pair_elem, d_pair_code,
+                                                p->d_sell_elem, p->d_sell_code);
+    }
+  }
   if (nr > 0) {
     int64_t ntiles = (nr + p->tile_nodes - 1) / p->tile_nodes;
-    tile_max<<<nblocks(ntiles, 128), 128, 0, st>>>(p->d_rowinfo, (int)nr, p->tile_nodes, d_flags + 2);
+    tile_max<<<nblocks(ntiles, 128), 128, 0, st>>>(p->d_rowinfo, p->d_slice_ptr, (int)nr, p->tile_nodes, d_flags + 2);
   }
   PB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
   PB_CUDA(cudaStreamSynchronize(st));
   PB_CUDA(cudaGetLastError());
   p->max_tile_nnz = h_flags[2];
+  p->max_tile_codes = h_flags[3];
   cleanup();
   *out = p;
   return FEMX_OK;
@@ -434,8 +492,9 @@ void femx_pattern_destroy(femx_pattern* p) {
   if (!p) return;
   cudaFree(p->d_rowinfo);
   cudaFree(p->d_col_idx);
-  cudaFree(p->d_pair_code);
-  cudaFree(p->d_pair_elem);
+  cudaFree(p->d_slice_ptr);
+  cudaFree(p->d_sell_code);
+  cudaFree(p->d_sell_elem);
   delete p;
 }
 

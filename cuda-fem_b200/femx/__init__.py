@@ -32,7 +32,7 @@ class _FormDesc(C.Structure):
         ("entries", C.POINTER(C.c_char_p)), ("prologue", C.c_char_p),
         ("nq", C.c_int), ("qw", C.POINTER(C.c_double)), ("qr", C.POINTER(C.c_double)),
         ("qs", C.POINTER(C.c_double)), ("qt", C.POINTER(C.c_double)),
-        ("qu", C.POINTER(C.c_double)), ("fmad", C.c_int),
+        ("qu", C.POINTER(C.c_double)), ("fmad", C.c_int), ("integrated", C.c_int),
     ]
 
 
@@ -214,7 +214,7 @@ class Form:
     fea_symbolic_nvrtc_sparse.cpp:307-356, 506-561)."""
 
     def __init__(self, ctx, dim, builtin=POISSON, nd=1, dtype=F64, params=(), entries=None, prologue=None,
-                 rule=None, fmad=True, offline=False):
+                 rule=None, fmad=True, offline=False, integrated=False):
         self.ctx = ctx
         self.dim, self.nn, self.nd, self.dtype = dim, dim + 1, nd, dtype
         self.n = self.nn * nd
@@ -245,6 +245,7 @@ class Form:
                     ptrs.append(C.cast(a, C.POINTER(C.c_double)))
             d.qw, d.qr, d.qs, d.qt, d.qu = ptrs
         d.fmad = 1 if fmad else 0
+        d.integrated = 1 if integrated else 0
         self.h = C.c_void_p()
         if offline:
             st = lib().femx_form_compile_offline(C.byref(d), C.byref(self.h))

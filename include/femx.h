@@ -105,6 +105,10 @@ typedef struct femx_form_desc {
   const double* qu;
   int fmad; /* 1 (default build) allows FMA contraction; 0 = the reference's
                --fmad=false (fea_symbolic_nvrtc_sparse.cpp:529)              */
+  /* FEMX_FORM_CUSTOM only: 0 = entries are INTEGRANDS (the reference's
+   * semantics: weighted by w_q and summed over the rule); 1 = entries are the
+   * final element-matrix expressions, no quadrature applied. */
+  int integrated;
 } femx_form_desc;
 
 /* Replaces WeakForm::build + nvrtcCreateProgram … cuModuleGetFunction
@@ -123,7 +127,8 @@ const char* femx_form_log(const femx_form* form);
 const char* femx_form_entry(const femx_form* form, int li, int lj);
 const char* femx_form_prologue(const femx_form* form);
 /* Compile only (no device needed): emits source + cubin for inspection with
- * cuobjdump.  kernel: "coo", "csr", "csr_expanded".  cubin buffer is owned by the
+ * cuobjdump.  kernel: "coo", "csr" (node coordinates), "csr_x" (element-expanded
+ * coordinates), "csr_s" (strided node coordinates).  cubin buffer is owned by the
  * form. */
 int femx_form_cubin(femx_form* form, const char* kernel, const void** cubin, size_t* size);
 /* As femx_form_compile but never touches the device (ctx may be NULL):

@@ -58,7 +58,7 @@ def test_context_fails_loudly_without_device():
 @pytest.mark.parametrize("dtype", [femx.F64, femx.F32])
 def test_offline_jit_all_builtin_forms(dim, builtin, nd, dtype):
     f = femx.Form(None, dim, builtin, nd=nd, dtype=dtype, params=(0.6, 0.4), offline=True)
-    for k in ("coo", "csr"):
+    for k in ("coo", "csr", "csr_x", "csr_s"):
         cb = f.cubin(k)
         assert cb[:4] == b"\x7fELF"
     n = (dim + 1) * nd
@@ -71,8 +71,10 @@ def test_offline_jit_all_builtin_forms(dim, builtin, nd, dtype):
 def test_emitter_matches_reference_orientation():
     # entry (li, lj) = a(u=phi_lj, v=phi_li)*jac; Poisson is symmetric in the names
     f = femx.Form(None, 2, femx.POISSON, offline=True)
-    assert f.entry(0, 1) == "(g2x*g1x+g2y*g1y)*jac"
-    assert f.entry(2, 0) == "(g1x*g3x+g1y*g3y)*jac"
+    # d_a = jac * grad(phi_a); kq = (sum of weights) / jac  →  (d_lj . d_li) * kq
+    assert f.entry(0, 1) == "(d2x*d1x+d2y*d1y)*kq"
+    assert f.entry(2, 0) == "(d1x*d3x+d1y*d3y)*kq"
+    assert "kq = real(0.50000001" in f.prologue  # the reference's 8-digit weights, summed
     f.close()
 
 
