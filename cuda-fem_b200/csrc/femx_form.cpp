@@ -260,6 +260,35 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
     o << " break;";
   }
   o << "\n";
+  // Numeric pass: one case per dof row li = a*ND + c of the element matrix.  In case (a, c) the
+  // row's own node is local node a (coordinates sx,sy,sz) and the other vertices follow in
+  // cyclic order (ox[j] = local node (a+1+j) % NN), so every name binding, the diagonal
+  // accumulator and the scatter positions po[j] are static inside the case.
+  const int nn = f->nn, nd = f->nd;
+  static const char* ax[3] = {"x", "y", "z"};
+  o << "#define FEMX_CSR_CASES";
+  for (int a = 0; a < nn; ++a)
+    for (int c = 0; c < nd; ++c) {
+      const int li = a * nd + c;
+      o << " \\\n    case " << li << ": {";
+      for (int k = 0; k < f->dim; ++k) {
+        o << " const real " << ax[k] << a + 1 << " = s" << ax[k] << ";";
+        for (int j = 0; j < nn - 1; ++j)
+          o << " const real " << ax[k] << (a + 1 + j) % nn + 1 << " = o" << ax[k] << "[" << j << "];";
+      }
+      o << " \\\n      FEMX_PROLOGUE real out[NDOF];";
+      if (has_q[li]) {
+        o << " _Pragma(\"unroll\") for (int j_ = 0; j_ < NDOF; ++j_) out[j_] = real(0);";
+      }
+      o << " FEMX_ROWC_" << li;
+      if (has_q[li]) o << " FEMX_QUAD(FEMX_ROWQ_" << li << ")";
+      for (int d = 0; d < nd; ++d) o << " \\\n      dacc[" << d << "] += out[" << a * nd + d << "];";
+      for (int j = 0; j < nn - 1; ++j)
+        for (int d = 0; d < nd; ++d)
+          o << " \\\n      srow[po[" << j << "] + " << d << "] += out[" << ((a + 1 + j) % nn) * nd + d << "];";
+      o << " } break;";
+    }
+  o << "\n";
   return o.str();
 }
 
@@ -539,13 +568,12 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   const void* const* c = expanded ? mesh->d_elem_xyz : mesh->d_node_xyz;
   const void* X = c[0]; const void* Y = c[1]; const void* Z = c[2];
   int n_rows = (int)pat->n_rows;
-  int col_base = (int)pat->col_base;
   const int2* rowinfo = pat->d_rowinfo;
   const int32_t* col = pat->d_col_idx;
   const int32_t* slice_ptr = pat->d_slice_ptr;
   const uint32_t* code = pat->d_sell_code;
   const int32_t* pelem = pat->d_sell_elem;
-  void* args[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &n_rows, &col_base};
+  void* args[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &n_rows};
   unsigned blocks = (unsigned)((pat->n_rows + pat->tile_nodes - 1) / pat->tile_nodes);
   unsigned threads = (unsigned)(pat->tile_nodes * form->nd);
   CUresult cr = drv->LaunchKernel(v->fn, blocks, 1, 1, threads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);

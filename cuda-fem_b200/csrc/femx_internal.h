@@ -61,7 +61,7 @@ struct femx_pattern {
   int64_t max_tile_nnz = 0;
   int64_t max_tile_codes = 0;  // most padded incidences (SELL entries) in one tile
   int2* d_rowinfo = nullptr;       // [n_rows+1] {row_ptr, number of incidences}
-  int32_t* d_col_idx = nullptr;    // [nnz_node] local node id + col_base, ascending per row
+  int32_t* d_col_idx = nullptr;    // [nnz_node] LOCAL node id, ascending per row (exports add col_base)
   // SELL-32 scatter map: slice s = rows [32s, 32s+32); incidence `it` of row r sits at
   // slice_ptr[s] + 32*it + r%32 (rows padded to the slice's longest incidence list)
   int32_t* d_slice_ptr = nullptr;  // [n_slices+1]

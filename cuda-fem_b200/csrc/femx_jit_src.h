@@ -109,15 +109,19 @@ femx_coo(const int* __restrict__ conn, const real* __restrict__ X,
 // reads one contiguous 128-byte line per incidence.  Node ids come from the
 // tile's column list staged in shared memory, so connectivity is not re-read.
 static const char* const kFemxJitCsr = R"FEMX(
-// predicated read-only global load (keeps the gathers of the software pipeline
-// branch-free so that they are issued before the current incidence is evaluated)
-__device__ __forceinline__ void femx_ldg_if(double& v, const double* p, int pred) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.f64 %0, [%1];\n\t}"
-               : "+d"(v) : "l"(p), "r"(pred));
+// predicated read-only global load: keeps the gathers of the software pipeline
+// branch-free so that they are issued before the current incidence is evaluated
+__device__ __forceinline__ double femx_ldg_if(const double* p, int pred) {
+  double v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@p ld.global.nc.f64 %0, [%1];\n\t}"
+               : "=d"(v) : "l"(p), "r"(pred));
+  return v;
 }
-__device__ __forceinline__ void femx_ldg_if(float& v, const float* p, int pred) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.f32 %0, [%1];\n\t}"
-               : "+f"(v) : "l"(p), "r"(pred));
+__device__ __forceinline__ float femx_ldg_if(const float* p, int pred) {
+  float v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@p ld.global.nc.f32 %0, [%1];\n\t}"
+               : "=f"(v) : "l"(p), "r"(pred));
+  return v;
 }
 #if FEMX_UNIT_STRIDE
 #define FEMX_CS 1
@@ -125,12 +129,17 @@ __device__ __forceinline__ void femx_ldg_if(float& v, const float* p, int pred) 
 #define FEMX_CS cs
 #endif
 
+// Scatter code of one incidence (row node = local node li of element e):
+//   bits  0-6, 7-13, 14-20 : positions in the row's column list of the OTHER vertices,
+//                            in cyclic order (li+1)%NN, (li+2)%NN, ...
+//   bits 21-27             : position of the row's own node (the diagonal)
+//   bits 28-29             : li
 extern "C" __global__ void __launch_bounds__(FEMX_TILE_NODES * ND)
 femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
-         const int* __restrict__ col_idx, const unsigned* __restrict__ sell_code,
+         const int* __restrict__ col_loc, const unsigned* __restrict__ sell_code,
          const int* __restrict__ sell_elem, const real* __restrict__ X,
          const real* __restrict__ Y, const real* __restrict__ Z, const i64 cs,
-         real* __restrict__ vals, const int n_rows, const int col_base) {
+         real* __restrict__ vals, const int n_rows) {
   extern __shared__ __align__(128) unsigned char femx_smem[];
   const int i0 = blockIdx.x * FEMX_TILE_NODES;
   const int nt = min(FEMX_TILE_NODES, n_rows - i0);
@@ -151,19 +160,15 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
     const unsigned* gsrc = sell_code + sbase;  // 128-byte aligned (slices are 32-entry multiples)
     for (int j = threadIdx.x * 4; j < ncode; j += blockDim.x * 4)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + j * 4), "l"(gsrc + j) : "memory");
+#if !FEMX_EXPANDED
     const unsigned cdst = (unsigned)__cvta_generic_to_shared(s_cols);
-    const int* csrc = col_idx + base;
+    const int* csrc = col_loc + base;
     for (int j = threadIdx.x; j < cntn; j += blockDim.x)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cdst + j * 4), "l"(csrc + j) : "memory");
+#endif
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   for (int j = threadIdx.x; j < cnt; j += blockDim.x) s_vals[j] = real(0);
-  // column ids are local node id + col_base: fold the offset into the coordinate bases
-#if !FEMX_EXPANDED
-  X -= (i64)col_base * FEMX_CS;
-  Y -= (i64)col_base * FEMX_CS;
-  if (DIM == 3) Z -= (i64)col_base * FEMX_CS;
-#endif
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   const int ln = threadIdx.x / ND;
@@ -174,98 +179,92 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
     const int rlen = __ldg(&rowinfo[row + 1].x) - r0.x;
     const int off = r0.x - base;
     real* srow = s_vals + off * (ND * ND) + c * rlen * ND;
-    const int* scol = s_cols + off;
     const int sp = __ldg(slice_ptr + (row >> 5)) + (row & 31);
     const unsigned* sc = s_code + (sp - sbase);
     const int np = r0.y;
     if (np > 0) {
       unsigned code = sc[0];
+      real ox[NN - 1], oy[NN - 1], oz[NN - 1];
 #if FEMX_EXPANDED
-      // element-expanded coordinates X[NN*e + a] (the reference's layout): plain pipelined loads
+      // element-expanded coordinates X[NN*e + a] (the reference's layout, SURVEY Q17)
       const int* pelem = sell_elem + sp;
-      real cx[NN], cy[NN], cz[NN];
+      real sx, sy, sz = real(0);
       {
-        const i64 p0 = (i64)(__ldg(pelem) / NN) * NN;
+        const int ea = __ldg(pelem);  // e*NN + li
+        const int li = (code >> 28) & 3;
+        const int e0 = ea - li;
+        sx = __ldg(X + ea); sy = __ldg(Y + ea);
+        if (DIM == 3) sz = __ldg(Z + ea);
 #pragma unroll
-        for (int a = 0; a < NN; ++a) {
-          cx[a] = __ldg(X + p0 + a); cy[a] = __ldg(Y + p0 + a);
-          cz[a] = DIM == 3 ? __ldg(Z + p0 + a) : real(0);
+        for (int j = 0; j < NN - 1; ++j) {
+          int b = li + 1 + j; b -= b >= NN ? NN : 0;
+          ox[j] = __ldg(X + e0 + b); oy[j] = __ldg(Y + e0 + b);
+          oz[j] = DIM == 3 ? __ldg(Z + e0 + b) : real(0);
         }
       }
 #else
-      // the row's own node is a vertex of every incident element: keep it in registers
-      const int self_pos = (code >> (7 * ((code >> 28) & 3))) & 127;
-      const i64 pself = (i64)scol[self_pos] * FEMX_CS;
-      const real xs = __ldg(X + pself), ys = __ldg(Y + pself), zs = DIM == 3 ? __ldg(Z + pself) : real(0);
-      real cx[NN], cy[NN], cz[NN];
-      {
-        const int li = (code >> 28) & 3;
+      // the row's own node is a vertex of every incident element: it stays in registers
+      const int* scol = s_cols + off;
+      const i64 pself = (i64)scol[(code >> 21) & 127] * FEMX_CS;
+      const real sx = __ldg(X + pself), sy = __ldg(Y + pself), sz = DIM == 3 ? __ldg(Z + pself) : real(0);
 #pragma unroll
-        for (int a = 0; a < NN; ++a) {
-          const i64 p = (i64)scol[(code >> (7 * a)) & 127] * FEMX_CS;
-          cx[a] = xs; cy[a] = ys; cz[a] = zs;
-          femx_ldg_if(cx[a], X + p, a != li);
-          femx_ldg_if(cy[a], Y + p, a != li);
-          if (DIM == 3) femx_ldg_if(cz[a], Z + p, a != li);
-        }
+      for (int j = 0; j < NN - 1; ++j) {
+        const i64 p = (i64)scol[(code >> (7 * j)) & 127] * FEMX_CS;
+        ox[j] = __ldg(X + p); oy[j] = __ldg(Y + p);
+        oz[j] = DIM == 3 ? __ldg(Z + p) : real(0);
       }
 #endif
-      real dacc[ND];  // the diagonal block row (self column) accumulates in registers
+      real dacc[ND];  // the diagonal block row (own column) accumulates in registers
 #pragma unroll
       for (int d = 0; d < ND; ++d) dacc[d] = real(0);
       for (int it = 0; it < np; ++it) {
-        // ---- software pipeline: gathers of incidence it+1 are issued first
+        // ---- software pipeline: the gathers of incidence it+1 are issued first
         const int more = it + 1 < np;
-        const unsigned ncd = sc[(it + more) * 32];
-        real nx[NN], ny[NN], nz[NN];
+        sc += more ? 32 : 0;
+        const unsigned ncd = *sc;
+        real nox[NN - 1], noy[NN - 1], noz[NN - 1];
 #if FEMX_EXPANDED
+        pelem += more ? 32 : 0;
+        real nsx, nsy, nsz = real(0);
         {
-          const i64 p0 = (i64)(__ldg(pelem + (it + more) * 32) / NN) * NN;
+          const int ea = __ldg(pelem);
+          const int nli = (ncd >> 28) & 3;
+          const int e0 = ea - nli;
+          nsx = femx_ldg_if(X + ea, more); nsy = femx_ldg_if(Y + ea, more);
+          if (DIM == 3) nsz = femx_ldg_if(Z + ea, more);
 #pragma unroll
-          for (int a = 0; a < NN; ++a) {
-            nx[a] = cx[a]; ny[a] = cy[a]; nz[a] = cz[a];
-            femx_ldg_if(nx[a], X + p0 + a, more);
-            femx_ldg_if(ny[a], Y + p0 + a, more);
-            if (DIM == 3) femx_ldg_if(nz[a], Z + p0 + a, more);
+          for (int j = 0; j < NN - 1; ++j) {
+            int b = nli + 1 + j; b -= b >= NN ? NN : 0;
+            nox[j] = femx_ldg_if(X + e0 + b, more); noy[j] = femx_ldg_if(Y + e0 + b, more);
+            noz[j] = DIM == 3 ? femx_ldg_if(Z + e0 + b, more) : real(0);
           }
         }
 #else
-        {
-          const int nli = (ncd >> 28) & 3;
 #pragma unroll
-          for (int a = 0; a < NN; ++a) {
-            const i64 p = (i64)scol[(ncd >> (7 * a)) & 127] * FEMX_CS;
-            const int pr = more & (a != nli);
-            nx[a] = xs; ny[a] = ys; nz[a] = zs;
-            femx_ldg_if(nx[a], X + p, pr);
-            femx_ldg_if(ny[a], Y + p, pr);
-            if (DIM == 3) femx_ldg_if(nz[a], Z + p, pr);
-          }
+        for (int j = 0; j < NN - 1; ++j) {
+          const i64 p = (i64)scol[(ncd >> (7 * j)) & 127] * FEMX_CS;
+          nox[j] = femx_ldg_if(X + p, more); noy[j] = femx_ldg_if(Y + p, more);
+          noz[j] = DIM == 3 ? femx_ldg_if(Z + p, more) : real(0);
         }
 #endif
-        // ---- evaluate incidence it
-        const int li = (code >> 28) & 3;
-        real out[NDOF];
-        femx_row(li * ND + c, cx, cy, cz, out);
+        // ---- evaluate incidence it: row li*ND + c of the element matrix
+        int po[NN - 1];
 #pragma unroll
-        for (int a = 0; a < NN; ++a) {
-          if (a == li) {
-#pragma unroll
-            for (int d = 0; d < ND; ++d) dacc[d] += out[a * ND + d];
-          } else {
-            const int pa = ((code >> (7 * a)) & 127) * ND;
-#pragma unroll
-            for (int d = 0; d < ND; ++d) srow[pa + d] += out[a * ND + d];
-          }
+        for (int j = 0; j < NN - 1; ++j) po[j] = ((code >> (7 * j)) & 127) * ND;
+        switch (((code >> 28) & 3) * ND + c) {
+          FEMX_CSR_CASES
         }
         if (!more) {
-          const int pa = ((code >> (7 * li)) & 127) * ND;
+          const int ps = ((code >> 21) & 127) * ND;
 #pragma unroll
-          for (int d = 0; d < ND; ++d) srow[pa + d] = dacc[d];
+          for (int d = 0; d < ND; ++d) srow[ps + d] = dacc[d];
         }
         code = ncd;
 #pragma unroll
-        for (int a = 0; a < NN; ++a) { cx[a] = nx[a]; cy[a] = ny[a]; cz[a] = nz[a]; }
+        for (int j = 0; j < NN - 1; ++j) { ox[j] = nox[j]; oy[j] = noy[j]; oz[j] = noz[j]; }
+#if FEMX_EXPANDED
+        sx = nsx; sy = nsy; sz = nsz;
+#endif
       }
     }
   }

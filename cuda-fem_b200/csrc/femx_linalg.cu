@@ -17,7 +17,7 @@ __global__ void spmv_k(const int2* __restrict__ rowinfo, const int* __restrict__
   const T* v = vals + (long long)lo * nd * nd + (long long)c * nd * len;
   double s = 0.0;
   for (int p = 0; p < len; ++p) {
-    long long col = (long long)col_idx[lo + p] * nd - x_base;
+    long long col = (long long)col_idx[lo + p] * nd - x_base;  // x_base already holds -nd*col_base
     for (int d = 0; d < nd; ++d) s += (double)v[p * nd + d] * (double)x[col + d];
   }
   y[t] = (T)s;
@@ -86,11 +86,11 @@ int femx_spmv(const femx_pattern* p, int dtype, const void* d_values, const void
   if (dtype == FEMX_F64)
     spmv_k<double><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
                                                             (const double*)d_values, (const double*)d_x,
-                                                            (long long)x_base, (double*)d_y);
+                                                            (long long)x_base - (long long)p->nd * p->col_base, (double*)d_y);
   else
     spmv_k<float><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
                                                            (const float*)d_values, (const float*)d_x,
-                                                           (long long)x_base, (float*)d_y);
+                                                           (long long)x_base - (long long)p->nd * p->col_base, (float*)d_y);
   FEMX_CUDA_OK(p->ctx, cudaGetLastError());
   return FEMX_OK;
 }

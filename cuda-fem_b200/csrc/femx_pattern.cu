@@ -207,7 +207,7 @@ __global__ void row_lengths(const int* __restrict__ conn, const int* __restrict_
 template <int NN>
 __global__ void row_fill(const int* __restrict__ conn, const int* __restrict__ pair_ptr,
                          const int* __restrict__ pair_elem, const int* __restrict__ row_ptr, int n_rows,
-                         int col_base, int* __restrict__ col_idx, unsigned* __restrict__ pair_code,
+                         int* __restrict__ col_idx, unsigned* __restrict__ pair_code,
                          int2* __restrict__ rowinfo) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r > n_rows) return;
@@ -217,10 +217,12 @@ __global__ void row_fill(const int* __restrict__ conn, const int* __restrict__ p
   const int lo = pair_ptr[r], hi = pair_ptr[r + 1];
   const int len = build_row<NN>(conn, pair_elem, lo, hi, list);
   const int rp = row_ptr[r];
-  for (int p = 0; p < len; ++p) col_idx[rp + p] = list[p] + col_base;
+  for (int p = 0; p < len; ++p) col_idx[rp + p] = list[p];
   for (int k = lo; k < hi; ++k) {
     const int pe = pair_elem[k];
     const int e = pe / NN, li = pe - e * NN;
+    // positions of the element's vertices in the sorted row: the OTHER vertices in cyclic
+    // order after li at bits 7*j, the row's own node at bits 21-27, li at bits 28-29
     unsigned code = (unsigned)li << 28;
 #pragma unroll
     for (int a = 0; a < NN; ++a) {
@@ -230,7 +232,8 @@ __global__ void row_fill(const int* __restrict__ conn, const int* __restrict__ p
         int m = (a0 + b0) >> 1;
         if (list[m] < node) a0 = m + 1; else b0 = m;
       }
-      code |= (unsigned)a0 << (7 * a);
+      const int j = a == li ? 3 : (a - li - 1 + NN) % NN;
+      code |= (unsigned)a0 << (7 * j);
     }
     pair_code[k] = code;
   }
@@ -273,7 +276,7 @@ __global__ void tile_max(const int2* __restrict__ rowinfo, const int* __restrict
 
 // ---------------------------------------------------------------- exports ---
 __global__ void export_csr_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx, int n_rows,
-                             int nd, long long* __restrict__ rp64, int* __restrict__ rp32,
+                             int nd, int col_base, long long* __restrict__ rp64, int* __restrict__ rp32,
                              int* __restrict__ dcol) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // dof row
   int64_t nrows_d = (int64_t)n_rows * nd;
@@ -291,19 +294,19 @@ __global__ void export_csr_k(const int2* __restrict__ rowinfo, const int* __rest
   if (rp32) rp32[t] = (int)start;
   if (dcol)
     for (int p = 0; p < len; ++p) {
-      int col = col_idx[lo + p];
+      int col = col_idx[lo + p] + col_base;
       for (int d = 0; d < nd; ++d) dcol[start + (long long)p * nd + d] = col * nd + d;
     }
 }
 
 __global__ void export_ell_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx, int n_rows,
-                             int width, int* __restrict__ len_out, int* __restrict__ idx) {
+                             int width, int col_base, int* __restrict__ len_out, int* __restrict__ idx) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   int lo = rowinfo[r].x, len = rowinfo[r + 1].x - lo;
   if (len_out) len_out[r] = len;
   if (idx)
-    for (int j = 0; j < width; ++j) idx[(int64_t)r * width + j] = j < len ? col_idx[lo + j] : 0;
+    for (int j = 0; j < width; ++j) idx[(int64_t)r * width + j] = j < len ? col_idx[lo + j] + col_base : 0;
 }
 
 template <class T>
@@ -441,10 +444,10 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
   // 6: columns + scatter map
   if (nn == 3)
     row_fill<3><<<nblocks(nr + 1, 128), 128, 0, st>>>(d_conn, d_pair_ptr, d_pair_elem, d_row_ptr, (int)nr,
-                                                      (int)col_base, p->d_col_idx, d_pair_code, p->d_rowinfo);
+                                                      p->d_col_idx, d_pair_code, p->d_rowinfo);
   else
     row_fill<4><<<nblocks(nr + 1, 128), 128, 0, st>>>(d_conn, d_pair_ptr, d_pair_elem, d_row_ptr, (int)nr,
-                                                      (int)col_base, p->d_col_idx, d_pair_code, p->d_rowinfo);
+                                                      p->d_col_idx, d_pair_code, p->d_rowinfo);
   // SELL-32 transposition of the scatter map
   {
     const int64_t n_slices = (nr + 31) / 32;
@@ -516,7 +519,7 @@ int femx_pattern_export_csr(const femx_pattern* p, int64_t* d_rp64, int32_t* d_r
   FEMX_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
   int64_t n = p->n_rows * p->nd + 1;
   export_csr_k<<<nblocks(n, 128), 128, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
-                                                                  (long long*)d_rp64, d_rp32, d_col);
+                                                                  (int)p->col_base, (long long*)d_rp64, d_rp32, d_col);
   FEMX_CUDA_OK(p->ctx, cudaGetLastError());
   return FEMX_OK;
 }
@@ -529,7 +532,7 @@ int femx_pattern_export_ell(const femx_pattern* p, int width, int32_t* d_len, in
   if (p->n_rows == 0) return FEMX_OK;
   FEMX_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
   export_ell_k<<<nblocks(p->n_rows, 128), 128, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows,
-                                                                          width, d_len, d_idx);
+                                                                          width, (int)p->col_base, d_len, d_idx);
   FEMX_CUDA_OK(p->ctx, cudaGetLastError());
   return FEMX_OK;
 }
