@@ -222,6 +222,8 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
   o << "#define FEMX_REAL " << (f->dtype == FEMX_F32 ? "float" : "double") << "\n";
   o << "#define NN " << f->nn << "\n#define ND " << f->nd << "\n#define DIM " << f->dim
     << "\n#define FEMX_TILE_NODES " << femx_tile_nodes_for(f->nd) << "\n";
+  o << "#define FEMX_MIN_BLOCKS " << (getenv("FEMX_MINBLOCKS") ? atoi(getenv("FEMX_MINBLOCKS")) : 0) << "\n";
+  o << "#define FEMX_UNROLL " << (getenv("FEMX_UNROLL") ? atoi(getenv("FEMX_UNROLL")) : 1) << "\n";
   o << "#define FEMX_EXPANDED " << (kernel == "csr_x" ? 1 : 0) << "\n";
   o << "#define FEMX_UNIT_STRIDE " << (kernel == "csr" ? 1 : 0) << "\n";
   std::string esc;
@@ -549,7 +551,9 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   if (st != FEMX_OK) return st;
   const femx_driver* drv = femx_get_driver(nullptr);
   const size_t rs = form->dtype == FEMX_F32 ? 4 : 8;
-  size_t smem = (size_t)pat->max_tile_nnz * (form->nd * form->nd * rs + 4) + (size_t)pat->max_tile_codes * 4;
+  // [mbarrier 128 B | codes | values (+16 B phase pad) | columns (+32 B phase pad)]
+  size_t smem = 128 + (size_t)pat->max_tile_codes * 4 + (((size_t)pat->max_tile_nnz * form->nd * form->nd * rs + 15) / 16) * 16 + 32 +
+                (size_t)pat->max_tile_nnz * 4 + 32;
   if (smem > form->ctx->smem_optin)
     return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED,
                      "femx_assemble_csr: a %d-row tile needs %zu B of shared memory (> %zu)",

@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdint>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -73,4 +74,11 @@ struct femx_pattern {
 
 #define FEMX_DOT_BLOCKS 1024
 
-static inline int femx_tile_nodes_for(int nd) { return nd == 1 ? 256 : (nd == 2 ? 128 : 64); }
+// node rows per CTA of the numeric pass (FEMX_TILE overrides: tuning experiments only)
+static inline int femx_tile_nodes_for(int nd) {
+  if (const char* e = getenv("FEMX_TILE")) {
+    int t = atoi(e);
+    if (t >= 32 && t <= 1024 && t % 32 == 0 && t * nd <= 1024) return t;
+  }
+  return nd == 1 ? 256 : (nd == 2 ? 128 : 64);
+}

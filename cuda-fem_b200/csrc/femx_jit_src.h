@@ -111,15 +111,16 @@ femx_coo(const int* __restrict__ conn, const real* __restrict__ X,
 static const char* const kFemxJitCsr = R"FEMX(
 // predicated read-only global load: keeps the gathers of the software pipeline
 // branch-free so that they are issued before the current incidence is evaluated
+// (when the predicate is off the result is never used)
 __device__ __forceinline__ double femx_ldg_if(const double* p, int pred) {
   double v;
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@p ld.global.nc.f64 %0, [%1];\n\t}"
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.f64 %0, [%1];\n\t}"
                : "=d"(v) : "l"(p), "r"(pred));
   return v;
 }
 __device__ __forceinline__ float femx_ldg_if(const float* p, int pred) {
   float v;
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@p ld.global.nc.f32 %0, [%1];\n\t}"
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.f32 %0, [%1];\n\t}"
                : "=f"(v) : "l"(p), "r"(pred));
   return v;
 }
@@ -128,13 +129,25 @@ __device__ __forceinline__ float femx_ldg_if(const float* p, int pred) {
 #else
 #define FEMX_CS cs
 #endif
+#if FEMX_MIN_BLOCKS > 0
+#define FEMX_BOUNDS __launch_bounds__(FEMX_TILE_NODES * ND, FEMX_MIN_BLOCKS)
+#else
+#define FEMX_BOUNDS __launch_bounds__(FEMX_TILE_NODES * ND)
+#endif
+#define FEMX_EPV (16 / (int)sizeof(real))  // values per 16 bytes
 
 // Scatter code of one incidence (row node = local node li of element e):
 //   bits  0-6, 7-13, 14-20 : positions in the row's column list of the OTHER vertices,
 //                            in cyclic order (li+1)%NN, (li+2)%NN, ...
 //   bits 21-27             : position of the row's own node (the diagonal)
 //   bits 28-29             : li
-extern "C" __global__ void __launch_bounds__(FEMX_TILE_NODES * ND)
+//
+// Data movement of one tile (FEMX_TILE_NODES node rows):
+//   in : scatter codes + column list  -- two TMA bulk copies (cp.async.bulk, one thread,
+//        mbarrier completion), no per-thread load/store instructions
+//   out: the tile's CSR values        -- one TMA bulk store from the shared-memory image
+//   gathered node coordinates come through L1 (read-only path), software-pipelined.
+extern "C" __global__ void FEMX_BOUNDS
 femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
          const int* __restrict__ col_loc, const unsigned* __restrict__ sell_code,
          const int* __restrict__ sell_elem, const real* __restrict__ X,
@@ -148,29 +161,47 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   const int cnt = cntn * (ND * ND);
   const int sbase = __ldg(slice_ptr + (i0 >> 5));      // the tile's slices are contiguous
   const int ncode = __ldg(slice_ptr + ((i0 + nt + 31) >> 5)) - sbase;
-  // smem: [codes | values | columns]; codes first so that 16-byte async copies are aligned
-  unsigned* s_code = reinterpret_cast<unsigned*>(femx_smem);
-  real* s_vals = reinterpret_cast<real*>(s_code + ncode);
-  int* s_cols = reinterpret_cast<int*>(s_vals + cnt);
-  // Stage the tile's streamed inputs (scatter codes, column list) with asynchronous
-  // global->shared copies: every copy of the tile is in flight at once, no register
-  // staging, one memory latency per tile instead of one per loop trip.
-  {
-    const unsigned sdst = (unsigned)__cvta_generic_to_shared(s_code);
-    const unsigned* gsrc = sell_code + sbase;  // 128-byte aligned (slices are 32-entry multiples)
-    for (int j = threadIdx.x * 4; j < ncode; j += blockDim.x * 4)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + j * 4), "l"(gsrc + j) : "memory");
-#if !FEMX_EXPANDED
-    const unsigned cdst = (unsigned)__cvta_generic_to_shared(s_cols);
-    const int* csrc = col_loc + base;
-    for (int j = threadIdx.x; j < cntn; j += blockDim.x)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cdst + j * 4), "l"(csrc + j) : "memory");
+  // smem: [mbarrier | codes | values | columns].  Values and columns are placed with the
+  // same 16-byte phase as their global addresses so that bulk copies are aligned.
+  const i64 vb = (i64)base * (ND * ND);              // first value index of the tile
+  const int vph = (int)(vb & (FEMX_EPV - 1));         // phase of the value run (elements)
+  const int cph = base & 3;                           // phase of the column run (ints)
+  unsigned* s_code = reinterpret_cast<unsigned*>(femx_smem + 128);
+  real* s_vals = reinterpret_cast<real*>(s_code + ncode) + vph;
+  const int vspan = (vph + cnt + FEMX_EPV - 1) & ~(FEMX_EPV - 1);
+  int* s_cols = reinterpret_cast<int*>(s_vals - vph + vspan) + cph;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(femx_smem);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#if FEMX_EXPANDED
+    const unsigned cbytes = 0;
+#else
+    const unsigned cbytes = (unsigned)(((cph + cntn + 3) & ~3) * 4);
 #endif
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    const unsigned kbytes = (unsigned)ncode * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kbytes + cbytes) : "memory");
+    if (kbytes)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((unsigned)__cvta_generic_to_shared(s_code)), "l"(sell_code + sbase), "r"(kbytes), "r"(bar) : "memory");
+    if (cbytes)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((unsigned)__cvta_generic_to_shared(s_cols - cph)), "l"(col_loc + (base - cph)), "r"(cbytes), "r"(bar) : "memory");
   }
-  for (int j = threadIdx.x; j < cnt; j += blockDim.x) s_vals[j] = real(0);
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
+  // zero the value image with 16-byte stores (head/tail phases are inside the padded span)
+  {
+    float4* z = reinterpret_cast<float4*>(s_vals - vph);
+    const int n16 = vspan / FEMX_EPV;
+    for (int j = threadIdx.x; j < n16; j += blockDim.x) z[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();  // barrier initialised + image zeroed
+  {
+    unsigned done;
+    do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar) : "memory");
+    } while (!done);
+  }
   const int ln = threadIdx.x / ND;
   const int c = threadIdx.x - ln * ND;
   if (ln < nt) {
@@ -184,6 +215,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
     const int np = r0.y;
     if (np > 0) {
       unsigned code = sc[0];
+      const int ps = ((code >> 21) & 127) * ND;  // own column: the same for every incidence
       real ox[NN - 1], oy[NN - 1], oz[NN - 1];
 #if FEMX_EXPANDED
       // element-expanded coordinates X[NN*e + a] (the reference's layout, SURVEY Q17)
@@ -217,6 +249,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
       real dacc[ND];  // the diagonal block row (own column) accumulates in registers
 #pragma unroll
       for (int d = 0; d < ND; ++d) dacc[d] = real(0);
+#pragma unroll FEMX_UNROLL
       for (int it = 0; it < np; ++it) {
         // ---- software pipeline: the gathers of incidence it+1 are issued first
         const int more = it + 1 < np;
@@ -254,11 +287,6 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
         switch (((code >> 28) & 3) * ND + c) {
           FEMX_CSR_CASES
         }
-        if (!more) {
-          const int ps = ((code >> 21) & 127) * ND;
-#pragma unroll
-          for (int d = 0; d < ND; ++d) srow[ps + d] = dacc[d];
-        }
         code = ncd;
 #pragma unroll
         for (int j = 0; j < NN - 1; ++j) { ox[j] = nox[j]; oy[j] = noy[j]; oz[j] = noz[j]; }
@@ -266,10 +294,28 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
         sx = nsx; sy = nsy; sz = nsz;
 #endif
       }
+#pragma unroll
+      for (int d = 0; d < ND; ++d) srow[ps + d] = dacc[d];
     }
   }
+  // ---- write the tile: generic-proxy writes -> async proxy, then one bulk store
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
-  real* dst = vals + (i64)base * (ND * ND);
-  for (int j = threadIdx.x; j < cnt; j += blockDim.x) dst[j] = s_vals[j];
+  {
+    real* dst = vals + vb;
+    const int head = min(cnt, (FEMX_EPV - vph) & (FEMX_EPV - 1));   // elements before the first 16-byte boundary
+    const int mid = (cnt - head) & ~(FEMX_EPV - 1);                  // elements in whole 16-byte units
+    if (threadIdx.x == 0 && mid > 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   ::"l"(dst + head), "r"((unsigned)__cvta_generic_to_shared(s_vals + head)), "r"((unsigned)(mid * sizeof(real))) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    // ragged head / tail (fewer than 16 bytes each)
+    const int ntail = cnt - head - mid;
+    if ((int)threadIdx.x < head) dst[threadIdx.x] = s_vals[threadIdx.x];
+    else if ((int)threadIdx.x >= 32 && (int)threadIdx.x - 32 < ntail)
+      dst[head + mid + threadIdx.x - 32] = s_vals[head + mid + threadIdx.x - 32];
+    if (threadIdx.x == 0 && mid > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
 }
 )FEMX";

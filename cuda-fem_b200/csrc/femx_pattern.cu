@@ -440,7 +440,8 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
   }
   p->nnz_node = nnz;
   p->max_row = h_flags[1];
-  PB_TRY(dev_alloc(ctx, &p->d_col_idx, nnz, &p->bytes));
+  PB_TRY(dev_alloc(ctx, &p->d_col_idx, nnz + 8, &p->bytes));  // +8: 16-byte bulk copies may overrun the last row
+  PB_CUDA(cudaMemsetAsync(p->d_col_idx + nnz, 0, sizeof(int) * 8, st));
   // 6: columns + scatter map
   if (nn == 3)
     row_fill<3><<<nblocks(nr + 1, 128), 128, 0, st>>>(d_conn, d_pair_ptr, d_pair_elem, d_row_ptr, (int)nr,
