@@ -34,6 +34,7 @@ const femx_driver* femx_get_driver(std::string* why) {
         {"cuModuleGetFunction", (void**)&drv.ModuleGetFunction},
         {"cuLaunchKernel", (void**)&drv.LaunchKernel},
         {"cuFuncSetAttribute", (void**)&drv.FuncSetAttribute},
+        {"cuFuncGetAttribute", (void**)&drv.FuncGetAttribute},
         {"cuGetErrorString", (void**)&drv.GetErrorString},
     };
     for (auto& s : syms) {

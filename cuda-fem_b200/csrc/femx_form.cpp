@@ -558,10 +558,26 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
     return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED,
                      "femx_assemble_csr: a %d-row tile needs %zu B of shared memory (> %zu)",
                      pat->tile_nodes, smem, form->ctx->smem_optin);
-  if (!v->carveout_set) {
-    // prefer shared memory over L1 up to what full occupancy needs (experiment knob: FEMX_CARVEOUT=percent)
-    if (const char* cv = getenv("FEMX_CARVEOUT"))
-      drv->FuncSetAttribute(v->fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, atoi(cv));
+  if (!v->carveout_set || (int)smem > v->smem_set) {
+    // Shared-memory carve-out: just enough for the CTAs that registers/threads allow, the rest
+    // stays L1 for the coordinate gathers.  (FEMX_CARVEOUT=percent overrides: experiments.)
+    int pct = 0;
+    const char* cv = getenv("FEMX_CARVEOUT");
+    if (cv && *cv) {
+      pct = atoi(cv);
+    } else {
+      int regs = 64;
+      drv->FuncGetAttribute(&regs, CU_FUNC_ATTRIBUTE_NUM_REGS, v->fn);
+      const int threads = pat->tile_nodes * form->nd;
+      const int regs_alloc = ((regs + 7) / 8) * 8;
+      int ctas = 65536 / (regs_alloc * threads);
+      if (ctas > 2048 / threads) ctas = 2048 / threads;
+      if (ctas > 32) ctas = 32;
+      if (ctas < 1) ctas = 1;
+      pct = (int)((ctas * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+      if (pct > 100) pct = 100;
+    }
+    drv->FuncSetAttribute(v->fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct);
     v->carveout_set = 1;
   }
   if ((int)smem > v->smem_set && smem > 48 * 1024) {

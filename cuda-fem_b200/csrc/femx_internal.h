@@ -30,6 +30,7 @@ struct femx_driver {
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned,
                            unsigned, unsigned, CUstream, void**, void**) = nullptr;
   CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
   bool ok = false;
 };
@@ -80,5 +81,5 @@ static inline int femx_tile_nodes_for(int nd) {
     int t = atoi(e);
     if (t >= 32 && t <= 1024 && t % 32 == 0 && t * nd <= 1024) return t;
   }
-  return nd == 1 ? 256 : (nd == 2 ? 128 : 64);
+  return nd == 1 ? 128 : 64;
 }

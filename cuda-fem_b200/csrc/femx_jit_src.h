@@ -170,6 +170,13 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   real* s_vals = reinterpret_cast<real*>(s_code + ncode) + vph;
   const int vspan = (vph + cnt + FEMX_EPV - 1) & ~(FEMX_EPV - 1);
   int* s_cols = reinterpret_cast<int*>(s_vals - vph + vspan) + cph;
+  // per-row metadata: issued before the staging wait so that its latency overlaps the bulk copies
+  const int ln = threadIdx.x / ND;
+  const int c = threadIdx.x - ln * ND;
+  const int rowc = i0 + min(ln, nt - 1);
+  const int2 r0 = __ldg(&rowinfo[rowc]);
+  const int rnext = __ldg(&rowinfo[rowc + 1].x);
+  const int spg = __ldg(slice_ptr + (rowc >> 5));
   const unsigned bar = (unsigned)__cvta_generic_to_shared(femx_smem);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -202,15 +209,12 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
                    : "=r"(done) : "r"(bar) : "memory");
     } while (!done);
   }
-  const int ln = threadIdx.x / ND;
-  const int c = threadIdx.x - ln * ND;
   if (ln < nt) {
     const int row = i0 + ln;
-    const int2 r0 = __ldg(&rowinfo[row]);
-    const int rlen = __ldg(&rowinfo[row + 1].x) - r0.x;
+    const int rlen = rnext - r0.x;
     const int off = r0.x - base;
     real* srow = s_vals + off * (ND * ND) + c * rlen * ND;
-    const int sp = __ldg(slice_ptr + (row >> 5)) + (row & 31);
+    const int sp = spg + (row & 31);
     const unsigned* sc = s_code + (sp - sbase);
     const int np = r0.y;
     if (np > 0) {
