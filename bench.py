@@ -97,6 +97,40 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def ref_gpu_baseline(ctx, wl, mesh, pat):
+    """North-star reported baseline #1: the reference's own kernels (K4 COO, K5 ELL + global atomicAdd;
+    oracle/_ref, recompiled for sm_100 with the minimal fixes of oracle/build_ref.py) timed on the same
+    mesh.  fp32 as written and the mechanical fp64 retype.  Reported, not optimised."""
+    try:
+        from oracle import refimpl
+        if not refimpl.available() or wl["dim"] != 2:
+            return None
+        import torch
+        out = {"what": "reference fea_kernel recompiled for sm_100 (fixes Q2,Q3,Q4,Q8,Q13), CUDA events, 3 launches"}
+        ln, idx = pat.ell(7)
+        gidx = mesh.conn.reshape(-1).contiguous()
+        for prec, tdt in (("f32", torch.float32), ("f64", torch.float64)):
+            X = mesh.node_xyz[0][mesh.conn.reshape(-1).long()].to(tdt).contiguous()
+            Y = mesh.node_xyz[1][mesh.conn.reshape(-1).long()].to(tdt).contiguous()
+            _, ms_ell = refimpl.assemble_ell(prec, wl["rows"], wl["cols"], X, Y, gidx, ln, idx, iters=3)
+            _, _, _, ms_coo = refimpl.assemble_coo(prec, wl["rows"], wl["cols"], X, Y, gidx, iters=3)
+            out[prec] = {"ell_atomic_ms": ms_ell, "ell_atomic_elements_per_s": mesh.n_elems / (ms_ell * 1e-3),
+                         "coo_ms": ms_coo, "coo_elements_per_s": mesh.n_elems / (ms_coo * 1e-3)}
+            del X, Y
+        return out
+    except Exception as e:  # a reported extra must never take the headline down
+        return {"error": repr(e)}
+
+
+def profiled_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of femx_csr from the committed
+    `ncu --set full` capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(workload)
+    return None
+
+
 def slab_bounds(n_planes_total, world, rank):
     """Owned node rows/planes [r0, r1) of rank, and the slab [lo, hi] incl. one ghost layer each side."""
     r0 = round(rank * n_planes_total / world)
@@ -304,7 +338,7 @@ def main():
         },
         "nnz_per_s": pat.nnz * world / (ms_per_step * 1e-3),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "femx_csr", "kernel_ms": kern_ms, "kernel_ms_min": per_launch[0],
+                     "traffic": profiled_traffic(args.workload) if world == 1 else None, "kernel": "femx_csr", "kernel_ms": kern_ms, "kernel_ms_min": per_launch[0],
                      "algorithmic_bytes": b_alg, "peak_source": peak_src},
         "e2e": {"value": ne_global / (e2e_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
@@ -315,6 +349,9 @@ def main():
         "setup": {"pattern_build_ms": pattern_ms, "jit_plus_first_launch_ms": jit_ms, "pattern_bytes": pat.bytes},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rb = ref_gpu_baseline(ctx, wl, mesh, pat)
+        if rb:
+            line["ref_gpu_baseline"] = rb
         line["cpu_baseline"] = {k: v for k, v in cpu_baseline_port(wl).items() if k != "seconds"}
     if rank == 0:
         print(json.dumps(line))

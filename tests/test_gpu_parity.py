@@ -334,3 +334,31 @@ def test_large_mesh_properties(ctx):
     assert (dense_rows - pat.spmv(v, x)).norm().item() <= 1e-12 * dense_rows.norm().item()
     assert torch.equal(v, form.assemble_csr(pat, mesh))
     form.close(); pat.close()
+
+
+# ------------------------------------------------ validation layer: SpMV + CG ---
+def test_cg_matches_oracle_history(ctx):
+    """cfg5 in miniature: assembled 3-D operator, b = A 1, CG from 0 — residual history vs the oracle's CG."""
+    import torch
+    from femx.dist import SlabOperator, make_slab
+    n = 10
+    mesh = ctx.box_mesh(n, n, n)
+    pat = femx.Pattern(ctx, mesh)
+    form = femx.Form(ctx, 3, femx.POISSON_MASS)
+    vals = form.assemble_csr(pat, mesh)
+    slab = make_slab(0, 1, n, (n + 1) ** 2)
+    op = SlabOperator(ctx, pat, vals, slab)
+    ones = torch.ones(pat.n_rows, dtype=torch.float64, device="cuda")
+    b = op.matvec(ones).clone()
+    x, hist = op.cg(b, 40)
+    X, Y, Z, conn = orc.box_mesh(n, n, n)
+    rp, ci = orc.pattern(conn, len(X))
+    ov = orc.assemble_csr(orc.POISSON_MASS, 3, 1, conn, X, Y, Z, rp, ci)
+    ob = orc.spmv(rp, ci, ov, np.ones(len(X)))
+    ox, ores = orc.cg(rp, ci, ov, ob, 40)
+    h = hist.cpu().numpy()
+    assert len(h) == len(ores) == 41
+    assert np.all(np.abs(h - ores) <= 1e-8 * ores[0] + 1e-6 * ores)
+    assert h[-1] / h[0] < 1e-6
+    assert np.abs(x.cpu().numpy() - 1.0).max() < 1e-5
+    form.close(); pat.close()
