@@ -2,8 +2,8 @@
 """BASELINE config 5: assemble the 3-D operator (grad.grad + u v on a Kuhn cube) on N GPUs as
 owned-row slabs, then validate it with SpMV + CG (halo exchange + all-reduce over NCCL).
 
-  python tools/cg_validate.py --n 256 --iters 100                       (1 GPU)
-  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/cg_validate.py --n 256
+  python tools/cg_validate.py --size 256 --cg-iters 100                       (1 GPU)
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/cg_validate.py --size 256
 
 Prints one JSON line: assembly time, SpMV time, CG time/iteration, residual history checkpoints,
 and the checks  A 1 = M 1 (row sums = lumped mass → sum = volume)  and  ||x - 1||_inf after CG on b = A 1.
@@ -21,8 +21,8 @@ for p in (ROOT, os.path.join(ROOT, "cuda-fem_b200")):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=256)
-    ap.add_argument("--iters", type=int, default=100)
+    ap.add_argument("--size", dest="n", type=int, default=256)
+    ap.add_argument("--cg-iters", dest="iters", type=int, default=100)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
