@@ -69,7 +69,7 @@ void emit_geometry(int dim, std::string* pro) {
          "  const real d2x = y3-y1, d2y = x1-x3;\n"
          "  const real d3x = -(d1x+d2x), d3y = -(d1y+d2y);\n"
          "  const real jac = d2y*d1x-d2x*d1y;\n"   // (x1-x3)(y2-y3)-(y1-y3)(x2-x3)
-         "  const real ijac = real(1.0)/jac;\n";
+         "  const real ijac = femx_rcp(jac);\n";
   } else {
     // X = x1 r + x2 s + x3 t + x4 (1-r-s-t); J[c][a] = dX_c/dref_a; d_a = jac * (row a of J^-1)
     o << "const real j00 = x1-x4, j01 = x2-x4, j02 = x3-x4;\n"
@@ -80,7 +80,7 @@ void emit_geometry(int dim, std::string* pro) {
          "  const real d3x = j10*j21-j11*j20, d3y = j01*j20-j00*j21, d3z = j00*j11-j01*j10;\n"
          "  const real d4x = -(d1x+d2x+d3x), d4y = -(d1y+d2y+d3y), d4z = -(d1z+d2z+d3z);\n"
          "  const real jac = j00*d1x+j01*d2x+j02*d3x;\n"
-         "  const real ijac = real(1.0)/jac;\n";
+         "  const real ijac = femx_rcp(jac);\n";
   }
   *pro += o.str();
 }
