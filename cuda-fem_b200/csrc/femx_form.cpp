@@ -262,6 +262,16 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
     o << " break;";
   }
   o << "\n";
+  // COO, thread per element: every row in straight-line code
+  o << "#define FEMX_COO_ROWS";
+  for (int li = 0; li < n; ++li) {
+    o << " \\\n    { real out[NDOF];";
+    if (has_q[li]) o << " _Pragma(\"unroll\") for (int j_ = 0; j_ < NDOF; ++j_) out[j_] = real(0);";
+    o << " FEMX_ROWC_" << li;
+    if (has_q[li]) o << " FEMX_QUAD(FEMX_ROWQ_" << li << ")";
+    o << " FEMX_COO_STORE(" << li << ") }";
+  }
+  o << "\n";
   // Numeric pass: one case per dof row li = a*ND + c of the element matrix.  In case (a, c) the
   // row's own node is local node a (coordinates sx,sy,sz) and the other vertices follow in
   // cyclic order (ox[j] = local node (a+1+j) % NN), so every name binding, the diagonal
@@ -300,6 +310,7 @@ int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, boo
     Variant v;
     const char* body = nullptr;
     if (kernel == "coo") body = kFemxJitCoo;
+    else if (kernel == "coo_e") body = kFemxJitCooElem;
     else if (kernel == "csr" || kernel == "csr_x" || kernel == "csr_s") body = kFemxJitCsr;
     else return femx_fail(f->ctx, FEMX_ERR_INVALID, "unknown kernel variant '%s'", kernel.c_str());
     v.source = "// femx JIT kernel '" + kernel + "' (generated)\n" + build_defines(f, kernel) +
@@ -352,7 +363,7 @@ int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, boo
       drv->GetErrorString(cr, &es);
       return femx_fail(f->ctx, FEMX_ERR_CUDA, "cuModuleLoadData: %s", es ? es : "?");
     }
-    std::string entry = kernel == "coo" ? "femx_coo" : "femx_csr";
+    std::string entry = kernel.compare(0, 3, "coo") == 0 ? "femx_coo" : "femx_csr";
     cr = drv->ModuleGetFunction(&v.fn, v.module, entry.c_str());
     if (cr != CUDA_SUCCESS) {
       drv->GetErrorString(cr, &es);
@@ -430,7 +441,7 @@ int make_form(femx_ctx* ctx, const femx_form_desc* d, femx_form** out) {
                        d->builtin, d->nd, d->dim);
     }
   }
-  int st = compile_variant(f, "coo", nullptr, ctx != nullptr);
+  int st = compile_variant(f, f->nd == 1 ? "coo_e" : "coo", nullptr, ctx != nullptr);
   if (st != FEMX_OK) {
     if (ctx) ctx->err = f->err.empty() ? ctx->err : f->err;
     delete f;
@@ -506,8 +517,10 @@ int femx_assemble_coo(femx_form* form, const femx_mesh_view* mesh, void* d_A, in
   if (mesh->n_elems == 0) return FEMX_OK;
   if (!mesh->d_conn && (!expanded || d_rowA || d_colA))
     return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_coo: connectivity is NULL");
+  // scalar forms: one thread per element, TMA bulk stores; vector forms: one thread per (element, row)
+  const bool per_elem = form->nd == 1;
   Variant* v = nullptr;
-  st = compile_variant(form, "coo", &v, true);
+  st = compile_variant(form, per_elem ? "coo_e" : "coo", &v, true);
   if (st != FEMX_OK) return st;
   const femx_driver* drv = femx_get_driver(nullptr);
   const void* const* c = expanded ? mesh->d_elem_xyz : mesh->d_node_xyz;
@@ -517,11 +530,30 @@ int femx_assemble_coo(femx_form* form, const femx_mesh_view* mesh, void* d_A, in
   long long ne = mesh->n_elems;
   const int32_t* conn = mesh->d_conn;
   void* args[] = {&conn, &X, &Y, &Z, &cs, &ex, &d_A, &d_rowA, &d_colA, &ne};
-  long long threads = ne * form->n;
-  long long blocks = (threads + 255) / 256;
-  if (blocks > 2147483647LL)
-    return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED, "femx_assemble_coo: %lld blocks exceed grid limit", blocks);
-  CUresult cr = drv->LaunchKernel(v->fn, (unsigned)blocks, 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr);
+  CUresult cr;
+  if (per_elem) {
+    const size_t rs = form->dtype == FEMX_F32 ? 4 : 8;
+    const unsigned smem = (unsigned)(128 * form->n * form->n * (rs + 8));
+    if ((int)smem > v->smem_set && smem > 48 * 1024) {
+      if (drv->FuncSetAttribute(v->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS)
+        return femx_fail(form->ctx, FEMX_ERR_CUDA, "cuFuncSetAttribute(smem=%u) failed", smem);
+      v->smem_set = (int)smem;
+    }
+    if (!v->carveout_set) {
+      drv->FuncSetAttribute(v->fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100);
+      v->carveout_set = 1;
+    }
+    long long blocks = (ne + 127) / 128;
+    if (blocks > 2147483647LL)
+      return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED, "femx_assemble_coo: %lld blocks exceed grid limit", blocks);
+    cr = drv->LaunchKernel(v->fn, (unsigned)blocks, 1, 1, 128, 1, 1, smem, (CUstream)stream, args, nullptr);
+  } else {
+    long long threads = ne * form->n;
+    long long blocks = (threads + 255) / 256;
+    if (blocks > 2147483647LL)
+      return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED, "femx_assemble_coo: %lld blocks exceed grid limit", blocks);
+    cr = drv->LaunchKernel(v->fn, (unsigned)blocks, 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr);
+  }
   if (cr != CUDA_SUCCESS) {
     const char* es = nullptr;
     drv->GetErrorString(cr, &es);

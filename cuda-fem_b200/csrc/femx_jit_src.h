@@ -106,6 +106,83 @@ femx_coo(const int* __restrict__ conn, const real* __restrict__ X,
 }
 )FEMX";
 
+// ---- kernel ABI #1, scalar forms: one thread per ELEMENT -------------------------------
+// Geometry is evaluated once per element, all n*n entries are produced by straight-line code
+// (no divergent row switch), staged in shared memory in slot order and written with three TMA
+// bulk stores per 128-element tile (values, rows, columns): the global stores are perfectly
+// coalesced and cost no LSU work.  Same slot order / orientation as femx_coo.
+static const char* const kFemxJitCooElem = R"FEMX(
+#define FEMX_COO_TILE 128
+#define N2 (NDOF * NDOF)
+#define FEMX_COO_STORE(LI)                                                     \
+  _Pragma("unroll") for (int lj = 0; lj < NDOF; ++lj) {                        \
+    sA[t * N2 + (LI) * NDOF + lj] = out[lj];                                   \
+    sR[t * N2 + (LI) * NDOF + lj] = ND * nodes[(LI) / ND] + (LI) % ND;         \
+    sC[t * N2 + (LI) * NDOF + lj] = ND * nodes[lj / ND] + lj % ND;             \
+  }
+
+extern "C" __global__ void __launch_bounds__(FEMX_COO_TILE)
+femx_coo(const int* __restrict__ conn, const real* __restrict__ X,
+         const real* __restrict__ Y, const real* __restrict__ Z, const i64 cs,
+         const int expanded, real* __restrict__ A, int* __restrict__ rowA,
+         int* __restrict__ colA, const i64 n_elems) {
+  extern __shared__ __align__(128) unsigned char femx_smem[];
+  real* sA = reinterpret_cast<real*>(femx_smem);
+  int* sR = reinterpret_cast<int*>(sA + FEMX_COO_TILE * N2);
+  int* sC = sR + FEMX_COO_TILE * N2;
+  const i64 e0 = (i64)blockIdx.x * FEMX_COO_TILE;
+  const int ne_t = (int)min((i64)FEMX_COO_TILE, n_elems - e0);
+  const int t = threadIdx.x;
+  if (t < ne_t) {
+    const i64 e = e0 + t;
+    int nodes[NN];
+#pragma unroll
+    for (int a = 0; a < NN; ++a) nodes[a] = conn ? __ldg(conn + e * NN + a) : 0;
+    real cx[NN], cy[NN], cz[NN];
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+      const i64 p = expanded ? (e * NN + a) : (i64)nodes[a] * cs;
+      cx[a] = __ldg(X + p);
+      cy[a] = __ldg(Y + p);
+      cz[a] = DIM == 3 ? __ldg(Z + p) : real(0);
+    }
+    const real x1 = cx[0], x2 = cx[1], x3 = cx[2];
+    const real y1 = cy[0], y2 = cy[1], y3 = cy[2];
+#if DIM == 3
+    const real x4 = cx[3], y4 = cy[3];
+    const real z1 = cz[0], z2 = cz[1], z3 = cz[2], z4 = cz[3];
+#endif
+    FEMX_PROLOGUE
+    FEMX_COO_ROWS
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const i64 s0 = e0 * N2;  // first slot of the tile
+  if (ne_t == FEMX_COO_TILE) {
+    // full tile: sizes and addresses are multiples of 16 bytes
+    if (t == 0) {
+      if (A)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(A + s0), "r"((unsigned)__cvta_generic_to_shared(sA)), "r"((unsigned)(FEMX_COO_TILE * N2 * sizeof(real))) : "memory");
+      if (rowA)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(rowA + s0), "r"((unsigned)__cvta_generic_to_shared(sR)), "r"((unsigned)(FEMX_COO_TILE * N2 * 4)) : "memory");
+      if (colA)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(colA + s0), "r"((unsigned)__cvta_generic_to_shared(sC)), "r"((unsigned)(FEMX_COO_TILE * N2 * 4)) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else {
+    for (int j = t; j < ne_t * N2; j += FEMX_COO_TILE) {
+      if (A) A[s0 + j] = sA[j];
+      if (rowA) rowA[s0 + j] = sR[j];
+      if (colA) colA[s0 + j] = sC[j];
+    }
+  }
+}
+)FEMX";
+
 // ---- kernel ABI #2: deterministic numeric pass into CSR --------------------
 // A CTA owns FEMX_TILE_NODES consecutive node rows (x ND dof rows).  Thread
 // (node, c) walks the node's incident elements in ascending element order,
