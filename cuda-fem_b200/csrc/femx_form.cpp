@@ -39,6 +39,8 @@ struct femx_form {
   int integrated = 0;  // entries are final element-matrix expressions (no quadrature applied)
   std::string prologue;
   std::vector<std::string> entries;  // n*n
+  std::vector<std::string> rhs;      // n load-vector integrands (may be empty)
+  int rhs_integrated = 0;
   int nq = 0;
   std::vector<double> qw, qr, qs, qt, qu;
   std::map<std::string, Variant> variants;
@@ -155,6 +157,14 @@ int emit_builtin(femx_form* f, const femx_form_desc* d) {
       }
       f->entries[(size_t)li * n + lj] = o.str();
     }
+  // constant source: b[a,c] = f_c * (sum_q w_q phi_a(q)) * jac, pre-integrated like the matrix
+  f->rhs.assign(n, "");
+  f->rhs_integrated = 1;
+  for (int a = 0; a < nn; ++a) {
+    double m = 0.0;
+    for (int q = 0; q < f->nq; ++q) m += f->qw[q] * phi_at(f, a, q);
+    for (int c = 0; c < nd; ++c) f->rhs[(size_t)a * nd + c] = num(d->rhs_vec[c] * m) + "*jac";
+  }
   return FEMX_OK;
 }
 
@@ -262,6 +272,37 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
     o << " break;";
   }
   o << "\n";
+  // Load vector: case per local node a; racc[c] += integrated rhs entry (a*ND + c)
+  o << "#define FEMX_RHS_CASES";
+  if (!f->rhs.empty()) {
+    for (int a = 0; a < f->nn; ++a) {
+      o << " \\\n    case " << a << ": {";
+      for (int k = 0; k < f->dim; ++k) {
+        const char AXU = (char)toupper("xyz"[k]);
+        o << " const real " << "xyz"[k] << a + 1 << " = S" << AXU << ";";
+        for (int j = 0; j < f->nn - 1; ++j)
+          o << " const real " << "xyz"[k] << (a + 1 + j) % f->nn + 1 << " = O" << AXU << "[" << j << "];";
+      }
+      o << " \\\n      FEMX_PROLOGUE";
+      for (int c = 0; c < f->nd; ++c) {
+        const std::string& e = f->rhs[(size_t)a * f->nd + c];
+        if (f->rhs_integrated)
+          o << " \\\n      racc[" << c << "] += (" << e << ");";
+        else if (!depends_on_q(e))
+          o << " \\\n      racc[" << c << "] += " << num(W) << "*(" << e << ");";
+        else {
+          o << " \\\n      {";
+          for (int q = 0; q < f->nq; ++q)
+            o << " { const real r = " << num(f->qr[q]) << ", s = " << num(f->qs[q]) << ", t = " << num(f->qt[q])
+              << ", u = " << num(f->qu[q]) << "; (void)r; (void)s; (void)t; (void)u; racc[" << c << "] += "
+              << num(f->qw[q]) << "*(" << e << "); }";
+          o << " }";
+        }
+      }
+      o << " } break;";
+    }
+  }
+  o << "\n";
   // COO, thread per element: every row in straight-line code
   o << "#define FEMX_COO_ROWS";
   for (int li = 0; li < n; ++li) {
@@ -311,6 +352,7 @@ int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, boo
     const char* body = nullptr;
     if (kernel == "coo") body = kFemxJitCoo;
     else if (kernel == "coo_e") body = kFemxJitCooElem;
+    else if (kernel == "rhs") body = kFemxJitRhs;
     else if (kernel == "csr" || kernel == "csr_x" || kernel == "csr_s") body = kFemxJitCsr;
     else return femx_fail(f->ctx, FEMX_ERR_INVALID, "unknown kernel variant '%s'", kernel.c_str());
     v.source = "// femx JIT kernel '" + kernel + "' (generated)\n" + build_defines(f, kernel) +
@@ -363,7 +405,7 @@ int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, boo
       drv->GetErrorString(cr, &es);
       return femx_fail(f->ctx, FEMX_ERR_CUDA, "cuModuleLoadData: %s", es ? es : "?");
     }
-    std::string entry = kernel.compare(0, 3, "coo") == 0 ? "femx_coo" : "femx_csr";
+    std::string entry = kernel.compare(0, 3, "coo") == 0 ? "femx_coo" : (kernel == "rhs" ? "femx_rhs" : "femx_csr");
     cr = drv->ModuleGetFunction(&v.fn, v.module, entry.c_str());
     if (cr != CUDA_SUCCESS) {
       drv->GetErrorString(cr, &es);
@@ -439,6 +481,19 @@ int make_form(femx_ctx* ctx, const femx_form_desc* d, femx_form** out) {
       delete f;
       return femx_fail(ctx, st, "femx_form_compile: bad built-in form %d (nd=%d, dim=%d)",
                        d->builtin, d->nd, d->dim);
+    }
+  }
+  if (d->rhs_entries) {  // explicit load-vector integrands (reference semantics: weighted and summed)
+    f->rhs.clear();
+    f->rhs_integrated = f->builtin == FEMX_FORM_CUSTOM ? f->integrated : 0;
+    for (int k = 0; k < f->n; ++k) {
+      if (!d->rhs_entries[k]) {
+        delete f;
+        return femx_fail(ctx, FEMX_ERR_INVALID, "femx_form_compile: rhs_entries[%d] is NULL", k);
+      }
+      std::string s = d->rhs_entries[k];
+      while (!s.empty() && (s.back() == '\n' || s.back() == ';' || s.back() == ' ')) s.pop_back();
+      f->rhs.push_back(s);
     }
   }
   int st = compile_variant(f, f->nd == 1 ? "coo_e" : "coo", nullptr, ctx != nullptr);
@@ -558,6 +613,45 @@ int femx_assemble_coo(femx_form* form, const femx_mesh_view* mesh, void* d_A, in
     const char* es = nullptr;
     drv->GetErrorString(cr, &es);
     return femx_fail(form->ctx, FEMX_ERR_CUDA, "femx_assemble_coo: launch failed: %s", es ? es : "?");
+  }
+  return FEMX_OK;
+}
+
+int femx_assemble_rhs(femx_form* form, const femx_pattern* pat, const femx_mesh_view* mesh, void* d_rhs,
+                      void* stream) {
+  if (!form || !pat) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_assemble_rhs: NULL argument");
+  if (form->rhs.empty())
+    return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_rhs: the form has no load-vector integrands");
+  bool expanded = false;
+  int st = check_mesh(form, mesh, &expanded);
+  if (st != FEMX_OK) return st;
+  if (pat->nn != form->nn || pat->nd != form->nd)
+    return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_rhs: pattern does not match the form");
+  if (mesh->n_nodes != pat->n_nodes || mesh->n_elems != pat->n_elems)
+    return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_rhs: mesh sizes differ from the pattern's");
+  if (pat->n_rows == 0) return FEMX_OK;
+  if (!d_rhs) return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_rhs: d_rhs is NULL");
+  Variant* v = nullptr;
+  st = compile_variant(form, "rhs", &v, true);
+  if (st != FEMX_OK) return st;
+  const femx_driver* drv = femx_get_driver(nullptr);
+  const void* const* c = expanded ? mesh->d_elem_xyz : mesh->d_node_xyz;
+  const void* X = c[0]; const void* Y = c[1]; const void* Z = c[2];
+  long long cs = mesh->node_stride ? mesh->node_stride : 1;
+  int ex = expanded ? 1 : 0;
+  int n_rows = (int)pat->n_rows;
+  const int2* rowinfo = pat->d_rowinfo;
+  const int32_t* slice_ptr = pat->d_slice_ptr;
+  const int32_t* col = pat->d_col_idx;
+  const uint32_t* code = pat->d_sell_code;
+  const int32_t* pelem = pat->d_sell_elem;
+  void* args[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &ex, &d_rhs, &n_rows};
+  unsigned blocks = (unsigned)((pat->n_rows + 127) / 128);
+  CUresult cr = drv->LaunchKernel(v->fn, blocks, 1, 1, 128, 1, 1, 0, (CUstream)stream, args, nullptr);
+  if (cr != CUDA_SUCCESS) {
+    const char* es = nullptr;
+    drv->GetErrorString(cr, &es);
+    return femx_fail(form->ctx, FEMX_ERR_CUDA, "femx_assemble_rhs: launch failed: %s", es ? es : "?");
   }
   return FEMX_OK;
 }

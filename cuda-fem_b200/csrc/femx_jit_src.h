@@ -414,3 +414,57 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   }
 }
 )FEMX";
+
+// ---- load vector: one thread per node row, ND components --------------------------------
+// Same incidence walk as femx_csr (SELL-32 codes, ascending element order) but the result is
+// one value per dof, so there is no shared-memory image: codes and columns are read straight
+// from global memory (coalesced / L1).
+static const char* const kFemxJitRhs = R"FEMX(
+extern "C" __global__ void __launch_bounds__(128)
+femx_rhs(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
+         const int* __restrict__ col_loc, const unsigned* __restrict__ sell_code,
+         const int* __restrict__ sell_elem, const real* __restrict__ X,
+         const real* __restrict__ Y, const real* __restrict__ Z, const i64 cs, const int expanded,
+         real* __restrict__ rhs, const int n_rows) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const int2 r0 = __ldg(&rowinfo[row]);
+  const int* cols = col_loc + r0.x;
+  const int sp = __ldg(slice_ptr + (row >> 5)) + (row & 31);
+  real racc[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) racc[d] = real(0);
+  for (int it = 0; it < r0.y; ++it) {
+    const unsigned code = __ldg(sell_code + sp + it * 32);
+    const int li = (code >> 28) & 3;
+    real SX, SY, SZ = real(0), OX[NN - 1], OY[NN - 1], OZ[NN - 1];
+    if (expanded) {
+      const int ea = __ldg(sell_elem + sp + it * 32);
+      const int e0 = ea - li;
+      SX = __ldg(X + ea); SY = __ldg(Y + ea);
+      if (DIM == 3) SZ = __ldg(Z + ea);
+#pragma unroll
+      for (int j = 0; j < NN - 1; ++j) {
+        int b = li + 1 + j; b -= b >= NN ? NN : 0;
+        OX[j] = __ldg(X + e0 + b); OY[j] = __ldg(Y + e0 + b);
+        OZ[j] = DIM == 3 ? __ldg(Z + e0 + b) : real(0);
+      }
+    } else {
+      const i64 ps = (i64)__ldg(cols + ((code >> 21) & 127)) * cs;
+      SX = __ldg(X + ps); SY = __ldg(Y + ps);
+      if (DIM == 3) SZ = __ldg(Z + ps);
+#pragma unroll
+      for (int j = 0; j < NN - 1; ++j) {
+        const i64 p = (i64)__ldg(cols + ((code >> (7 * j)) & 127)) * cs;
+        OX[j] = __ldg(X + p); OY[j] = __ldg(Y + p);
+        OZ[j] = DIM == 3 ? __ldg(Z + p) : real(0);
+      }
+    }
+    switch (li) {
+      FEMX_RHS_CASES
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < ND; ++d) rhs[(i64)row * ND + d] = racc[d];
+}
+)FEMX";

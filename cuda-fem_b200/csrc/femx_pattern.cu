@@ -120,13 +120,13 @@ int exclusive_scan(femx_ctx* ctx, const int* d_in, int64_t n, int* d_out, long l
   }
   int nt = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
   long long* d_sums = nullptr;
-  FEMX_CUDA_OK(ctx, cudaMalloc(&d_sums, sizeof(long long) * (nt + 1)));
+  FEMX_CUDA_OK(ctx, cudaMallocAsync(&d_sums, sizeof(long long) * (nt + 1), st));
   scan_tile_sums<<<nt, SCAN_THREADS, 0, st>>>(d_in, n, d_sums);
   scan_sums<<<1, SCAN_THREADS, 0, st>>>(d_sums, nt, d_sums + nt);
   scan_apply<<<nt, SCAN_THREADS, 0, st>>>(d_in, n, d_sums, d_out);
   cudaError_t e = cudaMemcpyAsync(h_total, d_sums + nt, sizeof(long long), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(d_sums);
+  cudaFreeAsync(d_sums, st);
   FEMX_CUDA_OK(ctx, e);
   return FEMX_OK;
 }
@@ -330,6 +330,18 @@ int dev_alloc(femx_ctx* ctx, T** p, int64_t n, int64_t* bytes) {
   return FEMX_OK;
 }
 
+// temporaries of the symbolic pass come from the stream-ordered pool (no device-wide sync per free)
+template <class T>
+int tmp_alloc(femx_ctx* ctx, T** p, int64_t n, cudaStream_t st) {
+  size_t b = sizeof(T) * (size_t)(n > 0 ? n : 1);
+  cudaError_t e = cudaMallocAsync((void**)p, b, st);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return femx_fail(ctx, FEMX_ERR_NOMEM, "cudaMallocAsync(%zu bytes) failed: %s", b, cudaGetErrorString(e));
+  }
+  return FEMX_OK;
+}
+
 inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
@@ -367,8 +379,8 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
   unsigned* d_pair_code = nullptr;
   int st_code = FEMX_OK;
   auto cleanup = [&]() {
-    cudaFree(d_cnt); cudaFree(d_pair_ptr); cudaFree(d_row_ptr); cudaFree(d_flags);
-    cudaFree(d_pair_elem); cudaFree(d_pair_code);
+    cudaFreeAsync(d_cnt, st); cudaFreeAsync(d_pair_ptr, st); cudaFreeAsync(d_row_ptr, st); cudaFreeAsync(d_flags, st);
+    cudaFreeAsync(d_pair_elem, st); cudaFreeAsync(d_pair_code, st);
   };
 #define PB_TRY(x)                                   \
   do {                                              \
@@ -384,10 +396,10 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
     }                                                                                  \
   } while (0)
 
-  PB_TRY(dev_alloc(ctx, &d_cnt, nr + 1, nullptr));
-  PB_TRY(dev_alloc(ctx, &d_pair_ptr, nr + 1, nullptr));
-  PB_TRY(dev_alloc(ctx, &d_row_ptr, nr + 1, nullptr));
-  PB_TRY(dev_alloc(ctx, &d_flags, 4, nullptr));  // [0] err, [1] max_row, [2] max tile nnz
+  PB_TRY(tmp_alloc(ctx, &d_cnt, nr + 1, st));
+  PB_TRY(tmp_alloc(ctx, &d_pair_ptr, nr + 1, st));
+  PB_TRY(tmp_alloc(ctx, &d_row_ptr, nr + 1, st));
+  PB_TRY(tmp_alloc(ctx, &d_flags, 4, st));  // [0] err, [1] max_row, [2] max tile nnz
   PB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (nr + 1), st));
   PB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, st));
 
@@ -406,8 +418,8 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
                      (long long)n_nodes);
   }
   p->n_pairs = n_pairs;
-  PB_TRY(dev_alloc(ctx, &d_pair_elem, n_pairs, nullptr));
-  PB_TRY(dev_alloc(ctx, &d_pair_code, n_pairs, nullptr));
+  PB_TRY(tmp_alloc(ctx, &d_pair_elem, n_pairs, st));
+  PB_TRY(tmp_alloc(ctx, &d_pair_code, n_pairs, st));
   PB_TRY(dev_alloc(ctx, &p->d_rowinfo, nr + 1, &p->bytes));
 
   // 3: bucket fill + sort
@@ -453,14 +465,14 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
   {
     const int64_t n_slices = (nr + 31) / 32;
     int* d_ssize = nullptr;
-    PB_TRY(dev_alloc(ctx, &d_ssize, n_slices + 1, nullptr));
+    PB_TRY(tmp_alloc(ctx, &d_ssize, n_slices + 1, st));
     st_code = dev_alloc(ctx, &p->d_slice_ptr, n_slices + 1, &p->bytes);
     long long n_sell = 0;
     if (st_code == FEMX_OK) {
       if (n_slices > 0) slice_sizes<<<nblocks(n_slices, 8), 256, 0, st>>>(d_pair_ptr, (int)nr, (int)n_slices, d_ssize);
       st_code = exclusive_scan(ctx, d_ssize, n_slices, p->d_slice_ptr, &n_sell, st);
     }
-    cudaFree(d_ssize);
+    cudaFreeAsync(d_ssize, st);
     if (st_code != FEMX_OK) { cleanup(); femx_pattern_destroy(p); return st_code; }
     if (n_sell >= (1LL << 31) - 1) {
       cleanup(); femx_pattern_destroy(p);

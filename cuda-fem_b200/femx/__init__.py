@@ -33,6 +33,7 @@ class _FormDesc(C.Structure):
         ("nq", C.c_int), ("qw", C.POINTER(C.c_double)), ("qr", C.POINTER(C.c_double)),
         ("qs", C.POINTER(C.c_double)), ("qt", C.POINTER(C.c_double)),
         ("qu", C.POINTER(C.c_double)), ("fmad", C.c_int), ("integrated", C.c_int),
+        ("rhs_entries", C.POINTER(C.c_char_p)), ("rhs_vec", C.c_double * 3),
     ]
 
 
@@ -52,7 +53,7 @@ SYMBOLS = [
     "femx_mesh_rectangle", "femx_mesh_expand", "femx_mesh_box",
     "femx_assemble_coo", "femx_pattern_build", "femx_pattern_destroy", "femx_pattern_info",
     "femx_pattern_bytes", "femx_pattern_export_csr", "femx_pattern_export_ell",
-    "femx_assemble_csr", "femx_csr_to_ell", "femx_spmv", "femx_dot2", "femx_axpy_ratio",
+    "femx_assemble_csr", "femx_assemble_rhs", "femx_csr_to_ell", "femx_spmv", "femx_dot2", "femx_axpy_ratio",
     "femx_xpby_ratio",
 ]
 
@@ -214,7 +215,7 @@ class Form:
     fea_symbolic_nvrtc_sparse.cpp:307-356, 506-561)."""
 
     def __init__(self, ctx, dim, builtin=POISSON, nd=1, dtype=F64, params=(), entries=None, prologue=None,
-                 rule=None, fmad=True, offline=False, integrated=False):
+                 rule=None, fmad=True, offline=False, integrated=False, rhs=None, rhs_vec=(1.0, 0.0, 0.0)):
         self.ctx = ctx
         self.dim, self.nn, self.nd, self.dtype = dim, dim + 1, nd, dtype
         self.n = self.nn * nd
@@ -230,6 +231,12 @@ class Form:
             d.entries = C.cast(arr, C.POINTER(C.c_char_p))
             d.builtin = CUSTOM
         d.prologue = prologue.encode() if prologue else None
+        if rhs is not None:
+            rarr = (C.c_char_p * len(rhs))(*[s_.encode() for s_ in rhs])
+            keep.append(rarr)
+            d.rhs_entries = C.cast(rarr, C.POINTER(C.c_char_p))
+        for i in range(3):
+            d.rhs_vec[i] = float(rhs_vec[i]) if i < len(rhs_vec) else 0.0
         if rule is not None:
             cols = [list(map(float, c)) if c is not None else None for c in rule]
             while len(cols) < 5:
@@ -307,6 +314,15 @@ class Form:
         v = mesh.view()
         self._check(lib().femx_assemble_csr(self.h, pattern.h, C.byref(v), _vp(values), _stream(stream)))
         return values
+
+    def assemble_rhs(self, pattern, mesh, out=None, stream=None):
+        """Load vector b (one value per dof row of the pattern), deterministic."""
+        import torch
+        if out is None:
+            out = torch.empty(pattern.n_rows, dtype=self._tdtype(), device=torch.device("cuda", self.ctx.device))
+        v = mesh.view()
+        self._check(lib().femx_assemble_rhs(self.h, pattern.h, C.byref(v), _vp(out), _stream(stream)))
+        return out
 
     def close(self):
         if self.h:

@@ -109,6 +109,13 @@ typedef struct femx_form_desc {
    * semantics: weighted by w_q and summed over the rule); 1 = entries are the
    * final element-matrix expressions, no quadrature applied. */
   int integrated;
+  /* Load vector (optional).  n strings rhs_entries[li] = integrand of b[dof li] = f * phi_li * jac
+   * over the same names — what WeakForm::build generates as rhs[j] and then discards
+   * (fea_symbolic_nvrtc_sparse.cpp:346-351; recorded output fea_symbolic.cu:335,339,343).
+   * Built-in forms without strings use the constant source rhs_vec (scalar forms: rhs_vec[0];
+   * elasticity: body force per component). */
+  const char* const* rhs_entries;
+  double rhs_vec[3];
 } femx_form_desc;
 
 /* Replaces WeakForm::build + nvrtcCreateProgram … cuModuleGetFunction
@@ -230,6 +237,12 @@ int femx_pattern_export_ell(const femx_pattern* pat, int width, int32_t* d_len,
  * d_values has nnz entries of the form's dtype and is fully overwritten. */
 int femx_assemble_csr(femx_form* form, const femx_pattern* pat,
                       const femx_mesh_view* mesh, void* d_values, void* stream);
+/* Load vector b[dof] = sum over incident elements of the integrated rhs entry, accumulated in
+ * ascending element order by the thread owning the row (deterministic, no atomics).  d_rhs has
+ * n_rows entries of the form's dtype.  No reference kernel exists (the reference drops its RHS
+ * strings); the author's intended host loop is the commented block fea_kernal.cu:193-214. */
+int femx_assemble_rhs(femx_form* form, const femx_pattern* pat, const femx_mesh_view* mesh,
+                      void* d_rhs, void* stream);
 /* CSR values → the reference's ELL value layout A[i*width + j] (zero padded). */
 int femx_csr_to_ell(const femx_pattern* pat, int dtype, int width,
                     const void* d_values, void* d_ell, void* stream);

@@ -226,6 +226,52 @@ void orc_element_matrix(int form, int dim, int nd, const double* params,
   }
 }
 
+/* ---- load vector.  WeakForm::build also generates rhs[j] = f*phi_j*jac
+ * (fea_symbolic_nvrtc_sparse.cpp:346-351; recorded output fea_symbolic.cu:335,339,343) and then
+ * discards it.  b[dof] = sum_e sum_q w_q f(x_q) phi_li(q) jac, scatter-add in element order.
+ *   kind 0: constant source, f = fvec[comp]         (scalar forms: fvec[0])
+ *   kind 1: the reference's f = -2 (x^2 + y^2) + 36  (fea_symbolic_nvrtc_sparse.cpp:495), 2-D scalar */
+void orc_assemble_rhs(int kind, int dim, int nd, const double* fvec, int64_t n_elems,
+                      const int32_t* conn, const double* X, const double* Y, const double* Z,
+                      int64_t n_dofs, double* b, double* b_elem) {
+  int nn = dim + 1;
+  const double *qw, *qr, *qs, *qt = NULL;
+  int nq;
+  if (dim == 2) { nq = 7; qw = TRI_W; qr = TRI_R; qs = TRI_S; }
+  else { nq = 4; qw = TET_W; qr = TET_R; qs = TET_S; qt = TET_T; }
+  for (int64_t i = 0; i < n_dofs; i++) b[i] = 0.0;
+  for (int64_t e = 0; e < n_elems; e++) {
+    double x[4], y[4], z[4] = {0, 0, 0, 0}, jac, g[4][3];
+    for (int a = 0; a < nn; a++) {
+      int32_t nd_ = conn[nn * e + a];
+      x[a] = X[nd_]; y[a] = Y[nd_];
+      if (dim == 3) z[a] = Z[nd_];
+    }
+    if (dim == 2) { double g2[3][2]; tri_grads(x, y, &jac, g2); }
+    else tet_grads(x, y, z, &jac, g);
+    for (int a = 0; a < nn; a++)
+      for (int c = 0; c < nd; c++) {
+        double acc = 0.0;
+        for (int q = 0; q < nq; q++) {
+          double phi[4];
+          phi[0] = qr[q]; phi[1] = qs[q];
+          if (dim == 2) phi[2] = 1.0 - qr[q] - qs[q];
+          else { phi[2] = qt[q]; phi[3] = 1.0 - qr[q] - qs[q] - qt[q]; }
+          double f;
+          if (kind == 0) f = fvec[c];
+          else {
+            double xq = 0.0, yq = 0.0;
+            for (int k = 0; k < nn; k++) { xq += x[k] * phi[k]; yq += y[k] * phi[k]; }
+            f = -2.0 * (xq * xq + yq * yq) + 36.0;
+          }
+          acc += qw[q] * (f * phi[a] * jac);
+        }
+        if (b_elem) b_elem[(e * nn + a) * nd + c] = acc;
+        b[(int64_t)nd * conn[nn * e + a] + c] += acc;
+      }
+  }
+}
+
 /* ---- COO surface: slot = e*n*n + li*n + lj, rowA = dof(li), colA = dof(lj)
  * (fea_symbolic_nvrtc_sparse.cpp:444-445, 473-477).  Coordinates are node-indexed
  * (X[node]); dof = nd*node + comp. */

@@ -108,6 +108,18 @@ def assemble_coo(form, dim, nd, conn, X, Y, Z=None, params=None):
     return A, row, col
 
 
+def assemble_rhs(kind, dim, nd, conn, X, Y, Z=None, fvec=(1.0, 0.0, 0.0)):
+    """Load vector: kind 0 constant source fvec, kind 1 the reference's f = -2(x^2+y^2)+36."""
+    conn = np.ascontiguousarray(conn, np.int32)
+    ne, nn = conn.shape
+    f = np.zeros(3)
+    f[: len(fvec)] = fvec
+    b = np.empty(len(X) * nd)
+    be = np.empty(ne * nn * nd)
+    lib().orc_assemble_rhs(kind, dim, nd, _p(f), _i64(ne), _p(conn), _p(X), _p(Y), _p(Z), _i64(len(b)), _p(b), _p(be))
+    return b, be.reshape(ne, nn * nd)
+
+
 def pattern(conn, n_nodes):
     """Node-level CSR pattern (row_ptr int64, col_idx int32) of getNeighborNodesList."""
     conn = np.ascontiguousarray(conn, np.int32)

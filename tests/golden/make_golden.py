@@ -6,6 +6,8 @@ What is pinned
                               into its kernels (fea_test_sm_sym_sparse2.cu:188-205;
                               identical text at fea_test_sm_sym_sparse.cu:153-170) and the
                               quadrature literals (:30-33).
+  (+ "rhs")                   the 3 RHS strings rhs[j] = f*phi_j*jac the reference generated and
+                              discarded (fea_symbolic.cu:335,339,343)
   ref_poisson2d_*.npz         those strings evaluated VERBATIM (python eval, float64,
                               powf→pow) on RectangleMesh inputs built with the reference's
                               mesh semantics (fea_test_sm_sym_sparse2.cu:119-165), summed
@@ -35,11 +37,17 @@ def parse_reference():
             assert body.startswith("return ") and body.endswith(";")
             exprs[int(m.group(1))] = body[len("return "):-1]
     assert sorted(exprs) == list(range(9))
+    # RHS strings rhs[j] = f*phi_j*jac, f = -2(x^2+y^2)+36: generated and then DISCARDED by the
+    # reference (fea_symbolic_nvrtc_sparse.cpp:346-351); its recorded output: fea_symbolic.cu:335,339,343
+    sym = open("/root/reference/fea_symbolic.cu").read().splitlines()
+    rhs = [sym[k - 1].strip() for k in (335, 339, 343)]
+    assert all("18.0" in r and "std::" not in r for r in rhs)
     lit = {}
     for name in ("triW", "triR", "triS", "triT"):
         line = next(l for l in src if f"float {name}[7]" in l)
         vals = re.search(r"\{(.*)\}", line).group(1)
         lit[name] = [v.strip().rstrip("f") for v in vals.split(",")]
+    lit["rhs"] = rhs
     return [exprs[k] for k in range(9)], lit
 
 
@@ -93,8 +101,29 @@ def evaluate(exprs, lit, X, Y, conn):
     return A
 
 
+def evaluate_rhs(lit, X, Y, conn):
+    w = [float(v) for v in lit["triW"]]
+    r_, s_, t_ = ([float(v) for v in lit[k]] for k in ("triR", "triS", "triT"))
+    codes = [compile(e, f"<rhs{k}>", "eval") for k, e in enumerate(lit["rhs"])]
+    B = np.zeros((len(conn), 3))
+    for e, (a, b, c) in enumerate(conn):
+        env = dict(x1=X[a], x2=X[b], x3=X[c], y1=Y[a], y2=Y[b], y3=Y[c], pow=pow)
+        for k in range(3):
+            acc = 0.0
+            for q in range(7):
+                env.update(r=r_[q], s=s_[q], t=t_[q])
+                acc += w[q] * eval(codes[k], {"__builtins__": {}}, env)
+            B[e, k] = acc
+    return B
+
+
 def make_case(name, exprs, lit, X, Y, conn):
     A = evaluate(exprs, lit, X, Y, conn)
+    B = evaluate_rhs(lit, X, Y, conn)
+    bvec = np.zeros(len(X))
+    for e in range(len(conn)):          # element order (the loop the author sketched: fea_kernal.cu:193-214)
+        for k in range(3):
+            bvec[conn[e, k]] += B[e, k]
     ne = len(conn)
     row = np.empty((ne, 9), np.int32)
     col = np.empty((ne, 9), np.int32)
@@ -114,7 +143,7 @@ def make_case(name, exprs, lit, X, Y, conn):
             gi, gj = row[e, k], col[e, k]
             ell_val[gi, nb[gi].index(gj)] += A[e, k]
     np.savez_compressed(os.path.join(HERE, name), X=X, Y=Y, conn=conn, A=A.ravel(), rowA=row.ravel(),
-                        colA=col.ravel(), ell_len=ell_len, ell_idx=ell_idx, ell_val=ell_val)
+                        colA=col.ravel(), ell_len=ell_len, ell_idx=ell_idx, ell_val=ell_val, rhs_elem=B, rhs=bvec)
     print(name, "elements", ne, "nnz", int(ell_len.sum()))
 
 

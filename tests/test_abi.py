@@ -115,3 +115,14 @@ def test_sass_uses_fp64_pipe_and_no_local_memory():
     sass = subprocess.check_output(["cuobjdump", "-sass", path]).decode()
     assert "DFMA" in sass and "STS" in sass
     f.close()
+
+
+def test_offline_jit_rhs_kernel(golden_dir):
+    import json
+    j = json.load(open(os.path.join(golden_dir, "ref_integrand_strings.json")))
+    f = femx.Form(None, 2, entries=j["integrand"], rhs=j["rhs"], offline=True)
+    assert f.cubin("rhs")[:4] == b"\x7fELF" and "femx_rhs" in f.source
+    f.close()
+    f = femx.Form(None, 3, femx.ELASTICITY, nd=3, params=(1.0, 0.5), rhs_vec=(0.0, 0.0, -9.81), offline=True)
+    assert f.cubin("rhs")[:4] == b"\x7fELF"
+    f.close()

@@ -11,6 +11,7 @@ import femx
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 TOL64 = 1e-12
 TOL32 = 1e-5
@@ -362,3 +363,66 @@ def test_cg_matches_oracle_history(ctx):
     assert h[-1] < 1e-2 * h.max()
     assert np.abs(x.cpu().numpy() - ox).max() < 1e-8
     form.close(); pat.close()
+
+
+# ------------------------------------------------------- load vector ---
+@pytest.mark.parametrize("case", ["ref_poisson2d_2x2.npz", "ref_poisson2d_10x7.npz", "ref_poisson2d_jitter12.npz"])
+def test_rhs_reference_strings(ctx, golden_dir, case):
+    """b = sum_e sum_q w_q rhs_li with the RHS strings the reference generates and discards."""
+    j = json.load(open(os.path.join(golden_dir, "ref_integrand_strings.json")))
+    g = np.load(os.path.join(golden_dir, case))
+    mesh = host_mesh_to_dev(2, g["conn"], (g["X"], g["Y"]))
+    pat = femx.Pattern(ctx, mesh)
+    form = femx.Form(ctx, 2, entries=j["integrand"], rhs=j["rhs"])
+    b = form.assemble_rhs(pat, mesh)
+    assert relF(b.cpu().numpy(), g["rhs"]) <= TOL64
+    b2 = form.assemble_rhs(pat, mesh.expanded(ctx))
+    assert np.array_equal(b.cpu().numpy(), b2.cpu().numpy())
+    form.close(); pat.close()
+
+
+@pytest.mark.parametrize("dim,builtin,nd,fvec", [(2, femx.POISSON, 1, (2.5,)), (3, femx.POISSON_MASS, 1, (1.0,)),
+                                                (3, femx.ELASTICITY, 3, (0.1, -0.2, -9.81))])
+def test_rhs_constant_source(ctx, dim, builtin, nd, fvec):
+    rng = np.random.RandomState(4)
+    if dim == 2:
+        X, Y, _, conn = orc.rect_mesh(0, 1, 0, 2, 14, 9)
+        X = X + rng.uniform(-0.02, 0.02, X.shape)
+        coords, oc = (X, Y), (X, Y, None)
+    else:
+        X, Y, Z, conn = orc.box_mesh(5, 6, 4)
+        Y = Y + rng.uniform(-0.02, 0.02, Y.shape)
+        coords = oc = (X, Y, Z)
+    mesh = host_mesh_to_dev(dim, conn, coords)
+    pat = femx.Pattern(ctx, mesh, nd=nd)
+    form = femx.Form(ctx, dim, builtin, nd=nd, params=(0.6, 0.4), rhs_vec=fvec)
+    b = form.assemble_rhs(pat, mesh)
+    ob, _ = orc.assemble_rhs(0, dim, nd, conn, *oc, fvec=fvec)
+    assert relF(b.cpu().numpy(), ob) <= TOL64
+    assert np.array_equal(b.cpu().numpy(), form.assemble_rhs(pat, mesh).cpu().numpy())
+    form.close(); pat.close()
+
+
+def test_poisson_solve_manufactured(ctx):
+    """A x = b end to end: -lap(u) + u = f with the assembled operator and load vector; CG recovers
+    the discrete solution the oracle's CG finds (the reference's f, its mesh, its quadrature)."""
+    import torch
+    from femx.dist import SlabOperator, make_slab
+    j = json.load(open(os.path.join(GOLDEN_DIR, "ref_integrand_strings.json")))
+    nR = nC = 24
+    mesh = ctx.rectangle_mesh(-3.0, 3.0, -3.0, 3.0, nR, nC)
+    pat = femx.Pattern(ctx, mesh)
+    fA = femx.Form(ctx, 2, femx.POISSON_MASS)
+    fb = femx.Form(ctx, 2, entries=j["integrand"], rhs=j["rhs"])
+    vals = fA.assemble_csr(pat, mesh)
+    b = fb.assemble_rhs(pat, mesh)
+    op = SlabOperator(ctx, pat, vals, make_slab(0, 1, nR, nC + 1))
+    x, hist = op.cg(b, 200)
+    X, Y, _, conn = orc.rect_mesh(-3.0, 3.0, -3.0, 3.0, nR, nC)
+    rp, ci = orc.pattern(conn, len(X))
+    ov = orc.assemble_csr(orc.POISSON_MASS, 2, 1, conn, X, Y, None, rp, ci)
+    ob, _ = orc.assemble_rhs(1, 2, 1, conn, X, Y)
+    ox, ores = orc.cg(rp, ci, ov, ob, 200)
+    assert hist[-1].item() < 1e-8 * hist[0].item()
+    assert np.abs(x.cpu().numpy() - ox).max() <= 1e-8 * np.abs(ox).max()
+    fA.close(); fb.close(); pat.close()

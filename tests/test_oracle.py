@@ -140,3 +140,21 @@ def test_golden_strings_fixture(golden_dir):
                dict(x1=x1, x2=x2, x3=x3, y1=y1, y2=y2, y3=y3, pow=pow))
     jac = (x1 - x3) * (y2 - y3) - (y1 - y3) * (x2 - x3)
     assert abs(val - ((x2 - x3) ** 2 + (y2 - y3) ** 2) / jac) < 1e-13
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_rhs_matches_reference_strings(golden_dir, case):
+    """Load vector: oracle vs the reference's (generated-then-discarded) RHS strings, fea_symbolic.cu:335,339,343."""
+    g = np.load(os.path.join(golden_dir, case))
+    b, be = orc.assemble_rhs(1, 2, 1, g["conn"], g["X"], g["Y"])
+    assert relF(be, g["rhs_elem"]) <= 1e-13
+    assert relF(b, g["rhs"]) <= 1e-13
+
+
+def test_rhs_constant_source_integrates_to_volume():
+    X, Y, Z, conn = orc.box_mesh(3, 4, 2, hi=(1.0, 2.0, 0.5))
+    b, _ = orc.assemble_rhs(0, 3, 1, conn, X, Y, Z, fvec=(2.0,))
+    assert abs(b.sum() - 2.0) < 1e-12          # f * |Omega| = 2 * 1
+    X, Y, _, conn = orc.rect_mesh(0, 2, 0, 3, 5, 4)
+    b, _ = orc.assemble_rhs(0, 2, 2, conn, X, Y, None, fvec=(1.0, -3.0))
+    assert abs(b[0::2].sum() - 6.00000012) < 1e-9 and abs(b[1::2].sum() + 18.00000036) < 1e-9  # 8-digit weights (Q9)
