@@ -71,6 +71,34 @@ __global__ void xpby_ratio_k(int64_t n, const double* __restrict__ num, const do
   if (i < n) p[i] = (T)((double)r[i] + beta * (double)p[i]);
 }
 
+// one thread per dof row; columns are LOCAL node ids, so flag/g are indexed by local dof
+template <class T>
+__global__ void dirichlet_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx, int n_rows, int nd,
+                            int row_begin, const int* __restrict__ flag, const T* __restrict__ g,
+                            T* __restrict__ vals, T* __restrict__ rhs) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n_rows * nd) return;
+  int i = (int)(t / nd), c = (int)(t - (int64_t)i * nd);
+  int lo = rowinfo[i].x, len = rowinfo[i + 1].x - lo;
+  T* v = vals + (long long)lo * nd * nd + (long long)c * nd * len;
+  const long long self = (long long)(row_begin + i) * nd + c;  // local dof of this row
+  const bool fixed = flag[self] != 0;
+  T corr = T(0);
+  for (int p = 0; p < len; ++p) {
+    const long long colb = (long long)col_idx[lo + p] * nd;
+    for (int d = 0; d < nd; ++d) {
+      const long long col = colb + d;
+      if (fixed) {
+        v[p * nd + d] = col == self ? T(1) : T(0);
+      } else if (flag[col] != 0) {
+        corr += v[p * nd + d] * g[col];
+        v[p * nd + d] = T(0);
+      }
+    }
+  }
+  if (rhs) rhs[t] = fixed ? g[self] : rhs[t] - corr;
+}
+
 inline unsigned nb(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
@@ -91,6 +119,25 @@ int femx_spmv(const femx_pattern* p, int dtype, const void* d_values, const void
     spmv_k<float><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
                                                            (const float*)d_values, (const float*)d_x,
                                                            (long long)x_base - (long long)p->nd * p->col_base, (float*)d_y);
+  FEMX_CUDA_OK(p->ctx, cudaGetLastError());
+  return FEMX_OK;
+}
+
+int femx_apply_dirichlet(const femx_pattern* p, int dtype, const int32_t* d_flag, const void* d_g, void* d_values,
+                         void* d_rhs, void* stream) {
+  if (!p || !d_flag || !d_g || !d_values)
+    return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_apply_dirichlet: NULL argument");
+  if (p->n_rows == 0) return FEMX_OK;
+  FEMX_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
+  int64_t n = p->n_rows * p->nd;
+  if (dtype == FEMX_F64)
+    dirichlet_k<double><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
+                                                                 (int)p->row_begin, d_flag, (const double*)d_g,
+                                                                 (double*)d_values, (double*)d_rhs);
+  else
+    dirichlet_k<float><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
+                                                                (int)p->row_begin, d_flag, (const float*)d_g,
+                                                                (float*)d_values, (float*)d_rhs);
   FEMX_CUDA_OK(p->ctx, cudaGetLastError());
   return FEMX_OK;
 }

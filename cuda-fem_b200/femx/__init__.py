@@ -53,7 +53,7 @@ SYMBOLS = [
     "femx_mesh_rectangle", "femx_mesh_expand", "femx_mesh_box",
     "femx_assemble_coo", "femx_pattern_build", "femx_pattern_destroy", "femx_pattern_info",
     "femx_pattern_bytes", "femx_pattern_export_csr", "femx_pattern_export_ell",
-    "femx_assemble_csr", "femx_assemble_rhs", "femx_csr_to_ell", "femx_spmv", "femx_dot2", "femx_axpy_ratio",
+    "femx_assemble_csr", "femx_assemble_rhs", "femx_apply_dirichlet", "femx_csr_to_ell", "femx_spmv", "femx_dot2", "femx_axpy_ratio",
     "femx_xpby_ratio",
 ]
 
@@ -377,6 +377,12 @@ class Pattern:
         dt = F64 if values.dtype == torch.float64 else F32
         self.ctx.check(lib().femx_csr_to_ell(self.h, dt, int(width), _vp(values), _vp(out), _stream(stream)))
         return out
+
+    def apply_dirichlet(self, flag, g, values, rhs=None, stream=None):
+        """Symmetric elimination of the dofs with flag != 0 (values g); in place."""
+        import torch
+        dt = F64 if values.dtype == torch.float64 else F32
+        self.ctx.check(lib().femx_apply_dirichlet(self.h, dt, _vp(flag), _vp(g), _vp(values), _vp(rhs), _stream(stream)))
 
     def spmv(self, values, x, x_base=0, y=None, stream=None):
         import torch

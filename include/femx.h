@@ -247,6 +247,16 @@ int femx_assemble_rhs(femx_form* form, const femx_pattern* pat, const femx_mesh_
 int femx_csr_to_ell(const femx_pattern* pat, int dtype, int width,
                     const void* d_values, void* d_ell, void* stream);
 
+/* Dirichlet conditions by symmetric elimination (the reference sets the node
+ * boundary `flag`, fea_test.cu:100-103, and never uses it).  d_flag[dof] != 0 marks a constrained
+ * dof, d_g[dof] its value; both are indexed by LOCAL dof (nd * local node + comp) and must cover
+ * every node of the slab (ghosts included).  For each owned row j:
+ *   constrained   : row := e_j,  rhs[j] := g_j
+ *   unconstrained : rhs[j] -= sum_{i constrained} A_ji g_i (ascending column order), A_ji := 0.
+ * d_rhs may be NULL (matrix only). */
+int femx_apply_dirichlet(const femx_pattern* pat, int dtype, const int32_t* d_flag, const void* d_g,
+                         void* d_values, void* d_rhs, void* stream);
+
 /* ------------------------------------------------- validation: SpMV and CG */
 
 /* y = A x for the rows of this pattern; x is indexed by (column - x_base). */

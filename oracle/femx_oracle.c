@@ -414,6 +414,21 @@ void orc_assemble_csr(int form, int dim, int nd, const double* params, int64_t n
   }
 }
 
+/* ---- Dirichlet conditions by symmetric elimination on the dof-level CSR (the
+ * reference sets Node::flag, fea_test.cu:100-103, and never uses it). */
+void orc_apply_dirichlet(int64_t n_rows, const int64_t* row_ptr, const int32_t* col_idx,
+                         const int32_t* flag, const double* g, double* values, double* rhs) {
+  for (int64_t j = 0; j < n_rows; j++) {
+    double corr = 0.0;
+    for (int64_t k = row_ptr[j]; k < row_ptr[j + 1]; k++) {
+      int32_t i = col_idx[k];
+      if (flag[j]) values[k] = (i == j) ? 1.0 : 0.0;
+      else if (flag[i]) { corr += values[k] * g[i]; values[k] = 0.0; }
+    }
+    if (rhs) rhs[j] = flag[j] ? g[j] : rhs[j] - corr;
+  }
+}
+
 /* ---- validation helpers: y = A x, and unpreconditioned CG (SURVEY cfg5). */
 void orc_spmv(int64_t n_rows, const int64_t* row_ptr, const int32_t* col_idx,
               const double* values, const double* x, double* y) {

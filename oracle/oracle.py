@@ -158,6 +158,13 @@ def assemble_csr(form, dim, nd, conn, X, Y, Z, drow_ptr, dcol_idx, params=None):
     return vals
 
 
+def apply_dirichlet(row_ptr, col_idx, flag, g, vals, rhs):
+    """In place: symmetric elimination of the dofs with flag != 0."""
+    flag = np.ascontiguousarray(flag, np.int32)
+    g = np.ascontiguousarray(g, np.float64)
+    lib().orc_apply_dirichlet(_i64(len(row_ptr) - 1), _p(row_ptr), _p(col_idx), _p(flag), _p(g), _p(vals), _p(rhs))
+
+
 def spmv(row_ptr, col_idx, vals, x):
     y = np.empty(len(row_ptr) - 1)
     lib().orc_spmv(_i64(len(y)), _p(row_ptr), _p(col_idx), _p(vals), _p(x), _p(y))

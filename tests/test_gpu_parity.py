@@ -426,3 +426,35 @@ def test_poisson_solve_manufactured(ctx):
     assert hist[-1].item() < 1e-8 * hist[0].item()
     assert np.abs(x.cpu().numpy() - ox).max() <= 1e-8 * np.abs(ox).max()
     fA.close(); fb.close(); pat.close()
+
+
+# --------------------------------------------------- Dirichlet conditions ---
+@pytest.mark.parametrize("nd", [1, 2])
+def test_dirichlet_elimination_matches_oracle(ctx, nd):
+    import torch
+    nR, nC = 13, 9
+    mesh = ctx.rectangle_mesh(0.0, 1.0, 0.0, 1.0, nR, nC, flags=True)
+    builtin = femx.POISSON_MASS if nd == 1 else femx.ELASTICITY
+    form = femx.Form(ctx, 2, builtin, nd=nd, params=(1.0, 0.5) if nd > 1 else (1.0,), rhs_vec=(1.0, -2.0))
+    pat = femx.Pattern(ctx, mesh, nd=nd)
+    vals = form.assemble_csr(pat, mesh)
+    b = form.assemble_rhs(pat, mesh)
+    flag = mesh.flag.repeat_interleave(nd).contiguous()           # the reference's boundary flag, per dof
+    g = torch.linspace(-1.0, 1.0, pat.n_rows, dtype=torch.float64, device="cuda")
+    X, Y, oflag, conn = orc.rect_mesh(0.0, 1.0, 0.0, 1.0, nR, nC)
+    rp, ci = orc.pattern(conn, len(X))
+    drp, dci = orc.expand_pattern(nd, rp, ci) if nd > 1 else (rp, ci)
+    ov = vals.cpu().numpy().copy(); ob = b.cpu().numpy().copy()
+    orc.apply_dirichlet(drp, dci, np.repeat(oflag, nd), g.cpu().numpy(), ov, ob)
+    pat.apply_dirichlet(flag, g, vals, b)
+    assert np.array_equal(vals.cpu().numpy(), ov)
+    assert np.allclose(b.cpu().numpy(), ob, rtol=1e-14, atol=1e-15)
+    # the constrained system is symmetric and solving it reproduces g on the boundary
+    import scipy.sparse as sp
+    import scipy.sparse.linalg
+    A = sp.csr_matrix((vals.cpu().numpy(), dci, drp))
+    assert abs(A - A.T).max() < 1e-13
+    x = sp.linalg.spsolve(A.tocsc(), b.cpu().numpy())
+    fl = np.repeat(oflag, nd).astype(bool)
+    assert np.abs(x[fl] - g.cpu().numpy()[fl]).max() < 1e-12
+    form.close(); pat.close()
