@@ -319,28 +319,32 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
   // accumulator and the scatter positions po[j] are static inside the case.
   const int nn = f->nn, nd = f->nd;
   static const char* ax[3] = {"x", "y", "z"};
+  // One thread owns a NODE row: geometry once per incidence, then the ND dof rows of the element
+  // matrix one after the other (component c), each into its own dof-row segment of the image.
   o << "#define FEMX_CSR_CASES";
-  for (int a = 0; a < nn; ++a)
+  for (int a = 0; a < nn; ++a) {
+    o << " \\\n    case " << a << ": {";
+    for (int k = 0; k < f->dim; ++k) {
+      o << " const real " << ax[k] << a + 1 << " = s" << ax[k] << ";";
+      for (int j = 0; j < nn - 1; ++j)
+        o << " const real " << ax[k] << (a + 1 + j) % nn + 1 << " = o" << ax[k] << "[" << j << "];";
+    }
+    o << " \\\n      FEMX_PROLOGUE";
     for (int c = 0; c < nd; ++c) {
       const int li = a * nd + c;
-      o << " \\\n    case " << li << ": {";
-      for (int k = 0; k < f->dim; ++k) {
-        o << " const real " << ax[k] << a + 1 << " = s" << ax[k] << ";";
-        for (int j = 0; j < nn - 1; ++j)
-          o << " const real " << ax[k] << (a + 1 + j) % nn + 1 << " = o" << ax[k] << "[" << j << "];";
-      }
-      o << " \\\n      FEMX_PROLOGUE real out[NDOF];";
-      if (has_q[li]) {
-        o << " _Pragma(\"unroll\") for (int j_ = 0; j_ < NDOF; ++j_) out[j_] = real(0);";
-      }
+      o << " \\\n      { real out[NDOF];";
+      if (has_q[li]) o << " _Pragma(\"unroll\") for (int j_ = 0; j_ < NDOF; ++j_) out[j_] = real(0);";
       o << " FEMX_ROWC_" << li;
       if (has_q[li]) o << " FEMX_QUAD(FEMX_ROWQ_" << li << ")";
-      for (int d = 0; d < nd; ++d) o << " \\\n      dacc[" << d << "] += out[" << a * nd + d << "];";
+      for (int d = 0; d < nd; ++d) o << " \\\n        dacc[" << c * nd + d << "] += out[" << a * nd + d << "];";
       for (int j = 0; j < nn - 1; ++j)
         for (int d = 0; d < nd; ++d)
-          o << " \\\n      srow[po[" << j << "] + " << d << "] += out[" << ((a + 1 + j) % nn) * nd + d << "];";
-      o << " } break;";
+          o << " \\\n        srow[" << c << " * rstride + po[" << j << "] + " << d << "] += out["
+            << ((a + 1 + j) % nn) * nd + d << "];";
+      o << " }";
     }
+    o << " } break;";
+  }
   o << "\n";
   return o.str();
 }
@@ -694,7 +698,7 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
     } else {
       int regs = 64;
       drv->FuncGetAttribute(&regs, CU_FUNC_ATTRIBUTE_NUM_REGS, v->fn);
-      const int threads = pat->tile_nodes * form->nd;
+      const int threads = pat->tile_nodes;
       const int regs_alloc = ((regs + 7) / 8) * 8;
       int ctas = 65536 / (regs_alloc * threads);
       if (ctas > 2048 / threads) ctas = 2048 / threads;
@@ -721,7 +725,7 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   const int32_t* pelem = pat->d_sell_elem;
   void* args[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &n_rows};
   unsigned blocks = (unsigned)((pat->n_rows + pat->tile_nodes - 1) / pat->tile_nodes);
-  unsigned threads = (unsigned)(pat->tile_nodes * form->nd);
+  unsigned threads = (unsigned)pat->tile_nodes;  // one thread per node row
   CUresult cr = drv->LaunchKernel(v->fn, blocks, 1, 1, threads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
   if (cr != CUDA_SUCCESS) {
     const char* es = nullptr;

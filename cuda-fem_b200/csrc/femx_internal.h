@@ -79,7 +79,7 @@ struct femx_pattern {
 static inline int femx_tile_nodes_for(int nd) {
   if (const char* e = getenv("FEMX_TILE")) {
     int t = atoi(e);
-    if (t >= 32 && t <= 1024 && t % 32 == 0 && t * nd <= 1024) return t;
+    if (t >= 32 && t <= 1024 && t % 32 == 0) return t;
   }
-  return nd == 1 ? 128 : 64;
+  return nd == 1 ? 128 : 32;
 }

@@ -221,9 +221,9 @@ __device__ __forceinline__ float femx_ldg_if(const float* p, int pred) {
 #define FEMX_CS cs
 #endif
 #if FEMX_MIN_BLOCKS > 0
-#define FEMX_BOUNDS __launch_bounds__(FEMX_TILE_NODES * ND, FEMX_MIN_BLOCKS)
+#define FEMX_BOUNDS __launch_bounds__(FEMX_TILE_NODES, FEMX_MIN_BLOCKS)
 #else
-#define FEMX_BOUNDS __launch_bounds__(FEMX_TILE_NODES * ND)
+#define FEMX_BOUNDS __launch_bounds__(FEMX_TILE_NODES)
 #endif
 #define FEMX_EPV (16 / (int)sizeof(real))  // values per 16 bytes
 
@@ -262,8 +262,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   const int vspan = (vph + cnt + FEMX_EPV - 1) & ~(FEMX_EPV - 1);
   int* s_cols = reinterpret_cast<int*>(s_vals - vph + vspan) + cph;
   // per-row metadata: issued before the staging wait so that its latency overlaps the bulk copies
-  const int ln = threadIdx.x / ND;
-  const int c = threadIdx.x - ln * ND;
+  const int ln = threadIdx.x;  // one thread per node row (all ND dof rows of the node)
   const int rowc = i0 + min(ln, nt - 1);
   const int2 r0 = __ldg(&rowinfo[rowc]);
   const int rnext = __ldg(&rowinfo[rowc + 1].x);
@@ -304,7 +303,8 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
     const int row = i0 + ln;
     const int rlen = rnext - r0.x;
     const int off = r0.x - base;
-    real* srow = s_vals + off * (ND * ND) + c * rlen * ND;
+    real* srow = s_vals + off * (ND * ND);
+    const int rstride = rlen * ND;  // dof row c of the node starts at srow + c*rstride
     const int sp = spg + (row & 31);
     const unsigned* sc = s_code + (sp - sbase);
     const int np = r0.y;
@@ -341,9 +341,9 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
         oz[j] = DIM == 3 ? __ldg(Z + p) : real(0);
       }
 #endif
-      real dacc[ND];  // the diagonal block row (own column) accumulates in registers
+      real dacc[ND * ND];  // the diagonal block (own column) accumulates in registers
 #pragma unroll
-      for (int d = 0; d < ND; ++d) dacc[d] = real(0);
+      for (int d = 0; d < ND * ND; ++d) dacc[d] = real(0);
 #pragma unroll FEMX_UNROLL
       for (int it = 0; it < np; ++it) {
         // ---- software pipeline: the gathers of incidence it+1 are issued first
@@ -379,7 +379,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
         int po[NN - 1];
 #pragma unroll
         for (int j = 0; j < NN - 1; ++j) po[j] = ((code >> (7 * j)) & 127) * ND;
-        switch (((code >> 28) & 3) * ND + c) {
+        switch ((code >> 28) & 3) {
           FEMX_CSR_CASES
         }
         code = ncd;
@@ -390,7 +390,9 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
 #endif
       }
 #pragma unroll
-      for (int d = 0; d < ND; ++d) srow[ps + d] = dacc[d];
+      for (int c = 0; c < ND; ++c)
+#pragma unroll
+        for (int d = 0; d < ND; ++d) srow[c * rstride + ps + d] = dacc[c * ND + d];
     }
   }
   // ---- write the tile: generic-proxy writes -> async proxy, then one bulk store
@@ -408,8 +410,8 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
     // ragged head / tail (fewer than 16 bytes each)
     const int ntail = cnt - head - mid;
     if ((int)threadIdx.x < head) dst[threadIdx.x] = s_vals[threadIdx.x];
-    else if ((int)threadIdx.x >= 32 && (int)threadIdx.x - 32 < ntail)
-      dst[head + mid + threadIdx.x - 32] = s_vals[head + mid + threadIdx.x - 32];
+    else if ((int)threadIdx.x - head < ntail)   // head, ntail < 16 bytes each: threads 0..6 at most
+      dst[mid + threadIdx.x] = s_vals[mid + threadIdx.x];
     if (threadIdx.x == 0 && mid > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 }

@@ -147,7 +147,10 @@ def _csr_case(ctx, dim, builtin, nd, conn, coords, params=(), dtype=femx.F64, to
     rp32, _ = pat.csr("int32")
     assert np.array_equal(rp32.cpu().numpy().astype(np.int64), drp)
     form = femx.Form(ctx, dim, builtin, nd=nd, params=params, dtype=dtype)
-    vals = form.assemble_csr(pat, mesh)
+    import torch
+    vals = torch.full((pat.nnz,), float("nan"), dtype=torch.float64 if dtype == femx.F64 else torch.float32, device="cuda")
+    form.assemble_csr(pat, mesh, vals)          # every value must be overwritten (NaN sentinel)
+    assert not torch.isnan(vals).any()
     oc = coords if dim == 3 else (coords[0], coords[1], None)
     ov = orc.assemble_csr(FORM_IDS[builtin], dim, nd, conn, *oc, drp, dci, params=params)
     assert relF(vals.cpu().numpy(), ov) <= tol
