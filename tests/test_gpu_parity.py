@@ -461,3 +461,47 @@ def test_dirichlet_elimination_matches_oracle(ctx, nd):
     fl = np.repeat(oflag, nd).astype(bool)
     assert np.abs(x[fl] - g.cpu().numpy()[fl]).max() < 1e-12
     form.close(); pat.close()
+
+
+# ---------------------------------------------------------------- edge cases ---
+def test_row_longer_than_127_columns_is_unsupported(ctx):
+    k = 130
+    ang = np.linspace(0, 2 * np.pi, k, endpoint=False)
+    X = np.concatenate([[0.0], np.cos(ang)]); Y = np.concatenate([[0.0], np.sin(ang)])
+    conn = np.array([[0, 1 + i, 1 + (i + 1) % k] for i in range(k)], np.int32)
+    mesh = host_mesh_to_dev(2, conn, (X, Y))
+    with pytest.raises(femx.FemxError) as ei:
+        femx.Pattern(ctx, mesh)
+    assert ei.value.status == 4 and "128" in str(ei.value)
+
+
+def test_oversized_mesh_is_rejected_before_any_work(ctx):
+    import ctypes as C
+    import torch
+    conn = torch.zeros(3, dtype=torch.int32, device="cuda")
+    h = C.c_void_p()
+    st = femx.lib().femx_pattern_build(ctx.h, 3, 1, C.c_int64(10), C.c_int64(800_000_000), C.c_void_p(conn.data_ptr()),
+                                       C.c_int64(0), C.c_int64(10), C.c_int64(0), None, C.byref(h))
+    assert st == 4 and b"32-bit" in femx.lib().femx_last_error(ctx.h)
+
+
+def test_isolated_nodes_and_duplicate_elements(ctx):
+    """Nodes that belong to no element give empty rows; an element listed twice contributes twice."""
+    X = np.array([0.0, 1.0, 0.0, 5.0, 1.0, 7.0]); Y = np.array([0.0, 0.0, 1.0, 5.0, 1.0, 7.0])
+    conn = np.array([[0, 1, 2], [1, 4, 2], [0, 1, 2]], np.int32)          # nodes 3 and 5 are isolated
+    mesh = host_mesh_to_dev(2, conn, (X, Y))
+    pat = femx.Pattern(ctx, mesh)
+    rp, ci = pat.csr("int64")
+    orp, oci = orc.pattern(conn, 6)
+    assert np.array_equal(rp.cpu().numpy(), orp) and np.array_equal(ci.cpu().numpy(), oci)
+    assert orp[4] - orp[3] == 0 and orp[6] - orp[5] == 0
+    form = femx.Form(ctx, 2, femx.POISSON_MASS)
+    v = form.assemble_csr(pat, mesh)
+    ov = orc.assemble_csr(orc.POISSON_MASS, 2, 1, conn, X, Y, None, orp, oci)
+    assert relF(v.cpu().numpy(), ov) <= TOL64
+    form.close(); pat.close()
+
+
+def test_csr_tets_fp32(ctx):
+    X, Y, Z, conn = orc.box_mesh(7, 5, 6)
+    _csr_case(ctx, 3, femx.POISSON_MASS, 1, conn, (X, Y, Z), params=(1.0,), dtype=femx.F32, tol=TOL32)
