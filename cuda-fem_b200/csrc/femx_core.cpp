@@ -93,6 +93,20 @@ int femx_ctx_create(int device, femx_ctx** out) {
   c->device = device;
   c->sm_count = p.multiProcessorCount;
   c->smem_optin = p.sharedMemPerBlockOptin;
+  {
+    // private pool: temporaries of repeated symbolic passes are recycled instead of going back to the driver
+    cudaMemPoolProps pp = {};
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    if (cudaMemPoolCreate(&c->pool, &pp) == cudaSuccess) {
+      unsigned long long thr = ~0ULL;
+      cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    } else {
+      (void)cudaGetLastError();
+      c->pool = nullptr;
+    }
+  }
   *out = c;
   return FEMX_OK;
 }
@@ -100,6 +114,7 @@ int femx_ctx_create(int device, femx_ctx** out) {
 void femx_ctx_destroy(femx_ctx* ctx) {
   if (!ctx) return;
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   delete ctx;
 }
 

@@ -17,6 +17,7 @@ struct femx_ctx {
   int sm_count = 0;
   size_t smem_optin = 0;
   double* d_scratch = nullptr;  // partial sums of femx_dot2 (2 * FEMX_DOT_BLOCKS doubles)
+  cudaMemPool_t pool = nullptr; // stream-ordered pool for the symbolic pass's temporaries (retains memory)
   mutable std::string err;
 };
 

@@ -120,7 +120,8 @@ int exclusive_scan(femx_ctx* ctx, const int* d_in, int64_t n, int* d_out, long l
   }
   int nt = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
   long long* d_sums = nullptr;
-  FEMX_CUDA_OK(ctx, cudaMallocAsync(&d_sums, sizeof(long long) * (nt + 1), st));
+  FEMX_CUDA_OK(ctx, ctx->pool ? cudaMallocFromPoolAsync((void**)&d_sums, sizeof(long long) * (nt + 1), ctx->pool, st)
+                              : cudaMallocAsync((void**)&d_sums, sizeof(long long) * (nt + 1), st));
   scan_tile_sums<<<nt, SCAN_THREADS, 0, st>>>(d_in, n, d_sums);
   scan_sums<<<1, SCAN_THREADS, 0, st>>>(d_sums, nt, d_sums + nt);
   scan_apply<<<nt, SCAN_THREADS, 0, st>>>(d_in, n, d_sums, d_out);
@@ -334,7 +335,7 @@ int dev_alloc(femx_ctx* ctx, T** p, int64_t n, int64_t* bytes) {
 template <class T>
 int tmp_alloc(femx_ctx* ctx, T** p, int64_t n, cudaStream_t st) {
   size_t b = sizeof(T) * (size_t)(n > 0 ? n : 1);
-  cudaError_t e = cudaMallocAsync((void**)p, b, st);
+  cudaError_t e = ctx->pool ? cudaMallocFromPoolAsync((void**)p, b, ctx->pool, st) : cudaMallocAsync((void**)p, b, st);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
     return femx_fail(ctx, FEMX_ERR_NOMEM, "cudaMallocAsync(%zu bytes) failed: %s", b, cudaGetErrorString(e));
