@@ -233,6 +233,7 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
   o << "#define NN " << f->nn << "\n#define ND " << f->nd << "\n#define DIM " << f->dim
     << "\n#define FEMX_TILE_NODES " << femx_tile_nodes_for(f->nd) << "\n";
   o << "#define FEMX_MIN_BLOCKS " << (getenv("FEMX_MINBLOCKS") ? atoi(getenv("FEMX_MINBLOCKS")) : 0) << "\n";
+  o << "#define FEMX_MIDGATHER " << (getenv("FEMX_MIDGATHER") ? atoi(getenv("FEMX_MIDGATHER")) : (f->dim == 2 && f->nd == 1 ? 1 : 0)) << "\n";
   o << "#define FEMX_UNROLL " << (getenv("FEMX_UNROLL") ? atoi(getenv("FEMX_UNROLL")) : 1) << "\n";
   o << "#define FEMX_EXPANDED " << (kernel == "csr_x" ? 1 : 0) << "\n";
   o << "#define FEMX_UNIT_STRIDE " << (kernel == "csr" ? 1 : 0) << "\n";
@@ -329,7 +330,7 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
       for (int j = 0; j < nn - 1; ++j)
         o << " const real " << ax[k] << (a + 1 + j) % nn + 1 << " = o" << ax[k] << "[" << j << "];";
     }
-    o << " \\\n      FEMX_PROLOGUE";
+    o << " \\\n      FEMX_PROLOGUE FEMX_GATHER_NEXT";
     for (int c = 0; c < nd; ++c) {
       const int li = a * nd + c;
       o << " \\\n      { real out[NDOF];";

@@ -344,6 +344,34 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
       real dacc[ND * ND];  // the diagonal block (own column) accumulates in registers
 #pragma unroll
       for (int d = 0; d < ND * ND; ++d) dacc[d] = real(0);
+#if FEMX_MIDGATHER && !FEMX_EXPANDED
+      // One coordinate buffer: the gathers of incidence it+1 are issued in the MIDDLE of incidence
+      // it, right after its geometry prologue has consumed the coordinates (saves the second
+      // buffer's registers; the loads fly during the entry evaluation and the scatter).
+      for (int it = 0; it < np; ++it) {
+        const int more = it + 1 < np;
+        sc += more ? 32 : 0;
+        const unsigned ncd = *sc;
+        int nidx[NN - 1];
+#pragma unroll
+        for (int j = 0; j < NN - 1; ++j) nidx[j] = scol[(ncd >> (7 * j)) & 127];
+        int po[NN - 1];
+#pragma unroll
+        for (int j = 0; j < NN - 1; ++j) po[j] = ((code >> (7 * j)) & 127) * ND;
+#define FEMX_GATHER_NEXT                                                        \
+        _Pragma("unroll") for (int j = 0; j < NN - 1; ++j) {                    \
+          const i64 p_ = (i64)nidx[j] * FEMX_CS;                                \
+          ox[j] = femx_ldg_if(X + p_, more); oy[j] = femx_ldg_if(Y + p_, more); \
+          if (DIM == 3) oz[j] = femx_ldg_if(Z + p_, more);                      \
+        }
+        switch ((code >> 28) & 3) {
+          FEMX_CSR_CASES
+        }
+#undef FEMX_GATHER_NEXT
+        code = ncd;
+      }
+#else
+#define FEMX_GATHER_NEXT
 #pragma unroll FEMX_UNROLL
       for (int it = 0; it < np; ++it) {
         // ---- software pipeline: the gathers of incidence it+1 are issued first
@@ -389,6 +417,8 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
         sx = nsx; sy = nsy; sz = nsz;
 #endif
       }
+#undef FEMX_GATHER_NEXT
+#endif
 #pragma unroll
       for (int c = 0; c < ND; ++c)
 #pragma unroll
