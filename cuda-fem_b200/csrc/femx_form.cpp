@@ -338,10 +338,18 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
       o << " FEMX_ROWC_" << li;
       if (has_q[li]) o << " FEMX_QUAD(FEMX_ROWQ_" << li << ")";
       for (int d = 0; d < nd; ++d) o << " \\\n        dacc[" << c * nd + d << "] += out[" << a * nd + d << "];";
+      // off-diagonal blocks: the (nn-1)*nd slots are distinct (the pattern build rejects elements
+      // with a repeated node), so all loads are issued before the first store — no serialised
+      // load/add/store chain through possibly-aliasing shared-memory addresses
+      o << " \\\n        { real* q_ = srow + " << c << " * rstride; real t_[" << (nn - 1) * nd << "];";
       for (int j = 0; j < nn - 1; ++j)
         for (int d = 0; d < nd; ++d)
-          o << " \\\n        srow[" << c << " * rstride + po[" << j << "] + " << d << "] += out["
+          o << " t_[" << j * nd + d << "] = q_[po[" << j << "] + " << d << "];";
+      for (int j = 0; j < nn - 1; ++j)
+        for (int d = 0; d < nd; ++d)
+          o << " \\\n          q_[po[" << j << "] + " << d << "] = t_[" << j * nd + d << "] + out["
             << ((a + 1 + j) % nn) * nd + d << "];";
+      o << " }";
       o << " }";
     }
     o << " } break;";

@@ -133,12 +133,19 @@ int exclusive_scan(femx_ctx* ctx, const int* d_in, int64_t n, int* d_out, long l
 }
 
 // ------------------------------------------------------------ incidences ---
-__global__ void count_pairs(const int* __restrict__ conn, int64_t total, int row_begin, int row_end,
+__global__ void count_pairs(const int* __restrict__ conn, int64_t total, int nn, int row_begin, int row_end,
                             int n_nodes, int* __restrict__ cnt, int* __restrict__ err) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= total) return;
   int node = conn[k];
   if (node < 0 || node >= n_nodes) { atomicOr(err, 1); return; }
+  // a vertex listed twice in one element: degenerate, and the numeric pass relies on the
+  // vertices of an element occupying distinct value slots
+  {
+    const int64_t e0 = (k / nn) * nn;
+    for (int64_t q = e0; q < k; ++q)
+      if (conn[q] == node) atomicOr(err, 4);
+  }
   if (node >= row_begin && node < row_end) atomicAdd(&cnt[node - row_begin], 1);
 }
 
@@ -406,7 +413,7 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
 
   // 1-2: incidence histogram + scan
   if (total > 0)
-    count_pairs<<<nblocks(total, 256), 256, 0, st>>>(d_conn, total, (int)row_begin, (int)row_end,
+    count_pairs<<<nblocks(total, 256), 256, 0, st>>>(d_conn, total, nn, (int)row_begin, (int)row_end,
                                                      (int)n_nodes, d_cnt, d_flags);
   long long n_pairs = 0;
   PB_TRY(exclusive_scan(ctx, d_cnt, nr, d_pair_ptr, &n_pairs, st));
@@ -417,6 +424,10 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
     cleanup(); femx_pattern_destroy(p);
     return femx_fail(ctx, FEMX_ERR_INVALID, "femx_pattern_build: connectivity holds a node id outside [0,%lld)",
                      (long long)n_nodes);
+  }
+  if (h_flags[0] & 4) {
+    cleanup(); femx_pattern_destroy(p);
+    return femx_fail(ctx, FEMX_ERR_INVALID, "femx_pattern_build: an element lists the same node twice (degenerate element)");
   }
   p->n_pairs = n_pairs;
   PB_TRY(tmp_alloc(ctx, &d_pair_elem, n_pairs, st));

@@ -505,3 +505,11 @@ def test_isolated_nodes_and_duplicate_elements(ctx):
 def test_csr_tets_fp32(ctx):
     X, Y, Z, conn = orc.box_mesh(7, 5, 6)
     _csr_case(ctx, 3, femx.POISSON_MASS, 1, conn, (X, Y, Z), params=(1.0,), dtype=femx.F32, tol=TOL32)
+
+
+def test_degenerate_element_is_rejected(ctx):
+    conn = np.array([[0, 1, 2], [1, 1, 2]], np.int32)
+    mesh = host_mesh_to_dev(2, conn, (np.array([0.0, 1.0, 0.0]), np.array([0.0, 0.0, 1.0])))
+    with pytest.raises(femx.FemxError) as ei:
+        femx.Pattern(ctx, mesh)
+    assert ei.value.status == 1 and "twice" in str(ei.value)
