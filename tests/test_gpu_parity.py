@@ -513,3 +513,37 @@ def test_degenerate_element_is_rejected(ctx):
     with pytest.raises(femx.FemxError) as ei:
         femx.Pattern(ctx, mesh)
     assert ei.value.status == 1 and "twice" in str(ei.value)
+
+
+# ------------------------------------------------------------ unstructured meshes ---
+def _delaunay(dim, npts, seed):
+    from scipy.spatial import Delaunay
+    rng = np.random.RandomState(seed)
+    P = rng.uniform(0, 1, (npts, dim))
+    tri = Delaunay(P)
+    conn = tri.simplices.astype(np.int32)
+    # orient positively (the engine keeps the reference's signed jac; mixed signs are legal but make
+    # the operator indefinite) and drop slivers the quadrature cannot resolve
+    V = P[conn]
+    J = np.transpose(V[:, :dim, :] - V[:, dim:dim + 1, :], (0, 2, 1))
+    det = np.linalg.det(J)
+    keep = np.abs(det) > 1e-9
+    conn, det = conn[keep], det[keep]
+    neg = det < 0
+    conn[neg, 0], conn[neg, 1] = conn[neg, 1].copy(), conn[neg, 0].copy()
+    return P, conn
+
+
+@pytest.mark.parametrize("dim,npts", [(2, 3000), (3, 1500)])
+def test_csr_delaunay_mesh(ctx, dim, npts):
+    """Random Delaunay triangulation / tetrahedralisation: irregular valence (rows of 3..30+ columns),
+    random numbering — nothing structured."""
+    P, conn = _delaunay(dim, npts, 12345)
+    coords = tuple(np.ascontiguousarray(P[:, k]) for k in range(dim))
+    _csr_case(ctx, dim, femx.POISSON_MASS, 1, conn, coords, params=(1.0,))
+
+
+def test_elasticity_delaunay_3d(ctx):
+    P, conn = _delaunay(3, 600, 7)
+    coords = tuple(np.ascontiguousarray(P[:, k]) for k in range(3))
+    _csr_case(ctx, 3, femx.ELASTICITY, 3, conn, coords, params=(0.5769, 0.3846))
