@@ -41,6 +41,8 @@ struct femx_form {
   std::vector<std::string> entries;  // n*n
   std::vector<std::string> rhs;      // n load-vector integrands (may be empty)
   int rhs_integrated = 0;
+  // the built-in entries are invariant under even permutations of the local vertices (see build_defines)
+  bool rot_ok_matrix = false, rot_ok_rhs = false;
   int nq = 0;
   std::vector<double> qw, qr, qs, qt, qu;
   std::map<std::string, Variant> variants;
@@ -120,6 +122,24 @@ int emit_builtin(femx_form* f, const femx_form_desc* d) {
       for (int q = 0; q < f->nq; ++q) m += f->qw[q] * (phi_at(f, b, q) * phi_at(f, a, q));
       M[a][b] = m;
     }
+  // Are the folded quadrature constants symmetric in the vertices?  (The reference's 8-digit 2-D rule
+  // is not, at the 1e-9 level, so 2-D forms with a mass term / load vector keep one case per li.)
+  bool msym = true, vsym = true;
+  double mvec[4];
+  for (int a = 0; a < nn; ++a) {
+    mvec[a] = 0.0;
+    for (int q = 0; q < f->nq; ++q) mvec[a] += f->qw[q] * phi_at(f, a, q);
+  }
+  for (int a = 0; a < nn; ++a) {
+    if (std::fabs(mvec[a] - mvec[0]) > 1e-15 * std::fabs(mvec[0])) vsym = false;
+    for (int b = 0; b < nn; ++b) {
+      const double ref = a == b ? M[0][0] : M[0][1];
+      if (std::fabs(M[a][b] - ref) > 1e-15 * std::fabs(ref)) msym = false;
+    }
+  }
+  const bool has_mass = d->builtin == FEMX_FORM_POISSON_MASS || d->builtin == FEMX_FORM_MASS;
+  f->rot_ok_matrix = !has_mass || msym;
+  f->rot_ok_rhs = vsym;
   std::ostringstream pro;
   pro << "  const real kq = " << num(W) << "*ijac;\n";
   if (d->builtin == FEMX_FORM_ELASTICITY) {
@@ -274,15 +294,23 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
   }
   o << "\n";
   // Load vector: case per local node a; racc[c] += integrated rhs entry (a*ND + c)
+  // Built-in forms are intrinsic (independent of the local vertex numbering), so every incidence
+  // can be evaluated as "row 0 of the element (own node, others...)" — an even permutation of the
+  // element, same signed Jacobian: one case, no switch, no divergence on unstructured meshes.
+  // Custom strings name local vertices explicitly and keep one case per li.
+  const bool rot_allowed = f->builtin != FEMX_FORM_CUSTOM && !(getenv("FEMX_ROTINV") && atoi(getenv("FEMX_ROTINV")) == 0);
+  const bool is_rhs = kernel == "rhs";
+  const bool rotinv = rot_allowed && (is_rhs ? (f->rot_ok_rhs && f->rhs_integrated) : f->rot_ok_matrix);
+  o << "#define FEMX_ROTINV " << (rotinv ? 1 : 0) << "\n";
   o << "#define FEMX_RHS_CASES";
   if (!f->rhs.empty()) {
-    for (int a = 0; a < f->nn; ++a) {
+    for (int a = 0; a < (rotinv ? 1 : f->nn); ++a) {
       o << " \\\n    case " << a << ": {";
       for (int k = 0; k < f->dim; ++k) {
         const char AXU = (char)toupper("xyz"[k]);
         o << " const real " << "xyz"[k] << a + 1 << " = S" << AXU << ";";
         for (int j = 0; j < f->nn - 1; ++j)
-          o << " const real " << "xyz"[k] << (a + 1 + j) % f->nn + 1 << " = O" << AXU << "[" << j << "];";
+          o << " const real " << "xyz"[k] << femx_oth(f->nn, a, j) + 1 << " = O" << AXU << "[" << j << "];";
       }
       o << " \\\n      FEMX_PROLOGUE";
       for (int c = 0; c < f->nd; ++c) {
@@ -323,12 +351,12 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
   // One thread owns a NODE row: geometry once per incidence, then the ND dof rows of the element
   // matrix one after the other (component c), each into its own dof-row segment of the image.
   o << "#define FEMX_CSR_CASES";
-  for (int a = 0; a < nn; ++a) {
+  for (int a = 0; a < (rotinv ? 1 : nn); ++a) {
     o << " \\\n    case " << a << ": {";
     for (int k = 0; k < f->dim; ++k) {
       o << " const real " << ax[k] << a + 1 << " = s" << ax[k] << ";";
       for (int j = 0; j < nn - 1; ++j)
-        o << " const real " << ax[k] << (a + 1 + j) % nn + 1 << " = o" << ax[k] << "[" << j << "];";
+        o << " const real " << ax[k] << femx_oth(nn, a, j) + 1 << " = o" << ax[k] << "[" << j << "];";
     }
     o << " \\\n      FEMX_PROLOGUE FEMX_GATHER_NEXT";
     for (int c = 0; c < nd; ++c) {
@@ -348,7 +376,7 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
       for (int j = 0; j < nn - 1; ++j)
         for (int d = 0; d < nd; ++d)
           o << " \\\n          q_[po[" << j << "] + " << d << "] = t_[" << j * nd + d << "] + out["
-            << ((a + 1 + j) % nn) * nd + d << "];";
+            << femx_oth(nn, a, j) * nd + d << "];";
       o << " }";
       o << " }";
     }

@@ -76,6 +76,14 @@ struct femx_pattern {
 
 #define FEMX_DOT_BLOCKS 1024
 
+// Local index of the j-th OTHER vertex of an incidence whose row node is local vertex li.
+// (li, oth(li,0), oth(li,1), ...) is always an EVEN permutation of the element's vertices
+// (3-cycles for triangles, XOR by li = two transpositions for tetrahedra), so the signed
+// Jacobian of the re-ordered element equals the original one.
+static inline __host__ __device__ int femx_oth(int nn, int li, int j) {
+  return nn == 4 ? (li ^ (j + 1)) : (li + 1 + j) % 3;
+}
+
 // node rows per CTA of the numeric pass (FEMX_TILE overrides: tuning experiments only)
 static inline int femx_tile_nodes_for(int nd) {
   if (const char* e = getenv("FEMX_TILE")) {

@@ -44,6 +44,8 @@ __device__ __forceinline__ double femx_rcp(double a) {
 __device__ __forceinline__ float femx_rcp(float a) { return 1.0f / a; }
 
 #define NDOF (NN * ND)
+// local index of the j-th other vertex of an incidence at local vertex li (even permutation; see femx_internal.h)
+#define FEMX_OTH(li, j) (NN == 4 ? ((li) ^ ((j) + 1)) : (((li) + 1 + (j)) % 3))
 
 // Row `li` of the element matrix: out[lj] = sum_q w_q * integrand(li, lj).
 __device__ __forceinline__ void femx_row(const int li, const real* cx, const real* cy,
@@ -324,7 +326,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
         if (DIM == 3) sz = __ldg(Z + ea);
 #pragma unroll
         for (int j = 0; j < NN - 1; ++j) {
-          int b = li + 1 + j; b -= b >= NN ? NN : 0;
+          const int b = FEMX_OTH(li, j);
           ox[j] = __ldg(X + e0 + b); oy[j] = __ldg(Y + e0 + b);
           oz[j] = DIM == 3 ? __ldg(Z + e0 + b) : real(0);
         }
@@ -348,6 +350,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
       // One coordinate buffer: the gathers of incidence it+1 are issued in the MIDDLE of incidence
       // it, right after its geometry prologue has consumed the coordinates (saves the second
       // buffer's registers; the loads fly during the entry evaluation and the scatter).
+#pragma unroll 1
       for (int it = 0; it < np; ++it) {
         const int more = it + 1 < np;
         sc += more ? 32 : 0;
@@ -364,7 +367,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
           ox[j] = femx_ldg_if(X + p_, more); oy[j] = femx_ldg_if(Y + p_, more); \
           if (DIM == 3) oz[j] = femx_ldg_if(Z + p_, more);                      \
         }
-        switch ((code >> 28) & 3) {
+        switch (FEMX_ROTINV ? 0 : (int)((code >> 28) & 3)) {
           FEMX_CSR_CASES
         }
 #undef FEMX_GATHER_NEXT
@@ -390,7 +393,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
           if (DIM == 3) nsz = femx_ldg_if(Z + ea, more);
 #pragma unroll
           for (int j = 0; j < NN - 1; ++j) {
-            int b = nli + 1 + j; b -= b >= NN ? NN : 0;
+            const int b = FEMX_OTH(nli, j);
             nox[j] = femx_ldg_if(X + e0 + b, more); noy[j] = femx_ldg_if(Y + e0 + b, more);
             noz[j] = DIM == 3 ? femx_ldg_if(Z + e0 + b, more) : real(0);
           }
@@ -407,7 +410,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
         int po[NN - 1];
 #pragma unroll
         for (int j = 0; j < NN - 1; ++j) po[j] = ((code >> (7 * j)) & 127) * ND;
-        switch ((code >> 28) & 3) {
+        switch (FEMX_ROTINV ? 0 : (int)((code >> 28) & 3)) {
           FEMX_CSR_CASES
         }
         code = ncd;
@@ -477,7 +480,7 @@ femx_rhs(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
       if (DIM == 3) SZ = __ldg(Z + ea);
 #pragma unroll
       for (int j = 0; j < NN - 1; ++j) {
-        int b = li + 1 + j; b -= b >= NN ? NN : 0;
+        const int b = FEMX_OTH(li, j);
         OX[j] = __ldg(X + e0 + b); OY[j] = __ldg(Y + e0 + b);
         OZ[j] = DIM == 3 ? __ldg(Z + e0 + b) : real(0);
       }
@@ -492,7 +495,7 @@ femx_rhs(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
         OZ[j] = DIM == 3 ? __ldg(Z + p) : real(0);
       }
     }
-    switch (li) {
+    switch (FEMX_ROTINV ? 0 : li) {
       FEMX_RHS_CASES
     }
   }

@@ -240,7 +240,8 @@ __global__ void row_fill(const int* __restrict__ conn, const int* __restrict__ p
         int m = (a0 + b0) >> 1;
         if (list[m] < node) a0 = m + 1; else b0 = m;
       }
-      const int j = a == li ? 3 : (a - li - 1 + NN) % NN;
+      // slot j of the code holds vertex femx_oth(NN, li, j); the row's own node goes to slot 3
+      const int j = a == li ? 3 : (NN == 4 ? (a ^ li) - 1 : (a - li - 1 + 3) % 3);
       code |= (unsigned)a0 << (7 * j);
     }
     pair_code[k] = code;
