@@ -253,7 +253,7 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
   o << "#define NN " << f->nn << "\n#define ND " << f->nd << "\n#define DIM " << f->dim
     << "\n#define FEMX_TILE_NODES " << femx_tile_nodes_for(f->nd) << "\n";
   o << "#define FEMX_MIN_BLOCKS " << (getenv("FEMX_MINBLOCKS") ? atoi(getenv("FEMX_MINBLOCKS")) : 0) << "\n";
-  o << "#define FEMX_MIDGATHER " << (getenv("FEMX_MIDGATHER") ? atoi(getenv("FEMX_MIDGATHER")) : (f->dim == 2 && f->nd == 1 ? 1 : 0)) << "\n";
+  o << "#define FEMX_MIDGATHER " << (getenv("FEMX_MIDGATHER") ? atoi(getenv("FEMX_MIDGATHER")) : 1) << "\n";
   o << "#define FEMX_UNROLL " << (getenv("FEMX_UNROLL") ? atoi(getenv("FEMX_UNROLL")) : 1) << "\n";
   o << "#define FEMX_EXPANDED " << (kernel == "csr_x" ? 1 : 0) << "\n";
   o << "#define FEMX_UNIT_STRIDE " << (kernel == "csr" ? 1 : 0) << "\n";
