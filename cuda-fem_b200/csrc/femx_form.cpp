@@ -372,7 +372,7 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
       o << " \\\n        { real* q_ = srow + " << c << " * rstride; real t_[" << (nn - 1) * nd << "];";
       for (int j = 0; j < nn - 1; ++j)
         for (int d = 0; d < nd; ++d)
-          o << " t_[" << j * nd + d << "] = q_[po[" << j << "] + " << d << "];";
+          o << " t_[" << j * nd + d << "] = FEMX_FIRST(" << j << ") ? real(0) : q_[po[" << j << "] + " << d << "];";
       for (int j = 0; j < nn - 1; ++j)
         for (int d = 0; d < nd; ++d)
           o << " \\\n          q_[po[" << j << "] + " << d << "] = t_[" << j * nd + d << "] + out["

@@ -232,14 +232,19 @@ __device__ __forceinline__ float femx_ldg_if(const float* p, int pred) {
 // Scatter code of one incidence (row node = local node li of element e):
 //   bits  0-6, 7-13, 14-20 : positions in the row's column list of the OTHER vertices,
 //                            in cyclic order (li+1)%NN, (li+2)%NN, ...
-//   bits 21-27             : position of the row's own node (the diagonal)
+//   bits 21-23             : first-touch flags of those positions (this incidence is the first of
+//                            the row to contribute there: store, do not add — the value image
+//                            needs no zero fill)
 //   bits 28-29             : li
+// rowinfo[i] = { row_ptr[i], #incidences | position of the row's own node << 24 }.
 //
 // Data movement of one tile (FEMX_TILE_NODES node rows):
 //   in : scatter codes + column list  -- two TMA bulk copies (cp.async.bulk, one thread,
 //        mbarrier completion), no per-thread load/store instructions
 //   out: the tile's CSR values        -- one TMA bulk store from the shared-memory image
 //   gathered node coordinates come through L1 (read-only path), software-pipelined.
+#define FEMX_FIRST(J) ((code >> (21 + (J))) & 1u)
+
 extern "C" __global__ void FEMX_BOUNDS
 femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
          const int* __restrict__ col_loc, const unsigned* __restrict__ sell_code,
@@ -287,13 +292,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"((unsigned)__cvta_generic_to_shared(s_cols - cph)), "l"(col_loc + (base - cph)), "r"(cbytes), "r"(bar) : "memory");
   }
-  // zero the value image with 16-byte stores (head/tail phases are inside the padded span)
-  {
-    float4* z = reinterpret_cast<float4*>(s_vals - vph);
-    const int n16 = vspan / FEMX_EPV;
-    for (int j = threadIdx.x; j < n16; j += blockDim.x) z[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  __syncthreads();  // barrier initialised + image zeroed
+  __syncthreads();  // barrier initialised
   {
     unsigned done;
     do {
@@ -309,10 +308,10 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
     const int rstride = rlen * ND;  // dof row c of the node starts at srow + c*rstride
     const int sp = spg + (row & 31);
     const unsigned* sc = s_code + (sp - sbase);
-    const int np = r0.y;
+    const int np = r0.y & 0xffffff;
     if (np > 0) {
       unsigned code = sc[0];
-      const int ps = ((code >> 21) & 127) * ND;  // own column: the same for every incidence
+      const int ps = (int)((unsigned)r0.y >> 24) * ND;  // own column: the same for every incidence
       real ox[NN - 1], oy[NN - 1], oz[NN - 1];
 #if FEMX_EXPANDED
       // element-expanded coordinates X[NN*e + a] (the reference's layout, SURVEY Q17)
@@ -334,7 +333,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
 #else
       // the row's own node is a vertex of every incident element: it stays in registers
       const int* scol = s_cols + off;
-      const i64 pself = (i64)scol[(code >> 21) & 127] * FEMX_CS;
+      const i64 pself = (i64)scol[(unsigned)r0.y >> 24] * FEMX_CS;
       const real sx = __ldg(X + pself), sy = __ldg(Y + pself), sz = DIM == 3 ? __ldg(Z + pself) : real(0);
 #pragma unroll
       for (int j = 0; j < NN - 1; ++j) {
@@ -469,7 +468,9 @@ femx_rhs(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   real racc[ND];
 #pragma unroll
   for (int d = 0; d < ND; ++d) racc[d] = real(0);
-  for (int it = 0; it < r0.y; ++it) {
+  const int np = r0.y & 0xffffff;
+  const int self_pos = (int)((unsigned)r0.y >> 24);
+  for (int it = 0; it < np; ++it) {
     const unsigned code = __ldg(sell_code + sp + it * 32);
     const int li = (code >> 28) & 3;
     real SX, SY, SZ = real(0), OX[NN - 1], OY[NN - 1], OZ[NN - 1];
@@ -485,7 +486,7 @@ femx_rhs(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
         OZ[j] = DIM == 3 ? __ldg(Z + e0 + b) : real(0);
       }
     } else {
-      const i64 ps = (i64)__ldg(cols + ((code >> 21) & 127)) * cs;
+      const i64 ps = (i64)__ldg(cols + self_pos) * cs;
       SX = __ldg(X + ps); SY = __ldg(Y + ps);
       if (DIM == 3) SZ = __ldg(Z + ps);
 #pragma unroll

@@ -215,34 +215,50 @@ __global__ void row_lengths(const int* __restrict__ conn, const int* __restrict_
 template <int NN>
 __global__ void row_fill(const int* __restrict__ conn, const int* __restrict__ pair_ptr,
                          const int* __restrict__ pair_elem, const int* __restrict__ row_ptr, int n_rows,
-                         int* __restrict__ col_idx, unsigned* __restrict__ pair_code,
+                         int row_begin, int* __restrict__ col_idx, unsigned* __restrict__ pair_code,
                          int2* __restrict__ rowinfo) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r > n_rows) return;
-  rowinfo[r] = make_int2(row_ptr[r], r < n_rows ? pair_ptr[r + 1] - pair_ptr[r] : 0);
-  if (r == n_rows) return;
+  if (r == n_rows) { rowinfo[r] = make_int2(row_ptr[r], 0); return; }
   int list[FEMX_MAX_ROW];
   const int lo = pair_ptr[r], hi = pair_ptr[r + 1];
   const int len = build_row<NN>(conn, pair_elem, lo, hi, list);
   const int rp = row_ptr[r];
   for (int p = 0; p < len; ++p) col_idx[rp + p] = list[p];
+  // position of the row's own node (local id = row_begin + r) in its sorted column list
+  int self_pos = 0;
+  {
+    const int self = row_begin + r;
+    int a0 = 0, b0 = len;
+    while (a0 < b0) {
+      int m = (a0 + b0) >> 1;
+      if (list[m] < self) a0 = m + 1; else b0 = m;
+    }
+    self_pos = a0;
+  }
+  rowinfo[r] = make_int2(rp, (hi - lo) | (self_pos << 24));
+  unsigned seen[FEMX_MAX_ROW / 32] = {0u, 0u, 0u, 0u};  // value slots already touched by an earlier incidence
   for (int k = lo; k < hi; ++k) {
     const int pe = pair_elem[k];
     const int e = pe / NN, li = pe - e * NN;
-    // positions of the element's vertices in the sorted row: the OTHER vertices in cyclic
-    // order after li at bits 7*j, the row's own node at bits 21-27, li at bits 28-29
+    // bits 7*j: position in the sorted row of vertex femx_oth(NN, li, j); bits 21+j: first-touch flag
+    // of that position (no earlier incidence of the row contributes there); bits 28-29: li
     unsigned code = (unsigned)li << 28;
 #pragma unroll
     for (int a = 0; a < NN; ++a) {
+      if (a == li) continue;
       const int node = conn[(int64_t)e * NN + a];
       int a0 = 0, b0 = len;  // binary search in the sorted list
       while (a0 < b0) {
         int m = (a0 + b0) >> 1;
         if (list[m] < node) a0 = m + 1; else b0 = m;
       }
-      // slot j of the code holds vertex femx_oth(NN, li, j); the row's own node goes to slot 3
-      const int j = a == li ? 3 : (NN == 4 ? (a ^ li) - 1 : (a - li - 1 + 3) % 3);
+      const int j = NN == 4 ? (a ^ li) - 1 : (a - li - 1 + 3) % 3;
       code |= (unsigned)a0 << (7 * j);
+      if (!(seen[a0 >> 5] & (1u << (a0 & 31)))) {
+        code |= 1u << (21 + j);
+        seen[a0 >> 5] |= 1u << (a0 & 31);
+      }
     }
     pair_code[k] = code;
   }
@@ -470,10 +486,10 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
   // 6: columns + scatter map
   if (nn == 3)
     row_fill<3><<<nblocks(nr + 1, 128), 128, 0, st>>>(d_conn, d_pair_ptr, d_pair_elem, d_row_ptr, (int)nr,
-                                                      p->d_col_idx, d_pair_code, p->d_rowinfo);
+                                                      (int)row_begin, p->d_col_idx, d_pair_code, p->d_rowinfo);
   else
     row_fill<4><<<nblocks(nr + 1, 128), 128, 0, st>>>(d_conn, d_pair_ptr, d_pair_elem, d_row_ptr, (int)nr,
-                                                      p->d_col_idx, d_pair_code, p->d_rowinfo);
+                                                      (int)row_begin, p->d_col_idx, d_pair_code, p->d_rowinfo);
   // SELL-32 transposition of the scatter map
   {
     const int64_t n_slices = (nr + 31) / 32;
