@@ -160,6 +160,12 @@ def main():
     os.makedirs(GEN, exist_ok=True)
     build_one("fea_test_sm_sym_sparse.cu", "ref_coo", SHIM_COO, "#define MESH_W 10000\n", "#define MESH_H 1000\n")
     build_one("fea_test_sm_sym_sparse2.cu", "ref_ell", SHIM_ELL, "#define MESH_W 1000L\n", "#define MESH_H 100L\n")
+    # The reference's own PROGRAM, completely unmodified (its main(), its 1000x100 mesh, its racy zero
+    # loop Q13 and all): its stdout is diffed against examples/femx_sparse2 on the GPU box.
+    exe = os.path.join(OUT, "fea_test_sm_sym_sparse2")
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100,code=sm_100", "-O2", "-std=c++14", "-w", "-cudart", "static",
+                           "-o", exe, os.path.join(REF, "fea_test_sm_sym_sparse2.cu")])
+    print("built", os.path.relpath(exe, HERE), "(unmodified reference program)")
     return 0
 
 

@@ -61,3 +61,33 @@ def test_engine_matches_reference_kernels(ctx, shape, prec):
     ell = pat.values_to_ell(vals, 7).reshape(-1)
     assert _relF(ell.cpu().numpy(), rell.double().cpu().numpy()) <= tol
     form.close(); pat.close()
+
+
+def _parse_rows(text):
+    """'(i,col) val    (i,col) val ...' lines → {(i,col): val}"""
+    import re
+    out = {}
+    for m in re.finditer(r"\((\d+),(\d+)\)\s+(\S+)", text):
+        out[(int(m.group(1)), int(m.group(2)))] = float(m.group(3))
+    return out
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_cpp_client_output_equals_unmodified_reference_program():
+    """The reference's own binary (fea_test_sm_sym_sparse2.cu compiled UNMODIFIED for sm_100, its main(),
+    its 1000x100 mesh) and the plain C++ client of the femx C ABI (examples/femx_sparse2) print the
+    same first 16 matrix rows: same (row, col) keys — the pattern — and values within 1e-5 (fp32)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_exe = os.path.join(root, "oracle", "_ref", "fea_test_sm_sym_sparse2")
+    my_exe = os.path.join(root, "examples", "femx_sparse2")
+    if not (os.path.exists(ref_exe) and os.path.exists(my_exe)):
+        pytest.skip("binaries not built")
+    ref = _parse_rows(subprocess.check_output([ref_exe], timeout=300).decode())
+    mine = _parse_rows(subprocess.check_output([my_exe, "1000", "100", "1"], timeout=300).decode())
+    assert len(ref) >= 60 and set(ref) == set(mine)
+    scale = max(abs(v) for v in ref.values())
+    for k in ref:
+        assert abs(ref[k] - mine[k]) <= 1e-5 * scale, (k, ref[k], mine[k])
