@@ -54,7 +54,7 @@ SYMBOLS = [
     "femx_assemble_coo", "femx_pattern_build", "femx_pattern_destroy", "femx_pattern_info",
     "femx_pattern_bytes", "femx_pattern_export_csr", "femx_pattern_export_ell",
     "femx_assemble_csr", "femx_assemble_rhs", "femx_apply_dirichlet", "femx_csr_to_ell", "femx_spmv", "femx_dot2", "femx_axpy_ratio",
-    "femx_xpby_ratio",
+    "femx_xpby_ratio", "femx_io_read_gmsh", "femx_io_free", "femx_io_write_matrix_market",
 ]
 
 _lib = None
@@ -396,3 +396,39 @@ class Pattern:
         if self.h:
             lib().femx_pattern_destroy(self.h)
             self.h = C.c_void_p()
+
+
+def read_gmsh(path):
+    """Gmsh MSH 2.x ASCII → (dim, X, Y, Z, conn[NE, nn]) as numpy arrays (host)."""
+    import numpy as np
+    L = lib()
+    dim, nn_, ne = C.c_int(), C.c_int64(), C.c_int64()
+    px, py, pz = (C.POINTER(C.c_double)() for _ in range(3))
+    pc = C.POINTER(C.c_int32)()
+    st = L.femx_io_read_gmsh(str(path).encode(), C.byref(dim), C.byref(nn_), C.byref(ne), C.byref(px), C.byref(py),
+                             C.byref(pz), C.byref(pc))
+    if st:
+        raise FemxError(st, L.femx_last_error(None).decode())
+    n, e, k = nn_.value, ne.value, dim.value + 1
+    try:
+        X, Y, Z = (np.ctypeslib.as_array(p, shape=(max(n, 1),))[:n].copy() for p in (px, py, pz))
+        conn = np.ctypeslib.as_array(pc, shape=(max(e * k, 1),))[: e * k].copy().reshape(e, k)
+    finally:
+        L.femx_io_free.argtypes = [C.c_void_p]
+        for p in (px, py, pz, pc):
+            L.femx_io_free(C.cast(p, C.c_void_p))
+    return dim.value, X, Y, Z, conn
+
+
+def write_matrix_market(path, row_ptr, col_idx, values, n_cols=None):
+    """Host CSR (numpy / CPU tensors) → Matrix Market coordinate file."""
+    import numpy as np
+    rp = np.ascontiguousarray(np.asarray(row_ptr), np.int64)
+    ci = np.ascontiguousarray(np.asarray(col_idx), np.int32)
+    v = np.ascontiguousarray(np.asarray(values), np.float64)
+    n = len(rp) - 1
+    st = lib().femx_io_write_matrix_market(str(path).encode(), C.c_int64(n), C.c_int64(n if n_cols is None else n_cols),
+                                           rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p),
+                                           v.ctypes.data_as(C.c_void_p))
+    if st:
+        raise FemxError(st, lib().femx_last_error(None).decode())

@@ -275,6 +275,20 @@ int femx_axpy_ratio(femx_ctx* ctx, int dtype, int64_t n, const double* d_num,
 int femx_xpby_ratio(femx_ctx* ctx, int dtype, int64_t n, const double* d_num,
                     const double* d_den, const void* d_r, void* d_p, void* stream);
 
+/* ------------------------------------------------ host-side I/O (no device needed) */
+
+/* Gmsh MSH 2.x ASCII: 3-node triangles, or 4-node tetrahedra when present (the boundary triangles of
+ * a volume mesh are then ignored).  Node tags are compacted to 0..n-1 in file order.  The four
+ * buffers are malloc'ed by the library; release them with femx_io_free.  (The reference can only
+ * print a mesh: printMesh(), fea_test.cu:53-67.) */
+int femx_io_read_gmsh(const char* path, int* dim, int64_t* n_nodes, int64_t* n_elems, double** h_x,
+                      double** h_y, double** h_z, int32_t** h_conn);
+void femx_io_free(void* p);
+/* Matrix Market "coordinate real general" (1-based) from a host CSR, %.17g values. */
+int femx_io_write_matrix_market(const char* path, int64_t n_rows, int64_t n_cols,
+                                const int64_t* h_row_ptr, const int32_t* h_col_idx,
+                                const double* h_values);
+
 #ifdef __cplusplus
 }
 #endif
