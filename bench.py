@@ -117,6 +117,21 @@ def ref_gpu_baseline(ctx, wl, mesh, pat):
             out[prec] = {"ell_atomic_ms": ms_ell, "ell_atomic_elements_per_s": mesh.n_elems / (ms_ell * 1e-3),
                          "coo_ms": ms_coo, "coo_elements_per_s": mesh.n_elems / (ms_coo * 1e-3)}
             del X, Y
+        # the reference's symbolic pass: host Mesh::getNeighborNodesList (std::set per node), timed on
+        # its own configured mesh (1000 x 100, fea_test_sm_sym_sparse2.cu:16-17) next to femx's device pass
+        t0 = time.perf_counter()
+        refimpl.neighbor_list(1000, 100)
+        host_ms = 1e3 * (time.perf_counter() - t0)
+        small = ctx.rectangle_mesh(-3.0, 3.0, -3.0, 3.0, 1000, 100)
+        import femx as _femx
+        _femx.Pattern(ctx, small).close()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sp_ = _femx.Pattern(ctx, small)
+        torch.cuda.synchronize()
+        dev_ms = 1e3 * (time.perf_counter() - t0)
+        sp_.close()
+        out["symbolic_pass_1000x100"] = {"reference_host_ms (incl. its mesh construction)": host_ms, "femx_device_ms": dev_ms}
         return out
     except Exception as e:  # a reported extra must never take the headline down
         return {"error": repr(e)}

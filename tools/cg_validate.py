@@ -61,6 +61,7 @@ def main():
     op = SlabOperator(ctx, pat, vals, slab)
     ones = torch.ones(slab.n_owned, dtype=torch.float64, device="cuda")
     y = torch.empty_like(ones)
+    op.matvec(ones, y)                       # warm-up: first NCCL point-to-point sets the channels up
     spmv_ms = timed(lambda: op.matvec(ones, y), 10)
     vol = y.sum().reshape(1).clone()
     if world > 1:
