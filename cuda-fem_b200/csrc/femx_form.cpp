@@ -709,6 +709,8 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
                      pat->nn, pat->nd, form->nn, form->nd);
   if (mesh->n_nodes != pat->n_nodes || mesh->n_elems != pat->n_elems)
     return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_csr: mesh sizes differ from the pattern's");
+  if (!form->ctx || !pat->ctx || form->ctx->device != pat->ctx->device)
+    return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_csr: form and pattern belong to different devices");
   if (!d_values && pat->nnz_node > 0)
     return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_csr: d_values is NULL");
   if (pat->n_rows == 0 || pat->nnz_node == 0) return FEMX_OK;
