@@ -23,6 +23,45 @@ __global__ void spmv_k(const int2* __restrict__ rowinfo, const int* __restrict__
   y[t] = (T)s;
 }
 
+// Scalar operators (nd == 1): one CTA per tile of node rows.  The tile's values and column list are
+// contiguous in the CSR arrays, so they are streamed into shared memory with fully coalesced
+// asynchronous copies (cp.async, all in flight at once); each thread then walks its own row out of
+// shared memory and only the x gathers go through L1/L2.  (Thread-per-row straight from global
+// memory reads each row with a 15-element stride between lanes.)
+template <class T, int TILE>
+__global__ void __launch_bounds__(TILE) spmv_tile_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx,
+                                                     int n_rows, const T* __restrict__ vals, const T* __restrict__ x,
+                                                     long long x_off, T* __restrict__ y) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int i0 = blockIdx.x * TILE;
+  const int nt = min(TILE, n_rows - i0);
+  const int base = rowinfo[i0].x;
+  const int cnt = rowinfo[i0 + nt].x - base;
+  T* s_v = reinterpret_cast<T*>(sm);
+  int* s_c = reinterpret_cast<int*>(s_v + cnt + (cnt & 1));
+  const unsigned vdst = (unsigned)__cvta_generic_to_shared(s_v), cdst = (unsigned)__cvta_generic_to_shared(s_c);
+  for (int j = threadIdx.x; j < cnt; j += TILE) {
+    if (sizeof(T) == 8)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(vdst + j * 8), "l"(vals + base + j) : "memory");
+    else
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(vdst + j * 4), "l"(vals + base + j) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cdst + j * 4), "l"(col_idx + base + j) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int lo = 0, len = 0;
+  if ((int)threadIdx.x < nt) {
+    lo = rowinfo[i0 + threadIdx.x].x - base;
+    len = rowinfo[i0 + threadIdx.x + 1].x - base - lo;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  if ((int)threadIdx.x < nt) {
+    double s = 0.0;
+    for (int p = 0; p < len; ++p) s += (double)s_v[lo + p] * (double)__ldg(x + ((long long)s_c[lo + p] - x_off));
+    y[i0 + threadIdx.x] = (T)s;
+  }
+}
+
 template <class T>
 __global__ void __launch_bounds__(256) dot2_partial(int64_t n, const T* __restrict__ a, const T* __restrict__ b,
                                                     const T* __restrict__ c, const T* __restrict__ d,
@@ -111,14 +150,29 @@ int femx_spmv(const femx_pattern* p, int dtype, const void* d_values, const void
   if (p->n_rows == 0) return FEMX_OK;
   FEMX_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
   int64_t n = p->n_rows * p->nd;
-  if (dtype == FEMX_F64)
+  const long long xb = (long long)x_base - (long long)p->nd * p->col_base;
+  const size_t rs = dtype == FEMX_F64 ? 8 : 4;
+  const size_t smem = (size_t)(p->max_tile_nnz + 2) * (rs + 4);
+  if (p->nd == 1 && p->tile_nodes == 128 && smem <= 200 * 1024) {
+    // tile-staged kernel (same 128-row tiles as the numeric pass)
+    const unsigned blocks = (unsigned)((p->n_rows + 127) / 128);
+    if (dtype == FEMX_F64) {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(spmv_tile_k<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      spmv_tile_k<double, 128><<<blocks, 128, smem, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows,
+                                                                             (const double*)d_values, (const double*)d_x, xb,
+                                                                             (double*)d_y);
+    } else {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(spmv_tile_k<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      spmv_tile_k<float, 128><<<blocks, 128, smem, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows,
+                                                                            (const float*)d_values, (const float*)d_x, xb,
+                                                                            (float*)d_y);
+    }
+  } else if (dtype == FEMX_F64)
     spmv_k<double><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
-                                                            (const double*)d_values, (const double*)d_x,
-                                                            (long long)x_base - (long long)p->nd * p->col_base, (double*)d_y);
+                                                            (const double*)d_values, (const double*)d_x, xb, (double*)d_y);
   else
     spmv_k<float><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
-                                                           (const float*)d_values, (const float*)d_x,
-                                                           (long long)x_base - (long long)p->nd * p->col_base, (float*)d_y);
+                                                           (const float*)d_values, (const float*)d_x, xb, (float*)d_y);
   FEMX_CUDA_OK(p->ctx, cudaGetLastError());
   return FEMX_OK;
 }
