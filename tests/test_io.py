@@ -57,6 +57,7 @@ def test_gmsh_errors(tmp_path):
     assert "unknown node" in str(ei.value)
 
 
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")
 def test_matrix_market_matches_scipy(tmp_path):
     import scipy.io
     import scipy.sparse as sp
@@ -71,6 +72,7 @@ def test_matrix_market_matches_scipy(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")
 def test_assemble_from_gmsh_file_and_export(ctx, tmp_path):
     """File in → assembled operator → file out, cross-checked with scipy."""
     import scipy.io
