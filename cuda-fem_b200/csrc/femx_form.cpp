@@ -20,6 +20,13 @@ struct Variant {
   int carveout_set = 0;
 };
 
+// a stencil class handed to the JIT (femx_pattern's dominant class, or an explicit one)
+struct StencilClass {
+  int np = 0, rlen = 0, self = 0;
+  std::vector<uint32_t> codes;
+  std::string key;
+};
+
 std::string num(double v) {
   char b[64];
   snprintf(b, sizeof b, "%.17g", v);
@@ -66,37 +73,81 @@ namespace {
 // with d_a = jac * grad phi_a (no division) and W, M_ab folded on the host from the
 // SAME quadrature rule (the reference's 8-digit literals in 2-D), so the values
 // equal the reference's quadrature sums up to rounding.
-void emit_geometry(int dim, std::string* pro) {
+// Every multiply-add is spelled out (fma / femx_mul) so that the rounding of an entry does not
+// depend on the compiler's contraction choices — the specialised and the generic numeric pass, the
+// COO kernel and any slab of a partitioned mesh produce the same bits.  Edges are taken from local
+// vertex 1: in the numeric pass that is the row's own node, so neighbouring incidences share them.
+//   2-D: d1 = (y2-y3, x3-x2), d2 = (y3-y1, x1-x3), d3 = -(d1+d2);  jac = d2y d1x - d2x d1y
+//        (= (x1-x3)(y2-y3)-(y1-y3)(x2-x3), fea_symbolic_nvrtc_sparse.cpp:258)
+//   3-D: d2 = u4 x u3, d3 = u2 x u4, d4 = u3 x u2, d1 = -(d2+d3+d4);  jac = u2 . d2
+//        (= det[x1-x4, x2-x4, x3-x4], the Jacobian of X = x1 r + x2 s + x3 t + x4 (1-r-s-t))
+std::string cross_c(const char* a, const char* b, int k) {  // component k of a x b, fused like fma(p, q, -(r*s))
+  static const char* ax[3] = {"x", "y", "z"};
+  const char *i = ax[(k + 1) % 3], *j = ax[(k + 2) % 3];
   std::ostringstream o;
-  if (dim == 2) {
+  o << "fma(" << a << i << "," << b << j << ",-femx_mul(" << a << j << "," << b << i << "))";
+  return o.str();
+}
+
+void emit_geometry(int dim, bool pinned, std::string* pro) {
+  std::ostringstream o;
+  if (!pinned) {
+    // vector forms (no specialised pass): plain expressions, contraction left to the compiler
+    if (dim == 2) {
+      o << "const real d1x = y2-y3, d1y = x3-x2;\n"
+           "  const real d2x = y3-y1, d2y = x1-x3;\n"
+           "  const real d3x = -(d1x+d2x), d3y = -(d1y+d2y);\n"
+           "  const real jac = d2y*d1x-d2x*d1y;\n"   // (x1-x3)(y2-y3)-(y1-y3)(x2-x3)
+           "  const real ijac = femx_rcp(jac);\n";
+    } else {
+      // X = x1 r + x2 s + x3 t + x4 (1-r-s-t); J[c][a] = dX_c/dref_a; d_a = jac * (row a of J^-1)
+      o << "const real j00 = x1-x4, j01 = x2-x4, j02 = x3-x4;\n"
+           "  const real j10 = y1-y4, j11 = y2-y4, j12 = y3-y4;\n"
+           "  const real j20 = z1-z4, j21 = z2-z4, j22 = z3-z4;\n"
+           "  const real d1x = j11*j22-j12*j21, d1y = j02*j21-j01*j22, d1z = j01*j12-j02*j11;\n"
+           "  const real d2x = j12*j20-j10*j22, d2y = j00*j22-j02*j20, d2z = j02*j10-j00*j12;\n"
+           "  const real d3x = j10*j21-j11*j20, d3y = j01*j20-j00*j21, d3z = j00*j11-j01*j10;\n"
+           "  const real d4x = -(d1x+d2x+d3x), d4y = -(d1y+d2y+d3y), d4z = -(d1z+d2z+d3z);\n"
+           "  const real jac = j00*d1x+j01*d2x+j02*d3x;\n"
+           "  const real ijac = femx_rcp(jac);\n";
+    }
+  } else if (dim == 2) {
     o << "const real d1x = y2-y3, d1y = x3-x2;\n"
          "  const real d2x = y3-y1, d2y = x1-x3;\n"
          "  const real d3x = -(d1x+d2x), d3y = -(d1y+d2y);\n"
-         "  const real jac = d2y*d1x-d2x*d1y;\n"   // (x1-x3)(y2-y3)-(y1-y3)(x2-x3)
+         "  const real jac = fma(d2y,d1x,-femx_mul(d2x,d1y));\n"   // (x1-x3)(y2-y3)-(y1-y3)(x2-x3)
          "  const real ijac = femx_rcp(jac);\n";
   } else {
-    // X = x1 r + x2 s + x3 t + x4 (1-r-s-t); J[c][a] = dX_c/dref_a; d_a = jac * (row a of J^-1)
-    o << "const real j00 = x1-x4, j01 = x2-x4, j02 = x3-x4;\n"
-         "  const real j10 = y1-y4, j11 = y2-y4, j12 = y3-y4;\n"
-         "  const real j20 = z1-z4, j21 = z2-z4, j22 = z3-z4;\n"
-         "  const real d1x = j11*j22-j12*j21, d1y = j02*j21-j01*j22, d1z = j01*j12-j02*j11;\n"
-         "  const real d2x = j12*j20-j10*j22, d2y = j00*j22-j02*j20, d2z = j02*j10-j00*j12;\n"
-         "  const real d3x = j10*j21-j11*j20, d3y = j01*j20-j00*j21, d3z = j00*j11-j01*j10;\n"
-         "  const real d4x = -(d1x+d2x+d3x), d4y = -(d1y+d2y+d3y), d4z = -(d1z+d2z+d3z);\n"
-         "  const real jac = j00*d1x+j01*d2x+j02*d3x;\n"
+    o << "const real u2x = x2-x1, u2y = y2-y1, u2z = z2-z1;\n"
+         "  const real u3x = x3-x1, u3y = y3-y1, u3z = z3-z1;\n"
+         "  const real u4x = x4-x1, u4y = y4-y1, u4z = z4-z1;\n";
+    const char* pairs[3][3] = {{"d2", "u4", "u3"}, {"d3", "u2", "u4"}, {"d4", "u3", "u2"}};
+    for (auto& pr : pairs) {
+      o << "  const real ";
+      for (int k = 0; k < 3; ++k) o << (k ? ", " : "") << pr[0] << "xyz"[k] << " = " << cross_c(pr[1], pr[2], k);
+      o << ";\n";
+    }
+    o << "  const real d1x = -(d2x+d3x+d4x), d1y = -(d2y+d3y+d4y), d1z = -(d2z+d3z+d4z);\n"
+         "  const real jac = fma(u2z,d2z,fma(u2y,d2y,femx_mul(u2x,d2x)));\n"
          "  const real ijac = femx_rcp(jac);\n";
   }
   *pro += o.str();
 }
 
-std::string dd(int dim, int a, int b) {  // d_a . d_b (1-based names)
+std::string dd(int dim, int a, int b, bool pinned = true) {  // d_a . d_b (1-based names)
   std::ostringstream o;
-  o << "(";
-  for (int k = 0; k < dim; ++k) {
-    if (k) o << "+";
-    o << "d" << a + 1 << AX[k] << "*d" << b + 1 << AX[k];
+  if (!pinned) {
+    o << "(";
+    for (int k = 0; k < dim; ++k) {
+      if (k) o << "+";
+      o << "d" << a + 1 << AX[k] << "*d" << b + 1 << AX[k];
+    }
+    o << ")";
+    return o.str();
   }
-  o << ")";
+  for (int k = dim - 1; k >= 1; --k) o << "fma(d" << a + 1 << AX[k] << ",d" << b + 1 << AX[k] << ",";
+  o << "femx_mul(d" << a + 1 << AX[0] << ",d" << b + 1 << AX[0] << ")";
+  for (int k = dim - 1; k >= 1; --k) o << ")";
   return o.str();
 }
 
@@ -110,7 +161,8 @@ double phi_at(const femx_form* f, int a, int q) {
 
 int emit_builtin(femx_form* f, const femx_form_desc* d) {
   const int dim = f->dim, nn = f->nn, nd = f->nd, n = f->n;
-  emit_geometry(dim, &f->prologue);
+  const bool pinned = nd == 1;  // scalar forms: every rounding fixed by the text (see emit_geometry)
+  emit_geometry(dim, pinned, &f->prologue);
   f->integrated = 1;
   f->entries.assign((size_t)n * n, "");
   double W = 0.0;
@@ -141,12 +193,13 @@ int emit_builtin(femx_form* f, const femx_form_desc* d) {
   f->rot_ok_matrix = !has_mass || msym;
   f->rot_ok_rhs = vsym;
   std::ostringstream pro;
-  pro << "  const real kq = " << num(W) << "*ijac;\n";
+  if (pinned) pro << "  const real kq = femx_mul(" << num(W) << ",ijac);\n";
+  else pro << "  const real kq = " << num(W) << "*ijac;\n";
   if (d->builtin == FEMX_FORM_ELASTICITY) {
     if (nd != dim) return FEMX_ERR_INVALID;
     for (int a = 0; a < nn; ++a)
       for (int b = a; b < nn; ++b)
-        pro << "  const real dd" << a + 1 << b + 1 << " = " << dd(dim, a, b) << ";\n";
+        pro << "  const real dd" << a + 1 << b + 1 << " = " << dd(dim, a, b, false) << ";\n";
     pro << "  const real LAMq = " << num(d->params[0]) << "*kq, MUq = " << num(d->params[1]) << "*kq;\n";
   }
   f->prologue += pro.str();
@@ -157,13 +210,13 @@ int emit_builtin(femx_form* f, const femx_form_desc* d) {
       std::ostringstream o;
       switch (d->builtin) {
         case FEMX_FORM_POISSON:
-          o << dd(dim, b, a) << "*kq";
+          o << "femx_mul(" << dd(dim, b, a) << ",kq)";
           break;
         case FEMX_FORM_POISSON_MASS:
-          o << dd(dim, b, a) << "*kq+" << num(cm * M[a][b]) << "*jac";
+          o << "fma(" << dd(dim, b, a) << ",kq,femx_mul(" << num(cm * M[a][b]) << ",jac))";
           break;
         case FEMX_FORM_MASS:
-          o << num(M[a][b]) << "*jac";
+          o << "femx_mul(" << num(M[a][b]) << ",jac)";
           break;
         case FEMX_FORM_ELASTICITY: {
           const int lo = a < b ? a : b, hi = a < b ? b : a;
@@ -246,7 +299,7 @@ bool depends_on_q(const std::string& e) {
 //   FEMX_ROWC_<li>              entries that do not depend on the quadrature point:
 //                               out[lj] = E (pre-integrated) or out[lj] = (sum_q w_q) * E
 //   FEMX_ROWQ_<li>(R,S,T,U,W)   one quadrature-point update of the entries that do
-std::string build_defines(const femx_form* f, const std::string& kernel) {
+std::string build_defines(const femx_form* f, const std::string& kernel, const StencilClass* sc) {
   std::ostringstream o;
   const int n = f->n;
   o << "#define FEMX_REAL " << (f->dtype == FEMX_F32 ? "float" : "double") << "\n";
@@ -383,11 +436,60 @@ std::string build_defines(const femx_form* f, const std::string& kernel) {
     o << " } break;";
   }
   o << "\n";
+  // Specialised body for one stencil class (scalar forms): the scatter codes are known here, so the
+  // incidence loop is unrolled on the host with every column position a literal — the coordinates of
+  // each column are loaded once into named registers, the row's values accumulate in registers
+  // (first touch: 0 + v, exactly as the generic path's shared-memory image) and are stored once.
+  // Per incidence the text is the generic case's: same bindings, same prologue, same row macro.
+  o << "#define FEMX_SPEC " << (sc ? 1 : 0) << "\n";
+  if (sc) {
+    const int dim = f->dim;
+    o << "#define FEMX_SPEC_BODY";
+    for (int k = 0; k < sc->rlen; ++k) {
+      o << " \\\n    const i64 q" << k << "_ = (i64)scol[" << k << "] * FEMX_CS; const real";
+      for (int c = 0; c < dim; ++c)
+        o << (c ? "," : "") << " c" << ax[c] << k << " = __ldg(" << "XYZ"[c] << " + q" << k << "_)";
+      o << ";";
+    }
+    o << " \\\n    real dacc0_ = real(0);";
+    for (int k = 0; k < sc->rlen; ++k)
+      if (k != sc->self) o << " real a" << k << "_;";
+    for (int it = 0; it < sc->np; ++it) {
+      const uint32_t code = sc->codes[it];
+      const int a = rotinv ? 0 : (int)((code >> 28) & 3);
+      o << " \\\n    {";
+      for (int c = 0; c < dim; ++c) {
+        o << " const real " << ax[c] << a + 1 << " = c" << ax[c] << sc->self << ";";
+        for (int j = 0; j < nn - 1; ++j)
+          o << " const real " << ax[c] << femx_oth(nn, a, j) + 1 << " = c" << ax[c] << ((code >> (7 * j)) & 127) << ";";
+      }
+      o << " \\\n      FEMX_PROLOGUE \\\n      { real out[NDOF];";
+      if (has_q[a]) o << " _Pragma(\"unroll\") for (int j_ = 0; j_ < NDOF; ++j_) out[j_] = real(0);";
+      o << " FEMX_ROWC_" << a;
+      if (has_q[a]) o << " FEMX_QUAD(FEMX_ROWQ_" << a << ")";
+      o << " \\\n        dacc0_ += out[" << a << "];";
+      for (int j = 0; j < nn - 1; ++j) {
+        const int pos = (int)((code >> (7 * j)) & 127);
+        o << " a" << pos << "_ = ";
+        if ((code >> (21 + j)) & 1) o << "real(0)"; else o << "a" << pos << "_";
+        o << " + out[" << femx_oth(nn, a, j) << "];";
+      }
+      o << " } }";
+    }
+    o << " \\\n   ";
+    for (int k = 0; k < sc->rlen; ++k)
+      if (k != sc->self) o << " srow[" << k << "] = a" << k << "_;";
+    o << " srow[" << sc->self << "] = dacc0_;\n";
+  }
   return o.str();
 }
 
-int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, bool load) {
-  auto it = f->variants.find(kernel);
+// kernel: "coo", "coo_e", "rhs", "csr" (unit node stride), "csr_s" (strided), "csr_x" (element-expanded
+// coordinates); sc != NULL: the csr kernel with a specialised body for that stencil class
+int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, bool load,
+                    const StencilClass* sc = nullptr) {
+  const std::string vkey = sc ? kernel + "@" + sc->key : kernel;
+  auto it = f->variants.find(vkey);
   if (it == f->variants.end()) {
     Variant v;
     const char* body = nullptr;
@@ -396,10 +498,12 @@ int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, boo
     else if (kernel == "rhs") body = kFemxJitRhs;
     else if (kernel == "csr" || kernel == "csr_x" || kernel == "csr_s") body = kFemxJitCsr;
     else return femx_fail(f->ctx, FEMX_ERR_INVALID, "unknown kernel variant '%s'", kernel.c_str());
-    v.source = "// femx JIT kernel '" + kernel + "' (generated)\n" + build_defines(f, kernel) +
+    if (sc && kernel != "csr" && kernel != "csr_s")
+      return femx_fail(f->ctx, FEMX_ERR_INVALID, "kernel '%s' has no specialised form", kernel.c_str());
+    v.source = "// femx JIT kernel '" + vkey + "' (generated)\n" + build_defines(f, kernel, sc) +
                kFemxJitCommon + body;
     nvrtcProgram prog;
-    std::string fname = "femx_" + kernel + ".cu";
+    std::string fname = "femx_" + kernel + (sc ? "_spec" : "") + ".cu";
     if (const char* dump = getenv("FEMX_JIT_DUMP")) {  // keep the source on disk (ncu --import-source)
       fname = std::string(dump) + "/" + fname;
       if (FILE* fp = fopen(fname.c_str(), "w")) { fwrite(v.source.data(), 1, v.source.size(), fp); fclose(fp); }
@@ -418,7 +522,7 @@ int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, boo
     f->last_log = v.log;
     if (r != NVRTC_SUCCESS) {
       nvrtcDestroyProgram(&prog);
-      f->err = "NVRTC compilation of kernel '" + kernel + "' failed:\n" + v.log;
+      f->err = "NVRTC compilation of kernel '" + vkey + "' failed:\n" + v.log;
       return femx_fail(f->ctx, FEMX_ERR_NVRTC, "%s", f->err.c_str());
     }
     size_t cs = 0;
@@ -430,7 +534,7 @@ int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, boo
     v.cubin.resize(cs);
     nvrtcGetCUBIN(prog, v.cubin.data());
     nvrtcDestroyProgram(&prog);
-    it = f->variants.emplace(kernel, std::move(v)).first;
+    it = f->variants.emplace(vkey, std::move(v)).first;
   }
   Variant& v = it->second;
   if (load && !v.fn) {
@@ -604,6 +708,39 @@ int femx_form_cubin(femx_form* form, const char* kernel, const void** cubin, siz
   return FEMX_OK;
 }
 
+int femx_form_cubin_stencil(femx_form* form, int n_incid, int row_len, int self_pos, const uint32_t* h_codes,
+                            const void** cubin, size_t* size) {
+  if (!form || !h_codes) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_form_cubin_stencil: NULL argument");
+  if (form->nd != 1) return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_form_cubin_stencil: scalar forms only");
+  if (n_incid < 1 || n_incid > FEMX_SPEC_MAX_NP || row_len < form->nn || row_len > FEMX_SPEC_MAX_RLEN ||
+      self_pos < 0 || self_pos >= row_len)
+    return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_form_cubin_stencil: class (%d incidences, %d columns, own %d) out of range",
+                     n_incid, row_len, self_pos);
+  StencilClass sc;
+  sc.np = n_incid; sc.rlen = row_len; sc.self = self_pos;
+  sc.codes.assign(h_codes, h_codes + n_incid);
+  unsigned long long h = 1469598103934665603ull;
+  for (int k = 0; k < n_incid; ++k) {
+    for (int j = 0; j < form->nn - 1; ++j) {
+      const int pos = (int)((h_codes[k] >> (7 * j)) & 127);
+      if (pos >= row_len || pos == self_pos)
+        return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_form_cubin_stencil: code %d names column %d", k, pos);
+    }
+    h = (h ^ h_codes[k]) * 1099511628211ull;
+  }
+  char key[96];
+  snprintf(key, sizeof key, "user%016llx_%d_%d_%d", h, n_incid, row_len, self_pos);
+  sc.key = key;
+  Variant* v = nullptr;
+  int st = compile_variant(form, "csr", &v, false, &sc);
+  if (st != FEMX_OK) return st;
+  form->last_source = v->source;
+  form->last_log = v->log;
+  if (cubin) *cubin = v->cubin.data();
+  if (size) *size = v->cubin.size();
+  return FEMX_OK;
+}
+
 int femx_assemble_coo(femx_form* form, const femx_mesh_view* mesh, void* d_A, int32_t* d_rowA,
                       int32_t* d_colA, void* stream) {
   if (!form) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_assemble_coo: form is NULL");
@@ -716,7 +853,18 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   if (pat->n_rows == 0 || pat->nnz_node == 0) return FEMX_OK;
   long long cs = mesh->node_stride ? mesh->node_stride : 1;
   Variant* v = nullptr;
-  st = compile_variant(form, expanded ? "csr_x" : (cs == 1 ? "csr" : "csr_s"), &v, true);
+  // The pattern's dominant stencil class gets a straight-line body when it covers most rows.  Only
+  // where both paths are certain to round identically: built-in forms (every fma spelled out) or
+  // strings compiled with --fmad=false.
+  StencilClass sc;
+  const bool spec = pat->spec_np > 0 && pat->spec_rows * 2 >= pat->n_rows && form->nd == 1 && !expanded &&
+                    (form->builtin != FEMX_FORM_CUSTOM || !form->fmad) &&
+                    !(getenv("FEMX_SPEC") && atoi(getenv("FEMX_SPEC")) == 0);
+  if (spec) {
+    sc.np = pat->spec_np; sc.rlen = pat->spec_rlen; sc.self = pat->spec_self;
+    sc.codes = pat->spec_codes; sc.key = pat->spec_key;
+  }
+  st = compile_variant(form, expanded ? "csr_x" : (cs == 1 ? "csr" : "csr_s"), &v, true, spec ? &sc : nullptr);
   if (st != FEMX_OK) return st;
   const femx_driver* drv = femx_get_driver(nullptr);
   const size_t rs = form->dtype == FEMX_F32 ? 4 : 8;

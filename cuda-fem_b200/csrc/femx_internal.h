@@ -72,7 +72,22 @@ struct femx_pattern {
   int32_t* d_sell_elem = nullptr;  // e*nn + li, ascending element order per row
   int64_t n_sell = 0;              // padded incidence count
   int64_t bytes = 0;
+  // Dominant stencil class (femx_pattern.cu: detect_stencil_class): the (incidence count, row length,
+  // own position, scatter-code sequence) shared by most rows — every interior row of a structured
+  // mesh.  Rows of the class carry FEMX_ROW_SPEC in rowinfo.y; a tile made of such rows only carries
+  // FEMX_TILE_SPEC on its first row.  The numeric pass may JIT a straight-line body for the class.
+  int spec_np = 0, spec_rlen = 0, spec_self = 0;
+  int64_t spec_rows = 0;
+  std::vector<uint32_t> spec_codes;  // host copy, spec_np entries
+  std::string spec_key;              // identifies the class in the form's kernel cache
 };
+
+// rowinfo[i].y = #incidences (bits 0-21) | FEMX_TILE_SPEC | FEMX_ROW_SPEC | own position << 24
+#define FEMX_NP_MASK 0x3fffff
+#define FEMX_TILE_SPEC (1 << 22)
+#define FEMX_ROW_SPEC (1 << 23)
+#define FEMX_SPEC_MAX_NP 32    // limits of a specialised stencil (register budget of the straight-line body)
+#define FEMX_SPEC_MAX_RLEN 24
 
 #define FEMX_DOT_BLOCKS 1024
 

@@ -42,6 +42,15 @@ __device__ __forceinline__ double femx_rcp(double a) {
   return x;
 }
 __device__ __forceinline__ float femx_rcp(float a) { return 1.0f / a; }
+// A product that must stay a product: the built-in forms spell every fused multiply-add out
+// (fma) and wrap the remaining products in femx_mul, so that no contraction decision is left to
+// the compiler and the specialised and the generic numeric pass round identically.
+__device__ __forceinline__ double femx_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float femx_mul(float a, float b) { return __fmul_rn(a, b); }
+// rowinfo[i].y = #incidences | FEMX_TILE_SPEC | FEMX_ROW_SPEC | own position << 24 (femx_internal.h)
+#define FEMX_NP_MASK 0x3fffff
+#define FEMX_TILE_SPEC (1 << 22)
+#define FEMX_ROW_SPEC (1 << 23)
 
 #define NDOF (NN * ND)
 // local index of the j-th other vertex of an incidence at local vertex li (even permutation; see femx_internal.h)
@@ -254,7 +263,13 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   extern __shared__ __align__(128) unsigned char femx_smem[];
   const int i0 = blockIdx.x * FEMX_TILE_NODES;
   const int nt = min(FEMX_TILE_NODES, n_rows - i0);
-  const int base = __ldg(&rowinfo[i0].x);
+  const int2 rt0 = __ldg(&rowinfo[i0]);
+  const int base = rt0.x;
+#if FEMX_SPEC
+  const bool tile_spec = (rt0.y & FEMX_TILE_SPEC) != 0;  // every row of the tile runs the specialised body: no codes needed
+#else
+  const bool tile_spec = false;
+#endif
   const int cntn = __ldg(&rowinfo[i0 + nt].x) - base;  // node-level nonzeros of the tile
   const int cnt = cntn * (ND * ND);
   const int sbase = __ldg(slice_ptr + (i0 >> 5));      // the tile's slices are contiguous
@@ -283,7 +298,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
 #else
     const unsigned cbytes = (unsigned)(((cph + cntn + 3) & ~3) * 4);
 #endif
-    const unsigned kbytes = (unsigned)ncode * 4u;
+    const unsigned kbytes = tile_spec ? 0u : (unsigned)ncode * 4u;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kbytes + cbytes) : "memory");
     if (kbytes)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -308,8 +323,16 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
     const int rstride = rlen * ND;  // dof row c of the node starts at srow + c*rstride
     const int sp = spg + (row & 31);
     const unsigned* sc = s_code + (sp - sbase);
-    const int np = r0.y & 0xffffff;
+    const int np = r0.y & FEMX_NP_MASK;
     if (np > 0) {
+#if FEMX_SPEC
+      if (r0.y & FEMX_ROW_SPEC) {
+        // the mesh's dominant stencil class: straight-line body generated for its scatter codes
+        const int* scol = s_cols + off;
+        FEMX_SPEC_BODY
+      } else
+#endif
+      {
       unsigned code = sc[0];
       const int ps = (int)((unsigned)r0.y >> 24) * ND;  // own column: the same for every incidence
       real ox[NN - 1], oy[NN - 1], oz[NN - 1];
@@ -425,6 +448,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
       for (int c = 0; c < ND; ++c)
 #pragma unroll
         for (int d = 0; d < ND; ++d) srow[c * rstride + ps + d] = dacc[c * ND + d];
+      }
     }
   }
   // ---- write the tile: generic-proxy writes -> async proxy, then one bulk store
@@ -468,7 +492,7 @@ femx_rhs(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   real racc[ND];
 #pragma unroll
   for (int d = 0; d < ND; ++d) racc[d] = real(0);
-  const int np = r0.y & 0xffffff;
+  const int np = r0.y & FEMX_NP_MASK;
   const int self_pos = (int)((unsigned)r0.y >> 24);
   for (int it = 0; it < np; ++it) {
     const unsigned code = __ldg(sell_code + sp + it * 32);

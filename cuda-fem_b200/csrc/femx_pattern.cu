@@ -12,6 +12,7 @@
 // The output is bit-identical to the reference's sorted std::set rows.
 #include <algorithm>
 #include <cstdio>
+#include <vector>
 
 #include "femx_internal.h"
 
@@ -299,6 +300,62 @@ __global__ void tile_max(const int2* __restrict__ rowinfo, const int* __restrict
   atomicMax(out + 1, slice_ptr[(i1 + 31) >> 5] - slice_ptr[i0 >> 5]);
 }
 
+// ------------------------------------------------------- stencil classes ---
+// Rows whose (incidence count, row length, own position, scatter-code sequence) coincide form a
+// stencil class: the numeric pass does exactly the same thing for each of them, only on different
+// nodes.  On a structured mesh every interior row is in one class.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsigned long long v) {
+  h += v + 0x9e3779b97f4a7c15ull;  // splitmix64 step
+  h = (h ^ (h >> 30)) * 0xbf58476d1ce4e5b9ull;
+  h = (h ^ (h >> 27)) * 0x94d049bb133111ebull;
+  return h ^ (h >> 31);
+}
+
+__global__ void row_class_hash(const int* __restrict__ pair_ptr, const unsigned* __restrict__ pair_code,
+                               const int2* __restrict__ rowinfo, int n_rows, unsigned long long* __restrict__ hash) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int lo = pair_ptr[r], hi = pair_ptr[r + 1];
+  const int2 ri = rowinfo[r];
+  const int rlen = rowinfo[r + 1].x - ri.x;
+  unsigned long long h = mix64(0x66656d78ull, (unsigned long long)(hi - lo) | ((unsigned long long)rlen << 24) |
+                                                  ((unsigned long long)((unsigned)ri.y >> 24) << 40));
+  for (int k = lo; k < hi; ++k) h = mix64(h, pair_code[k]);
+  hash[r] = h;
+}
+
+// flags the rows of the class of row `ref` (full comparison, the hash only filters) and counts them
+__global__ void mark_class(const int* __restrict__ pair_ptr, const unsigned* __restrict__ pair_code,
+                           int2* __restrict__ rowinfo, int n_rows, const unsigned long long* __restrict__ hash,
+                           int ref, int* __restrict__ count) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  bool match = false;
+  if (r < n_rows && hash[r] == hash[ref]) {
+    const int lo = pair_ptr[r], np = pair_ptr[r + 1] - lo;
+    const int rlo = pair_ptr[ref], rnp = pair_ptr[ref + 1] - rlo;
+    const int2 a = rowinfo[r], b = rowinfo[ref];
+    match = np == rnp && rowinfo[r + 1].x - a.x == rowinfo[ref + 1].x - b.x &&
+            ((unsigned)a.y >> 24) == ((unsigned)b.y >> 24);
+    for (int k = 0; match && k < np; ++k) match = pair_code[lo + k] == pair_code[rlo + k];
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, match);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
+  // `ref` itself is flagged last (by the host) so that it stays comparable while this kernel runs
+  if (match && r != ref) rowinfo[r].y |= FEMX_ROW_SPEC;
+}
+
+__global__ void mark_ref(int2* __restrict__ rowinfo, int ref) { rowinfo[ref].y |= FEMX_ROW_SPEC; }
+
+__global__ void mark_tiles(int2* __restrict__ rowinfo, int n_rows, int tile) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i0 = (int64_t)t * tile;
+  if (i0 >= n_rows) return;
+  const int i1 = (int)min((int64_t)n_rows, i0 + tile);
+  bool all = true;
+  for (int i = (int)i0; all && i < i1; ++i) all = (rowinfo[i].y & FEMX_ROW_SPEC) != 0;
+  if (all) rowinfo[i0].y |= FEMX_TILE_SPEC;
+}
+
 // ---------------------------------------------------------------- exports ---
 __global__ void export_csr_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx, int n_rows,
                              int nd, int col_base, long long* __restrict__ rp64, int* __restrict__ rp32,
@@ -368,6 +425,68 @@ int tmp_alloc(femx_ctx* ctx, T** p, int64_t n, cudaStream_t st) {
 }
 
 inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// Finds the dominant stencil class among evenly spaced sample rows, flags its rows / whole tiles in
+// rowinfo and keeps a host copy of the class's scatter codes for the JIT (femx_form.cpp).
+int detect_stencil_class(femx_ctx* ctx, femx_pattern* p, const int* d_pair_ptr, const unsigned* d_pair_code,
+                         cudaStream_t st) {
+  const int64_t nr = p->n_rows;
+  unsigned long long* d_hash = nullptr;
+  int* d_count = nullptr;
+  int rc = tmp_alloc(ctx, &d_hash, nr, st);
+  if (rc == FEMX_OK) rc = tmp_alloc(ctx, &d_count, 1, st);
+  auto done = [&](int code) {
+    cudaFreeAsync(d_hash, st);
+    cudaFreeAsync(d_count, st);
+    return code;
+  };
+  if (rc != FEMX_OK) return done(rc);
+#define SC_CUDA(call)                                                                                \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return done(femx_fail(ctx, FEMX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)));  \
+  } while (0)
+  row_class_hash<<<nblocks(nr, 128), 128, 0, st>>>(d_pair_ptr, d_pair_code, p->d_rowinfo, (int)nr, d_hash);
+  const int S = (int)std::min<int64_t>(nr, 256);
+  const int64_t stride = nr / S, start = stride / 2;
+  std::vector<unsigned long long> hs(S);
+  SC_CUDA(cudaMemcpy2DAsync(hs.data(), 8, d_hash + start, (size_t)stride * 8, 8, S, cudaMemcpyDeviceToHost, st));
+  SC_CUDA(cudaStreamSynchronize(st));
+  int best = -1, best_cnt = 0;
+  for (int i = 0; i < S; ++i) {
+    int c = 0;
+    for (int j = 0; j < S; ++j) c += hs[j] == hs[i];
+    if (c > best_cnt) { best_cnt = c; best = i; }
+  }
+  if (best < 0 || best_cnt * 4 < S) return done(FEMX_OK);  // no class covers a quarter of the samples
+  const int64_t ref = start + best * stride;
+  int2 ri[2];
+  int pp[2];
+  SC_CUDA(cudaMemcpyAsync(ri, p->d_rowinfo + ref, sizeof ri, cudaMemcpyDeviceToHost, st));
+  SC_CUDA(cudaMemcpyAsync(pp, d_pair_ptr + ref, sizeof pp, cudaMemcpyDeviceToHost, st));
+  SC_CUDA(cudaStreamSynchronize(st));
+  const int np = pp[1] - pp[0], rlen = ri[1].x - ri[0].x, self = (int)((unsigned)ri[0].y >> 24);
+  if (np < 1 || np > FEMX_SPEC_MAX_NP || rlen > (p->nn == 4 ? 16 : FEMX_SPEC_MAX_RLEN)) return done(FEMX_OK);
+  std::vector<uint32_t> codes(np);
+  SC_CUDA(cudaMemcpyAsync(codes.data(), d_pair_code + pp[0], sizeof(uint32_t) * np, cudaMemcpyDeviceToHost, st));
+  SC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), st));
+  mark_class<<<nblocks(nr, 128), 128, 0, st>>>(d_pair_ptr, d_pair_code, p->d_rowinfo, (int)nr, d_hash, (int)ref, d_count);
+  mark_ref<<<1, 1, 0, st>>>(p->d_rowinfo, (int)ref);
+  const int64_t ntiles = (nr + p->tile_nodes - 1) / p->tile_nodes;
+  mark_tiles<<<nblocks(ntiles, 128), 128, 0, st>>>(p->d_rowinfo, (int)nr, p->tile_nodes);
+  int cnt = 0;
+  SC_CUDA(cudaMemcpyAsync(&cnt, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SC_CUDA(cudaStreamSynchronize(st));
+  SC_CUDA(cudaGetLastError());
+#undef SC_CUDA
+  p->spec_np = np; p->spec_rlen = rlen; p->spec_self = self; p->spec_rows = cnt;
+  p->spec_codes = codes;
+  char key[96];
+  snprintf(key, sizeof key, "%016llx_%d_%d_%d", hs[best], np, rlen, self);
+  p->spec_key = key;
+  return done(FEMX_OK);
+}
 
 }  // namespace
 
@@ -521,6 +640,9 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
     int64_t ntiles = (nr + p->tile_nodes - 1) / p->tile_nodes;
     tile_max<<<nblocks(ntiles, 128), 128, 0, st>>>(p->d_rowinfo, p->d_slice_ptr, (int)nr, p->tile_nodes, d_flags + 2);
   }
+  // dominant stencil class (scalar problems; FEMX_SPEC=0 switches the detection off)
+  if (nd == 1 && nr > 0 && n_pairs > 0 && !(getenv("FEMX_SPEC") && atoi(getenv("FEMX_SPEC")) == 0))
+    PB_TRY(detect_stencil_class(ctx, p, d_pair_ptr, d_pair_code, st));
   PB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
   PB_CUDA(cudaStreamSynchronize(st));
   PB_CUDA(cudaGetLastError());
@@ -552,6 +674,18 @@ int femx_pattern_info(const femx_pattern* p, int64_t* n_rows, int64_t* nnz, int6
 }
 
 int64_t femx_pattern_bytes(const femx_pattern* p) { return p ? p->bytes : 0; }
+
+int femx_pattern_stencil(const femx_pattern* p, int* n_incid, int* row_len, int* self_pos, int64_t* rows,
+                         uint32_t* h_codes, int cap) {
+  if (!p) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_pattern_stencil: pattern is NULL");
+  if (n_incid) *n_incid = p->spec_np;
+  if (row_len) *row_len = p->spec_rlen;
+  if (self_pos) *self_pos = p->spec_self;
+  if (rows) *rows = p->spec_rows;
+  if (h_codes)
+    for (int k = 0; k < p->spec_np && k < cap; ++k) h_codes[k] = p->spec_codes[k];
+  return FEMX_OK;
+}
 
 int femx_pattern_export_csr(const femx_pattern* p, int64_t* d_rp64, int32_t* d_rp32, int32_t* d_col,
                             void* stream) {

@@ -53,6 +53,7 @@ SYMBOLS = [
     "femx_mesh_rectangle", "femx_mesh_expand", "femx_mesh_box",
     "femx_assemble_coo", "femx_pattern_build", "femx_pattern_destroy", "femx_pattern_info",
     "femx_pattern_bytes", "femx_pattern_export_csr", "femx_pattern_export_ell",
+    "femx_pattern_stencil", "femx_form_cubin_stencil",
     "femx_assemble_csr", "femx_assemble_rhs", "femx_apply_dirichlet", "femx_csr_to_ell", "femx_spmv", "femx_dot2", "femx_axpy_ratio",
     "femx_xpby_ratio", "femx_io_read_gmsh", "femx_io_free", "femx_io_write_matrix_market",
 ]
@@ -287,6 +288,15 @@ class Form:
         self._check(lib().femx_form_cubin(self.h, kernel.encode(), C.byref(p), C.byref(n)))
         return C.string_at(p.value, n.value)
 
+    def cubin_stencil(self, codes, row_len, self_pos):
+        """Numeric-pass kernel specialised for an explicit stencil class (diagnostic; works offline)."""
+        arr = (C.c_uint32 * len(codes))(*[int(c) for c in codes])
+        p = C.c_void_p()
+        n = C.c_size_t()
+        self._check(lib().femx_form_cubin_stencil(self.h, len(codes), int(row_len), int(self_pos), arr,
+                                                  C.byref(p), C.byref(n)))
+        return C.string_at(p.value, n.value)
+
     def _tdtype(self):
         import torch
         return torch.float64 if self.dtype == F64 else torch.float32
@@ -349,6 +359,16 @@ class Pattern:
     @property
     def bytes(self):
         return lib().femx_pattern_bytes(self.h)
+
+    def stencil(self):
+        """Dominant stencil class found by the symbolic pass: dict(n_incid, row_len, self_pos, rows,
+        codes); rows == 0 when there is none (unstructured mesh, nd > 1, FEMX_SPEC=0)."""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        r = C.c_int64()
+        codes = (C.c_uint32 * 32)()
+        self.ctx.check(lib().femx_pattern_stencil(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(r), codes, 32))
+        return dict(n_incid=a.value, row_len=b.value, self_pos=c.value, rows=r.value,
+                    codes=[int(codes[k]) for k in range(a.value)])
 
     def csr(self, index_dtype="int32", stream=None):
         import torch

@@ -72,9 +72,10 @@ def test_emitter_matches_reference_orientation():
     # entry (li, lj) = a(u=phi_lj, v=phi_li)*jac; Poisson is symmetric in the names
     f = femx.Form(None, 2, femx.POISSON, offline=True)
     # d_a = jac * grad(phi_a); kq = (sum of weights) / jac  →  (d_lj . d_li) * kq
-    assert f.entry(0, 1) == "(d2x*d1x+d2y*d1y)*kq"
-    assert f.entry(2, 0) == "(d1x*d3x+d1y*d3y)*kq"
-    assert "kq = real(0.50000001" in f.prologue  # the reference's 8-digit weights, summed
+    # (every multiply-add spelled out: the dot product is a chain of fma)
+    assert f.entry(0, 1) == "femx_mul(fma(d2y,d1y,femx_mul(d2x,d1x)),kq)"
+    assert f.entry(2, 0) == "femx_mul(fma(d1y,d3y,femx_mul(d1x,d3x)),kq)"
+    assert "kq = femx_mul(real(0.50000001" in f.prologue  # the reference's 8-digit weights, summed
     f.close()
 
 

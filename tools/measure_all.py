@@ -83,7 +83,8 @@ def main():
                "pattern_build_ms": pat_ms, "pattern_nnz_per_s": pat.nnz / (pat_ms * 1e-3), "pattern_bytes": pat.bytes,
                "csr_ms": ms, "csr_ms_min": ms_min, "elements_per_s": ne / (ms * 1e-3), "nnz_per_s": pat.nnz / (ms * 1e-3),
                "algorithmic_bytes": b_alg, "bytes_per_element": b_alg / ne, "achieved_GBs": b_alg / (ms * 1e-3) / 1e9,
-               "roofline_frac": b_alg / (ms * 1e-3) / 1e9 / PEAK, "peak_GBs": PEAK}
+               "roofline_frac": b_alg / (ms * 1e-3) / 1e9 / PEAK, "peak_GBs": PEAK,
+               "stencil_rows": pat.stencil()["rows"], "stencil_pass": os.environ.get("FEMX_SPEC", "1") != "0"}
         # ---- size-independent parity properties
         v2 = torch.empty_like(vals)
         form.assemble_csr(pat, mesh, v2)
