@@ -2,6 +2,7 @@
 // to an sm_100a cubin, and the launches of the two JIT kernels.
 #include <nvrtc.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <sstream>
@@ -305,7 +306,11 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
   o << "#define FEMX_REAL " << (f->dtype == FEMX_F32 ? "float" : "double") << "\n";
   o << "#define NN " << f->nn << "\n#define ND " << f->nd << "\n#define DIM " << f->dim
     << "\n#define FEMX_TILE_NODES " << femx_tile_nodes_for(f->nd) << "\n";
-  o << "#define FEMX_MIN_BLOCKS " << (getenv("FEMX_MINBLOCKS") ? atoi(getenv("FEMX_MINBLOCKS")) : 0) << "\n";
+  // (the specialised 3-D body holds 45 coordinates + 15 accumulators per thread: 512 threads per SM keep it at
+  //  128 registers without spills, measured faster than the 164 the compiler takes when left alone)
+  const int tile_nodes = femx_tile_nodes_for(f->nd);
+  const int min_blocks_default = sc && f->dim == 3 ? 512 / tile_nodes : 0;
+  o << "#define FEMX_MIN_BLOCKS " << (getenv("FEMX_MINBLOCKS") ? atoi(getenv("FEMX_MINBLOCKS")) : min_blocks_default) << "\n";
   o << "#define FEMX_MIDGATHER " << (getenv("FEMX_MIDGATHER") ? atoi(getenv("FEMX_MIDGATHER")) : 1) << "\n";
   o << "#define FEMX_UNROLL " << (getenv("FEMX_UNROLL") ? atoi(getenv("FEMX_UNROLL")) : 1) << "\n";
   o << "#define FEMX_EXPANDED " << (kernel == "csr_x" ? 1 : 0) << "\n";
@@ -444,13 +449,14 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
   o << "#define FEMX_SPEC " << (sc ? 1 : 0) << "\n";
   if (sc) {
     const int dim = f->dim;
-    o << "#define FEMX_SPEC_BODY";
+    o << "#define FEMX_SPEC_LOAD";
     for (int k = 0; k < sc->rlen; ++k) {
-      o << " \\\n    const i64 q" << k << "_ = (i64)scol[" << k << "] * FEMX_CS; const real";
+      o << " \\\n    const i64 q" << k << "_ = (i64)min(max(node_ + soff.v[" << k << "], 0), node_max) * FEMX_CS; const real";
       for (int c = 0; c < dim; ++c)
         o << (c ? "," : "") << " c" << ax[c] << k << " = __ldg(" << "XYZ"[c] << " + q" << k << "_)";
       o << ";";
     }
+    o << "\n#define FEMX_SPEC_BODY";
     o << " \\\n    real dacc0_ = real(0);";
     for (int k = 0; k < sc->rlen; ++k)
       if (k != sc->self) o << " real a" << k << "_;";
@@ -485,7 +491,8 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
 }
 
 // kernel: "coo", "coo_e", "rhs", "csr" (unit node stride), "csr_s" (strided), "csr_x" (element-expanded
-// coordinates); sc != NULL: the csr kernel with a specialised body for that stencil class
+// coordinates); sc != NULL: the csr kernel for a pattern with that stencil class (specialised body for
+// the class rows, row-list CTAs for the others)
 int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, bool load,
                     const StencilClass* sc = nullptr) {
   const std::string vkey = sc ? kernel + "@" + sc->key : kernel;
@@ -857,8 +864,12 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   // where both paths are certain to round identically: built-in forms (every fma spelled out) or
   // strings compiled with --fmad=false.
   StencilClass sc;
+  const size_t rs = form->dtype == FEMX_F32 ? 4 : 8;
+  // (the row-list CTAs of that kernel keep one private value segment per thread in shared memory:
+  //  patterns whose rows outside the class are very long stay on the generic kernel)
   const bool spec = pat->spec_np > 0 && pat->spec_rows * 2 >= pat->n_rows && form->nd == 1 && !expanded &&
                     (form->builtin != FEMX_FORM_CUSTOM || !form->fmad) &&
+                    (size_t)pat->tile_nodes * pat->max_row_other * rs <= 64 * 1024 &&
                     !(getenv("FEMX_SPEC") && atoi(getenv("FEMX_SPEC")) == 0);
   if (spec) {
     sc.np = pat->spec_np; sc.rlen = pat->spec_rlen; sc.self = pat->spec_self;
@@ -867,41 +878,49 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   st = compile_variant(form, expanded ? "csr_x" : (cs == 1 ? "csr" : "csr_s"), &v, true, spec ? &sc : nullptr);
   if (st != FEMX_OK) return st;
   const femx_driver* drv = femx_get_driver(nullptr);
-  const size_t rs = form->dtype == FEMX_F32 ? 4 : 8;
-  // [mbarrier 128 B | codes | values (+16 B phase pad) | columns (+32 B phase pad)]
-  size_t smem = 128 + (size_t)pat->max_tile_codes * 4 + (((size_t)pat->max_tile_nnz * form->nd * form->nd * rs + 15) / 16) * 16 + 32 +
-                (size_t)pat->max_tile_nnz * 4 + 32;
+  // generic kernel: [mbarrier 128 B | codes | values (+16 B phase pad) | columns (+32 B phase pad)];
+  // stencil-class kernel: [warp masks 128 B | row ends | values (+16 B phase pad)], or one value segment per thread
+  // in the row-list CTAs
+  const size_t img = (((size_t)pat->max_tile_nnz * form->nd * form->nd * rs + 15) / 16) * 16 + 32;
+  const int seg = pat->max_row_other * form->nd * form->nd;
+  const size_t spec_hdr = 128 + (((size_t)pat->tile_nodes * 4 + 127) / 128) * 128;  // FEMX_SPEC_HDR
+  size_t smem = spec ? std::max(spec_hdr + img, (size_t)pat->tile_nodes * seg * rs)
+                     : 128 + (size_t)pat->max_tile_codes * 4 + img + (size_t)pat->max_tile_nnz * 4 + 32;
   if (smem > form->ctx->smem_optin)
     return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED,
                      "femx_assemble_csr: a %d-row tile needs %zu B of shared memory (> %zu)",
                      pat->tile_nodes, smem, form->ctx->smem_optin);
-  if (!v->carveout_set || (int)smem > v->smem_set) {
-    // Shared-memory carve-out: just enough for the CTAs that registers/threads allow, the rest
-    // stays L1 for the coordinate gathers.  (FEMX_CARVEOUT=percent overrides: experiments.)
-    int pct = 0;
-    const char* cv = getenv("FEMX_CARVEOUT");
-    if (cv && *cv) {
-      pct = atoi(cv);
-    } else {
-      int regs = 64;
-      drv->FuncGetAttribute(&regs, CU_FUNC_ATTRIBUTE_NUM_REGS, v->fn);
-      const int threads = pat->tile_nodes;
-      const int regs_alloc = ((regs + 7) / 8) * 8;
-      int ctas = 65536 / (regs_alloc * threads);
-      if (ctas > 2048 / threads) ctas = 2048 / threads;
-      if (ctas > 32) ctas = 32;
-      if (ctas < 1) ctas = 1;
-      pct = (int)((ctas * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
-      if (pct > 100) pct = 100;
+  auto prepare = [&](Variant* vv, size_t bytes, int threads) -> int {
+    if (!vv->carveout_set || (int)bytes > vv->smem_set) {
+      // Shared-memory carve-out: just enough for the CTAs that registers/threads allow, the rest
+      // stays L1 for the coordinate gathers.  (FEMX_CARVEOUT=percent overrides: experiments.)
+      int pct = 0;
+      const char* cv = getenv("FEMX_CARVEOUT");
+      if (cv && *cv) {
+        pct = atoi(cv);
+      } else {
+        int regs = 64;
+        drv->FuncGetAttribute(&regs, CU_FUNC_ATTRIBUTE_NUM_REGS, vv->fn);
+        const int regs_alloc = ((regs + 7) / 8) * 8;
+        int ctas = 65536 / (regs_alloc * threads);
+        if (ctas > 2048 / threads) ctas = 2048 / threads;
+        if (ctas > 32) ctas = 32;
+        if (ctas < 1) ctas = 1;
+        pct = (int)((ctas * (bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+      }
+      drv->FuncSetAttribute(vv->fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct);
+      vv->carveout_set = 1;
     }
-    drv->FuncSetAttribute(v->fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct);
-    v->carveout_set = 1;
-  }
-  if ((int)smem > v->smem_set && smem > 48 * 1024) {
-    CUresult cr = drv->FuncSetAttribute(v->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
-    if (cr != CUDA_SUCCESS) return femx_fail(form->ctx, FEMX_ERR_CUDA, "cuFuncSetAttribute(smem=%zu) failed", smem);
-    v->smem_set = (int)smem;
-  }
+    if ((int)bytes > vv->smem_set && bytes > 48 * 1024) {
+      CUresult cr0 = drv->FuncSetAttribute(vv->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)bytes);
+      if (cr0 != CUDA_SUCCESS) return femx_fail(form->ctx, FEMX_ERR_CUDA, "cuFuncSetAttribute(smem=%zu) failed", bytes);
+      vv->smem_set = (int)bytes;
+    }
+    return FEMX_OK;
+  };
+  st = prepare(v, smem, pat->tile_nodes);
+  if (st != FEMX_OK) return st;
   const void* const* c = expanded ? mesh->d_elem_xyz : mesh->d_node_xyz;
   const void* X = c[0]; const void* Y = c[1]; const void* Z = c[2];
   int n_rows = (int)pat->n_rows;
@@ -910,9 +929,17 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   const int32_t* slice_ptr = pat->d_slice_ptr;
   const uint32_t* code = pat->d_sell_code;
   const int32_t* pelem = pat->d_sell_elem;
-  void* args[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &n_rows};
-  unsigned blocks = (unsigned)((pat->n_rows + pat->tile_nodes - 1) / pat->tile_nodes);
+  int row_node0 = (int)pat->row_begin, node_max = (int)pat->n_nodes - 1;
+  struct { int v[24]; } soff = {};
+  if (spec)
+    for (int k = 0; k < pat->spec_rlen; ++k) soff.v[k] = pat->spec_off[k];
+  const int32_t* rowlist = pat->d_other_rows;
+  int n_list = spec ? (int)pat->n_other : 0;
+  int seg_arg = seg;
+  void* args[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &n_rows,
+                  &row_node0, &node_max, &soff, &rowlist, &n_list, &seg_arg};
   unsigned threads = (unsigned)pat->tile_nodes;  // one thread per node row
+  unsigned blocks = (unsigned)((pat->n_rows + pat->tile_nodes - 1) / pat->tile_nodes) + (n_list + threads - 1) / threads;
   CUresult cr = drv->LaunchKernel(v->fn, blocks, 1, 1, threads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
   if (cr != CUDA_SUCCESS) {
     const char* es = nullptr;

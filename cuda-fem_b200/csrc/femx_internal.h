@@ -73,16 +73,20 @@ struct femx_pattern {
   int64_t n_sell = 0;              // padded incidence count
   int64_t bytes = 0;
   // Dominant stencil class (femx_pattern.cu: detect_stencil_class): the (incidence count, row length,
-  // own position, scatter-code sequence) shared by most rows — every interior row of a structured
-  // mesh.  Rows of the class carry FEMX_ROW_SPEC in rowinfo.y; a tile made of such rows only carries
-  // FEMX_TILE_SPEC on its first row.  The numeric pass may JIT a straight-line body for the class.
+  // own position, scatter-code sequence, column offsets from the own node) shared by most rows — every interior row of a structured
+  // mesh.  Rows of the class carry FEMX_ROW_SPEC in rowinfo.y; the others are listed in d_other_rows.
+  // The numeric pass may JIT a straight-line body for the class and run the listed rows separately.
   int spec_np = 0, spec_rlen = 0, spec_self = 0;
   int64_t spec_rows = 0;
   std::vector<uint32_t> spec_codes;  // host copy, spec_np entries
+  std::vector<int32_t> spec_off;     // column offsets from the row's own node (local ids), spec_rlen entries
   std::string spec_key;              // identifies the class in the form's kernel cache
+  int32_t* d_other_rows = nullptr;   // [n_other] rows outside the class, ascending (device)
+  int64_t n_other = 0;
+  int max_row_other = 0;             // longest of those rows
 };
 
-// rowinfo[i].y = #incidences (bits 0-21) | FEMX_TILE_SPEC | FEMX_ROW_SPEC | own position << 24
+// rowinfo[i].y = #incidences (bits 0-21) | (bit 22 reserved) | FEMX_ROW_SPEC | own position << 24
 #define FEMX_NP_MASK 0x3fffff
 #define FEMX_TILE_SPEC (1 << 22)
 #define FEMX_ROW_SPEC (1 << 23)

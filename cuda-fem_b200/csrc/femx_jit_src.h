@@ -47,10 +47,12 @@ __device__ __forceinline__ float femx_rcp(float a) { return 1.0f / a; }
 // the compiler and the specialised and the generic numeric pass round identically.
 __device__ __forceinline__ double femx_mul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ float femx_mul(float a, float b) { return __fmul_rn(a, b); }
-// rowinfo[i].y = #incidences | FEMX_TILE_SPEC | FEMX_ROW_SPEC | own position << 24 (femx_internal.h)
+// rowinfo[i].y = #incidences | FEMX_ROW_SPEC | own position << 24 (femx_internal.h)
 #define FEMX_NP_MASK 0x3fffff
 #define FEMX_TILE_SPEC (1 << 22)
 #define FEMX_ROW_SPEC (1 << 23)
+// column offsets (column - own node) of the pattern's stencil class, passed by value at launch
+struct femx_soff { int v[24]; };
 
 #define NDOF (NN * ND)
 // local index of the j-th other vertex of an incidence at local vertex li (even permutation; see femx_internal.h)
@@ -237,6 +239,8 @@ __device__ __forceinline__ float femx_ldg_if(const float* p, int pred) {
 #define FEMX_BOUNDS __launch_bounds__(FEMX_TILE_NODES)
 #endif
 #define FEMX_EPV (16 / (int)sizeof(real))  // values per 16 bytes
+// header of the stencil-class kernel's shared memory: warp masks (128 B) + per-row value ends
+#define FEMX_SPEC_HDR (128 + ((FEMX_TILE_NODES * 4 + 127) / 128) * 128)
 
 // Scatter code of one incidence (row node = local node li of element e):
 //   bits  0-6, 7-13, 14-20 : positions in the row's column list of the OTHER vertices,
@@ -254,40 +258,239 @@ __device__ __forceinline__ float femx_ldg_if(const float* p, int pred) {
 //   gathered node coordinates come through L1 (read-only path), software-pipelined.
 #define FEMX_FIRST(J) ((code >> (21 + (J))) & 1u)
 
+// ---- one row by the generic incidence loop -------------------------------------------------
+//   sc    the row's scatter codes, consecutive incidences 32 words apart (SELL-32)
+//   scol  the row's sorted column list (LOCAL node ids)
+//   pelem the row's e*NN+li list (SELL-32; element-expanded coordinates only)
+//   srow  the row's value segment (private to the thread), rstride = row length * ND
+// Tile mode passes shared-memory copies of codes and columns (staged by TMA), row-list mode reads
+// them straight from global memory; the arithmetic — and therefore every bit of the result — is the same.
+__device__ __forceinline__ void femx_generic_row(const int2 r0, const int np, const int rstride, real* srow,
+                                                 const unsigned* sc, const int* scol, const int* pelem,
+                                                 const real* __restrict__ X, const real* __restrict__ Y,
+                                                 const real* __restrict__ Z, const i64 cs) {
+  unsigned code = sc[0];
+  const int ps = (int)((unsigned)r0.y >> 24) * ND;  // own column: the same for every incidence
+  real ox[NN - 1], oy[NN - 1], oz[NN - 1];
+#if FEMX_EXPANDED
+  // element-expanded coordinates X[NN*e + a] (the reference's layout, SURVEY Q17)
+  real sx, sy, sz = real(0);
+  {
+    const int ea = __ldg(pelem);  // e*NN + li
+    const int li = (code >> 28) & 3;
+    const int e0 = ea - li;
+    sx = __ldg(X + ea); sy = __ldg(Y + ea);
+    if (DIM == 3) sz = __ldg(Z + ea);
+#pragma unroll
+    for (int j = 0; j < NN - 1; ++j) {
+      const int b = FEMX_OTH(li, j);
+      ox[j] = __ldg(X + e0 + b); oy[j] = __ldg(Y + e0 + b);
+      oz[j] = DIM == 3 ? __ldg(Z + e0 + b) : real(0);
+    }
+  }
+#else
+  // the row's own node is a vertex of every incident element: it stays in registers
+  const i64 pself = (i64)scol[(unsigned)r0.y >> 24] * FEMX_CS;
+  const real sx = __ldg(X + pself), sy = __ldg(Y + pself), sz = DIM == 3 ? __ldg(Z + pself) : real(0);
+#pragma unroll
+  for (int j = 0; j < NN - 1; ++j) {
+    const i64 p = (i64)scol[(code >> (7 * j)) & 127] * FEMX_CS;
+    ox[j] = __ldg(X + p); oy[j] = __ldg(Y + p);
+    oz[j] = DIM == 3 ? __ldg(Z + p) : real(0);
+  }
+#endif
+  real dacc[ND * ND];  // the diagonal block (own column) accumulates in registers
+#pragma unroll
+  for (int d = 0; d < ND * ND; ++d) dacc[d] = real(0);
+#if FEMX_MIDGATHER && !FEMX_EXPANDED
+  // One coordinate buffer: the gathers of incidence it+1 are issued in the MIDDLE of incidence
+  // it, right after its geometry prologue has consumed the coordinates (saves the second
+  // buffer's registers; the loads fly during the entry evaluation and the scatter).
+#pragma unroll 1
+  for (int it = 0; it < np; ++it) {
+    const int more = it + 1 < np;
+    sc += more ? 32 : 0;
+    const unsigned ncd = *sc;
+    int nidx[NN - 1];
+#pragma unroll
+    for (int j = 0; j < NN - 1; ++j) nidx[j] = scol[(ncd >> (7 * j)) & 127];
+    int po[NN - 1];
+#pragma unroll
+    for (int j = 0; j < NN - 1; ++j) po[j] = ((code >> (7 * j)) & 127) * ND;
+#define FEMX_GATHER_NEXT                                                        \
+    _Pragma("unroll") for (int j = 0; j < NN - 1; ++j) {                    \
+      const i64 p_ = (i64)nidx[j] * FEMX_CS;                                \
+      ox[j] = femx_ldg_if(X + p_, more); oy[j] = femx_ldg_if(Y + p_, more); \
+      if (DIM == 3) oz[j] = femx_ldg_if(Z + p_, more);                      \
+    }
+    switch (FEMX_ROTINV ? 0 : (int)((code >> 28) & 3)) {
+      FEMX_CSR_CASES
+    }
+#undef FEMX_GATHER_NEXT
+    code = ncd;
+  }
+#else
+#define FEMX_GATHER_NEXT
+#pragma unroll FEMX_UNROLL
+  for (int it = 0; it < np; ++it) {
+    // ---- software pipeline: the gathers of incidence it+1 are issued first
+    const int more = it + 1 < np;
+    sc += more ? 32 : 0;
+    const unsigned ncd = *sc;
+    real nox[NN - 1], noy[NN - 1], noz[NN - 1];
+#if FEMX_EXPANDED
+    pelem += more ? 32 : 0;
+    real nsx, nsy, nsz = real(0);
+    {
+      const int ea = __ldg(pelem);
+      const int nli = (ncd >> 28) & 3;
+      const int e0 = ea - nli;
+      nsx = femx_ldg_if(X + ea, more); nsy = femx_ldg_if(Y + ea, more);
+      if (DIM == 3) nsz = femx_ldg_if(Z + ea, more);
+#pragma unroll
+      for (int j = 0; j < NN - 1; ++j) {
+        const int b = FEMX_OTH(nli, j);
+        nox[j] = femx_ldg_if(X + e0 + b, more); noy[j] = femx_ldg_if(Y + e0 + b, more);
+        noz[j] = DIM == 3 ? femx_ldg_if(Z + e0 + b, more) : real(0);
+      }
+    }
+#else
+#pragma unroll
+    for (int j = 0; j < NN - 1; ++j) {
+      const i64 p = (i64)scol[(ncd >> (7 * j)) & 127] * FEMX_CS;
+      nox[j] = femx_ldg_if(X + p, more); noy[j] = femx_ldg_if(Y + p, more);
+      noz[j] = DIM == 3 ? femx_ldg_if(Z + p, more) : real(0);
+    }
+#endif
+    // ---- evaluate incidence it: row li*ND + c of the element matrix
+    int po[NN - 1];
+#pragma unroll
+    for (int j = 0; j < NN - 1; ++j) po[j] = ((code >> (7 * j)) & 127) * ND;
+    switch (FEMX_ROTINV ? 0 : (int)((code >> 28) & 3)) {
+      FEMX_CSR_CASES
+    }
+    code = ncd;
+#pragma unroll
+    for (int j = 0; j < NN - 1; ++j) { ox[j] = nox[j]; oy[j] = noy[j]; oz[j] = noz[j]; }
+#if FEMX_EXPANDED
+    sx = nsx; sy = nsy; sz = nsz;
+#endif
+  }
+#undef FEMX_GATHER_NEXT
+#endif
+#pragma unroll
+  for (int c = 0; c < ND; ++c)
+#pragma unroll
+    for (int d = 0; d < ND; ++d) srow[c * rstride + ps + d] = dacc[c * ND + d];
+}
+
 extern "C" __global__ void FEMX_BOUNDS
 femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
          const int* __restrict__ col_loc, const unsigned* __restrict__ sell_code,
          const int* __restrict__ sell_elem, const real* __restrict__ X,
          const real* __restrict__ Y, const real* __restrict__ Z, const i64 cs,
-         real* __restrict__ vals, const int n_rows) {
+         real* __restrict__ vals, const int n_rows, const int row_node0, const int node_max,
+         const femx_soff soff, const int* __restrict__ rowlist, const int n_list, const int seg) {
   extern __shared__ __align__(128) unsigned char femx_smem[];
-  const int i0 = blockIdx.x * FEMX_TILE_NODES;
-  const int nt = min(FEMX_TILE_NODES, n_rows - i0);
-  const int2 rt0 = __ldg(&rowinfo[i0]);
-  const int base = rt0.x;
 #if FEMX_SPEC
-  const bool tile_spec = (rt0.y & FEMX_TILE_SPEC) != 0;  // every row of the tile runs the specialised body: no codes needed
+  // ---- pattern with a stencil class.  The first CTAs take the rows OUTSIDE the class (the boundary
+  // rows of a structured mesh; compacted list, one thread each, generic incidence loop, codes and
+  // columns read straight from global memory, no barriers); the others take tiles of class rows.
+  // The two kinds write disjoint parts of `vals`.
+  const int n_lb = (n_list + FEMX_TILE_NODES - 1) / FEMX_TILE_NODES;
+  if ((int)blockIdx.x < n_lb) {
+    const int k_ = blockIdx.x * FEMX_TILE_NODES + threadIdx.x;
+    if (k_ >= n_list) return;
+    const int row = __ldg(rowlist + k_);
+    const int2 r0 = __ldg(&rowinfo[row]);
+    const int rlen = __ldg(&rowinfo[row + 1].x) - r0.x;
+    const int np = r0.y & FEMX_NP_MASK;
+    real* srow = reinterpret_cast<real*>(femx_smem) + (size_t)threadIdx.x * seg;
+    if (np > 0) {
+      const int sp = __ldg(slice_ptr + (row >> 5)) + (row & 31);
+      femx_generic_row(r0, np, rlen * ND, srow, sell_code + sp, col_loc + r0.x, sell_elem + sp, X, Y, Z, cs);
+      real* dst = vals + (i64)r0.x * (ND * ND);
+      for (int j = 0; j < rlen * (ND * ND); ++j) dst[j] = srow[j];
+    }
+    return;
+  }
+  const int i0 = (blockIdx.x - n_lb) * FEMX_TILE_NODES;
 #else
-  const bool tile_spec = false;
+  const int i0 = blockIdx.x * FEMX_TILE_NODES;
 #endif
+  const int nt = min(FEMX_TILE_NODES, n_rows - i0);
+#if FEMX_SPEC
+  // Speculative gathers, issued before any metadata has arrived: a row of the stencil class finds its
+  // columns at (own node + constant offset), so their coordinates need neither the row pointers nor
+  // the column list.  (Clamped: for a row outside the class the values are simply not used.)
+  const int node_ = row_node0 + i0 + min((int)threadIdx.x, nt - 1);
+  FEMX_SPEC_LOAD
+#endif
+  const int base = __ldg(&rowinfo[i0].x);
   const int cntn = __ldg(&rowinfo[i0 + nt].x) - base;  // node-level nonzeros of the tile
   const int cnt = cntn * (ND * ND);
+  const i64 vb = (i64)base * (ND * ND);              // first value index of the tile
+  const int vph = (int)(vb & (FEMX_EPV - 1));         // phase of the value run (elements)
+  const int ln = threadIdx.x;  // one thread per node row (all ND dof rows of the node)
+  const int rowc = i0 + min(ln, nt - 1);
+  const int2 r0 = __ldg(&rowinfo[rowc]);
+  const int rnext = __ldg(&rowinfo[rowc + 1].x);
+#if FEMX_SPEC
+  // ---- tile of class rows: the straight-line body generated for the class's scatter codes; nothing
+  // is staged in (no codes, no column list, no mbarrier).  smem: [class mask of each warp (128 B) | end
+  // of each row's values | values], the values placed with the 16-byte phase of their global address
+  // (aligned bulk stores).
+  unsigned* s_mask = reinterpret_cast<unsigned*>(femx_smem);
+  int* s_end = reinterpret_cast<int*>(femx_smem + 128);   // s_end[i]: end of row i's values, relative to the tile
+  real* s_vals = reinterpret_cast<real*>(femx_smem + FEMX_SPEC_HDR) + vph;
+  const bool mine = ln < nt && (r0.y & FEMX_ROW_SPEC);
+  {
+    const unsigned wm = __ballot_sync(0xffffffffu, mine);
+    if ((ln & 31) == 0) s_mask[ln >> 5] = wm;
+    if (ln < nt) s_end[ln] = (rnext - base) * (ND * ND);
+  }
+  if (mine) {
+    real* srow = s_vals + (r0.x - base) * (ND * ND);
+    FEMX_SPEC_BODY
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  // ---- write the tile: one bulk store per maximal run of class rows, issued by the run's first row
+  // (the rows in between belong to the row-list CTAs and must not be touched)
+  if (mine && (ln == 0 || !((s_mask[(ln - 1) >> 5] >> ((ln - 1) & 31)) & 1u))) {
+    int e = ln + 1;  // first row after the run
+    while (e < nt) {
+      const unsigned z = (~s_mask[e >> 5]) >> (e & 31);
+      if (z) { e += __ffs(z) - 1; break; }
+      e = (e | 31) + 1;
+    }
+    e = min(e, nt);
+    const int a0 = (r0.x - base) * (ND * ND);
+    const int n = s_end[e - 1] - a0;
+    real* dst = vals + vb + a0;
+    const real* src = s_vals + a0;
+    const int head = min(n, (FEMX_EPV - (int)((vb + a0) & (FEMX_EPV - 1))) & (FEMX_EPV - 1));
+    const int mid = (n - head) & ~(FEMX_EPV - 1);
+    if (mid > 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   ::"l"(dst + head), "r"((unsigned)__cvta_generic_to_shared(src + head)), "r"((unsigned)(mid * sizeof(real))) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    for (int j = 0; j < head; ++j) dst[j] = src[j];                    // ragged ends: < 16 bytes each
+    for (int j = head + mid; j < n; ++j) dst[j] = src[j];
+    if (mid > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+#else
   const int sbase = __ldg(slice_ptr + (i0 >> 5));      // the tile's slices are contiguous
   const int ncode = __ldg(slice_ptr + ((i0 + nt + 31) >> 5)) - sbase;
   // smem: [mbarrier | codes | values | columns].  Values and columns are placed with the
   // same 16-byte phase as their global addresses so that bulk copies are aligned.
-  const i64 vb = (i64)base * (ND * ND);              // first value index of the tile
-  const int vph = (int)(vb & (FEMX_EPV - 1));         // phase of the value run (elements)
   const int cph = base & 3;                           // phase of the column run (ints)
   unsigned* s_code = reinterpret_cast<unsigned*>(femx_smem + 128);
   real* s_vals = reinterpret_cast<real*>(s_code + ncode) + vph;
   const int vspan = (vph + cnt + FEMX_EPV - 1) & ~(FEMX_EPV - 1);
   int* s_cols = reinterpret_cast<int*>(s_vals - vph + vspan) + cph;
-  // per-row metadata: issued before the staging wait so that its latency overlaps the bulk copies
-  const int ln = threadIdx.x;  // one thread per node row (all ND dof rows of the node)
-  const int rowc = i0 + min(ln, nt - 1);
-  const int2 r0 = __ldg(&rowinfo[rowc]);
-  const int rnext = __ldg(&rowinfo[rowc + 1].x);
+  // per-row metadata (above) is issued before the staging wait so that its latency overlaps the bulk copies
   const int spg = __ldg(slice_ptr + (rowc >> 5));
   const unsigned bar = (unsigned)__cvta_generic_to_shared(femx_smem);
   if (threadIdx.x == 0) {
@@ -298,7 +501,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
 #else
     const unsigned cbytes = (unsigned)(((cph + cntn + 3) & ~3) * 4);
 #endif
-    const unsigned kbytes = tile_spec ? 0u : (unsigned)ncode * 4u;
+    const unsigned kbytes = (unsigned)ncode * 4u;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kbytes + cbytes) : "memory");
     if (kbytes)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -319,137 +522,11 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
     const int row = i0 + ln;
     const int rlen = rnext - r0.x;
     const int off = r0.x - base;
-    real* srow = s_vals + off * (ND * ND);
-    const int rstride = rlen * ND;  // dof row c of the node starts at srow + c*rstride
     const int sp = spg + (row & 31);
-    const unsigned* sc = s_code + (sp - sbase);
     const int np = r0.y & FEMX_NP_MASK;
-    if (np > 0) {
-#if FEMX_SPEC
-      if (r0.y & FEMX_ROW_SPEC) {
-        // the mesh's dominant stencil class: straight-line body generated for its scatter codes
-        const int* scol = s_cols + off;
-        FEMX_SPEC_BODY
-      } else
-#endif
-      {
-      unsigned code = sc[0];
-      const int ps = (int)((unsigned)r0.y >> 24) * ND;  // own column: the same for every incidence
-      real ox[NN - 1], oy[NN - 1], oz[NN - 1];
-#if FEMX_EXPANDED
-      // element-expanded coordinates X[NN*e + a] (the reference's layout, SURVEY Q17)
-      const int* pelem = sell_elem + sp;
-      real sx, sy, sz = real(0);
-      {
-        const int ea = __ldg(pelem);  // e*NN + li
-        const int li = (code >> 28) & 3;
-        const int e0 = ea - li;
-        sx = __ldg(X + ea); sy = __ldg(Y + ea);
-        if (DIM == 3) sz = __ldg(Z + ea);
-#pragma unroll
-        for (int j = 0; j < NN - 1; ++j) {
-          const int b = FEMX_OTH(li, j);
-          ox[j] = __ldg(X + e0 + b); oy[j] = __ldg(Y + e0 + b);
-          oz[j] = DIM == 3 ? __ldg(Z + e0 + b) : real(0);
-        }
-      }
-#else
-      // the row's own node is a vertex of every incident element: it stays in registers
-      const int* scol = s_cols + off;
-      const i64 pself = (i64)scol[(unsigned)r0.y >> 24] * FEMX_CS;
-      const real sx = __ldg(X + pself), sy = __ldg(Y + pself), sz = DIM == 3 ? __ldg(Z + pself) : real(0);
-#pragma unroll
-      for (int j = 0; j < NN - 1; ++j) {
-        const i64 p = (i64)scol[(code >> (7 * j)) & 127] * FEMX_CS;
-        ox[j] = __ldg(X + p); oy[j] = __ldg(Y + p);
-        oz[j] = DIM == 3 ? __ldg(Z + p) : real(0);
-      }
-#endif
-      real dacc[ND * ND];  // the diagonal block (own column) accumulates in registers
-#pragma unroll
-      for (int d = 0; d < ND * ND; ++d) dacc[d] = real(0);
-#if FEMX_MIDGATHER && !FEMX_EXPANDED
-      // One coordinate buffer: the gathers of incidence it+1 are issued in the MIDDLE of incidence
-      // it, right after its geometry prologue has consumed the coordinates (saves the second
-      // buffer's registers; the loads fly during the entry evaluation and the scatter).
-#pragma unroll 1
-      for (int it = 0; it < np; ++it) {
-        const int more = it + 1 < np;
-        sc += more ? 32 : 0;
-        const unsigned ncd = *sc;
-        int nidx[NN - 1];
-#pragma unroll
-        for (int j = 0; j < NN - 1; ++j) nidx[j] = scol[(ncd >> (7 * j)) & 127];
-        int po[NN - 1];
-#pragma unroll
-        for (int j = 0; j < NN - 1; ++j) po[j] = ((code >> (7 * j)) & 127) * ND;
-#define FEMX_GATHER_NEXT                                                        \
-        _Pragma("unroll") for (int j = 0; j < NN - 1; ++j) {                    \
-          const i64 p_ = (i64)nidx[j] * FEMX_CS;                                \
-          ox[j] = femx_ldg_if(X + p_, more); oy[j] = femx_ldg_if(Y + p_, more); \
-          if (DIM == 3) oz[j] = femx_ldg_if(Z + p_, more);                      \
-        }
-        switch (FEMX_ROTINV ? 0 : (int)((code >> 28) & 3)) {
-          FEMX_CSR_CASES
-        }
-#undef FEMX_GATHER_NEXT
-        code = ncd;
-      }
-#else
-#define FEMX_GATHER_NEXT
-#pragma unroll FEMX_UNROLL
-      for (int it = 0; it < np; ++it) {
-        // ---- software pipeline: the gathers of incidence it+1 are issued first
-        const int more = it + 1 < np;
-        sc += more ? 32 : 0;
-        const unsigned ncd = *sc;
-        real nox[NN - 1], noy[NN - 1], noz[NN - 1];
-#if FEMX_EXPANDED
-        pelem += more ? 32 : 0;
-        real nsx, nsy, nsz = real(0);
-        {
-          const int ea = __ldg(pelem);
-          const int nli = (ncd >> 28) & 3;
-          const int e0 = ea - nli;
-          nsx = femx_ldg_if(X + ea, more); nsy = femx_ldg_if(Y + ea, more);
-          if (DIM == 3) nsz = femx_ldg_if(Z + ea, more);
-#pragma unroll
-          for (int j = 0; j < NN - 1; ++j) {
-            const int b = FEMX_OTH(nli, j);
-            nox[j] = femx_ldg_if(X + e0 + b, more); noy[j] = femx_ldg_if(Y + e0 + b, more);
-            noz[j] = DIM == 3 ? femx_ldg_if(Z + e0 + b, more) : real(0);
-          }
-        }
-#else
-#pragma unroll
-        for (int j = 0; j < NN - 1; ++j) {
-          const i64 p = (i64)scol[(ncd >> (7 * j)) & 127] * FEMX_CS;
-          nox[j] = femx_ldg_if(X + p, more); noy[j] = femx_ldg_if(Y + p, more);
-          noz[j] = DIM == 3 ? femx_ldg_if(Z + p, more) : real(0);
-        }
-#endif
-        // ---- evaluate incidence it: row li*ND + c of the element matrix
-        int po[NN - 1];
-#pragma unroll
-        for (int j = 0; j < NN - 1; ++j) po[j] = ((code >> (7 * j)) & 127) * ND;
-        switch (FEMX_ROTINV ? 0 : (int)((code >> 28) & 3)) {
-          FEMX_CSR_CASES
-        }
-        code = ncd;
-#pragma unroll
-        for (int j = 0; j < NN - 1; ++j) { ox[j] = nox[j]; oy[j] = noy[j]; oz[j] = noz[j]; }
-#if FEMX_EXPANDED
-        sx = nsx; sy = nsy; sz = nsz;
-#endif
-      }
-#undef FEMX_GATHER_NEXT
-#endif
-#pragma unroll
-      for (int c = 0; c < ND; ++c)
-#pragma unroll
-        for (int d = 0; d < ND; ++d) srow[c * rstride + ps + d] = dacc[c * ND + d];
-      }
-    }
+    if (np > 0)
+      femx_generic_row(r0, np, rlen * ND, s_vals + off * (ND * ND), s_code + (sp - sbase), s_cols + off,
+                       sell_elem + sp, X, Y, Z, cs);
   }
   // ---- write the tile: generic-proxy writes -> async proxy, then one bulk store
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -470,6 +547,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
       dst[mid + threadIdx.x] = s_vals[mid + threadIdx.x];
     if (threadIdx.x == 0 && mid > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
+#endif
 }
 )FEMX";
 

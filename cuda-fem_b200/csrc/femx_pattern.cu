@@ -312,7 +312,8 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsign
 }
 
 __global__ void row_class_hash(const int* __restrict__ pair_ptr, const unsigned* __restrict__ pair_code,
-                               const int2* __restrict__ rowinfo, int n_rows, unsigned long long* __restrict__ hash) {
+                               const int2* __restrict__ rowinfo, const int* __restrict__ col_idx, int row_begin,
+                               int n_rows, unsigned long long* __restrict__ hash) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   const int lo = pair_ptr[r], hi = pair_ptr[r + 1];
@@ -321,13 +322,14 @@ __global__ void row_class_hash(const int* __restrict__ pair_ptr, const unsigned*
   unsigned long long h = mix64(0x66656d78ull, (unsigned long long)(hi - lo) | ((unsigned long long)rlen << 24) |
                                                   ((unsigned long long)((unsigned)ri.y >> 24) << 40));
   for (int k = lo; k < hi; ++k) h = mix64(h, pair_code[k]);
+  for (int k = 0; k < rlen; ++k) h = mix64(h, (unsigned)(col_idx[ri.x + k] - (row_begin + r)));
   hash[r] = h;
 }
 
 // flags the rows of the class of row `ref` (full comparison, the hash only filters) and counts them
 __global__ void mark_class(const int* __restrict__ pair_ptr, const unsigned* __restrict__ pair_code,
-                           int2* __restrict__ rowinfo, int n_rows, const unsigned long long* __restrict__ hash,
-                           int ref, int* __restrict__ count) {
+                           int2* __restrict__ rowinfo, const int* __restrict__ col_idx, int n_rows,
+                           const unsigned long long* __restrict__ hash, int ref, int* __restrict__ count) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   bool match = false;
   if (r < n_rows && hash[r] == hash[ref]) {
@@ -337,6 +339,9 @@ __global__ void mark_class(const int* __restrict__ pair_ptr, const unsigned* __r
     match = np == rnp && rowinfo[r + 1].x - a.x == rowinfo[ref + 1].x - b.x &&
             ((unsigned)a.y >> 24) == ((unsigned)b.y >> 24);
     for (int k = 0; match && k < np; ++k) match = pair_code[lo + k] == pair_code[rlo + k];
+    // ... and the same column OFFSETS from the row's own node (col - row is what the kernel adds)
+    const int rlen = rowinfo[ref + 1].x - b.x;
+    for (int k = 0; match && k < rlen; ++k) match = col_idx[a.x + k] - r == col_idx[b.x + k] - ref;
   }
   const unsigned m = __ballot_sync(0xffffffffu, match);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
@@ -346,14 +351,18 @@ __global__ void mark_class(const int* __restrict__ pair_ptr, const unsigned* __r
 
 __global__ void mark_ref(int2* __restrict__ rowinfo, int ref) { rowinfo[ref].y |= FEMX_ROW_SPEC; }
 
-__global__ void mark_tiles(int2* __restrict__ rowinfo, int n_rows, int tile) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t i0 = (int64_t)t * tile;
-  if (i0 >= n_rows) return;
-  const int i1 = (int)min((int64_t)n_rows, i0 + tile);
-  bool all = true;
-  for (int i = (int)i0; all && i < i1; ++i) all = (rowinfo[i].y & FEMX_ROW_SPEC) != 0;
-  if (all) rowinfo[i0].y |= FEMX_TILE_SPEC;
+// rows outside the class: flag (for the scan), then compaction in ascending order
+__global__ void other_flags(const int2* __restrict__ rowinfo, int n_rows, int* __restrict__ flag) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_rows) flag[r] = (rowinfo[r].y & FEMX_ROW_SPEC) ? 0 : 1;
+}
+
+__global__ void other_fill(const int2* __restrict__ rowinfo, int n_rows, const int* __restrict__ pos,
+                           int* __restrict__ list, int* __restrict__ max_len) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows || (rowinfo[r].y & FEMX_ROW_SPEC)) return;
+  list[pos[r]] = r;
+  atomicMax(max_len, rowinfo[r + 1].x - rowinfo[r].x);
 }
 
 // ---------------------------------------------------------------- exports ---
@@ -447,7 +456,8 @@ int detect_stencil_class(femx_ctx* ctx, femx_pattern* p, const int* d_pair_ptr, 
     if (e__ != cudaSuccess)                                                                          \
       return done(femx_fail(ctx, FEMX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)));  \
   } while (0)
-  row_class_hash<<<nblocks(nr, 128), 128, 0, st>>>(d_pair_ptr, d_pair_code, p->d_rowinfo, (int)nr, d_hash);
+  row_class_hash<<<nblocks(nr, 128), 128, 0, st>>>(d_pair_ptr, d_pair_code, p->d_rowinfo, p->d_col_idx,
+                                                   (int)p->row_begin, (int)nr, d_hash);
   const int S = (int)std::min<int64_t>(nr, 256);
   const int64_t stride = nr / S, start = stride / 2;
   std::vector<unsigned long long> hs(S);
@@ -469,19 +479,51 @@ int detect_stencil_class(femx_ctx* ctx, femx_pattern* p, const int* d_pair_ptr, 
   const int np = pp[1] - pp[0], rlen = ri[1].x - ri[0].x, self = (int)((unsigned)ri[0].y >> 24);
   if (np < 1 || np > FEMX_SPEC_MAX_NP || rlen > (p->nn == 4 ? 16 : FEMX_SPEC_MAX_RLEN)) return done(FEMX_OK);
   std::vector<uint32_t> codes(np);
+  std::vector<int32_t> offs(rlen);
   SC_CUDA(cudaMemcpyAsync(codes.data(), d_pair_code + pp[0], sizeof(uint32_t) * np, cudaMemcpyDeviceToHost, st));
+  SC_CUDA(cudaMemcpyAsync(offs.data(), p->d_col_idx + ri[0].x, sizeof(int32_t) * rlen, cudaMemcpyDeviceToHost, st));
   SC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), st));
-  mark_class<<<nblocks(nr, 128), 128, 0, st>>>(d_pair_ptr, d_pair_code, p->d_rowinfo, (int)nr, d_hash, (int)ref, d_count);
+  mark_class<<<nblocks(nr, 128), 128, 0, st>>>(d_pair_ptr, d_pair_code, p->d_rowinfo, p->d_col_idx, (int)nr, d_hash,
+                                               (int)ref, d_count);
   mark_ref<<<1, 1, 0, st>>>(p->d_rowinfo, (int)ref);
-  const int64_t ntiles = (nr + p->tile_nodes - 1) / p->tile_nodes;
-  mark_tiles<<<nblocks(ntiles, 128), 128, 0, st>>>(p->d_rowinfo, (int)nr, p->tile_nodes);
   int cnt = 0;
   SC_CUDA(cudaMemcpyAsync(&cnt, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
   SC_CUDA(cudaStreamSynchronize(st));
   SC_CUDA(cudaGetLastError());
+  // the rows outside the class, compacted (ascending): the numeric pass runs them in a launch of their own
+  {
+    int *d_flag = nullptr, *d_pos = nullptr;
+    rc = tmp_alloc(ctx, &d_flag, nr + 1, st);
+    if (rc == FEMX_OK) rc = tmp_alloc(ctx, &d_pos, nr + 1, st);
+    long long n_other = 0;
+    if (rc == FEMX_OK) {
+      other_flags<<<nblocks(nr, 256), 256, 0, st>>>(p->d_rowinfo, (int)nr, d_flag);
+      rc = exclusive_scan(ctx, d_flag, nr, d_pos, &n_other, st);
+    }
+    if (rc == FEMX_OK && n_other != nr - cnt)
+      rc = femx_fail(ctx, FEMX_ERR_CUDA, "stencil class: %lld rows outside the class, expected %lld", n_other,
+                     (long long)(nr - cnt));
+    if (rc == FEMX_OK) rc = dev_alloc(ctx, &p->d_other_rows, n_other, &p->bytes);
+    if (rc == FEMX_OK) {
+      cudaMemsetAsync(d_count, 0, sizeof(int), st);
+      other_fill<<<nblocks(nr, 256), 256, 0, st>>>(p->d_rowinfo, (int)nr, d_pos, p->d_other_rows, d_count);
+      int mx = 0;
+      cudaError_t e = cudaMemcpyAsync(&mx, d_count, sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) e = cudaGetLastError();
+      if (e != cudaSuccess) rc = femx_fail(ctx, FEMX_ERR_CUDA, "stencil class: row list failed: %s", cudaGetErrorString(e));
+      p->n_other = n_other;
+      p->max_row_other = mx;
+    }
+    cudaFreeAsync(d_flag, st);
+    cudaFreeAsync(d_pos, st);
+    if (rc != FEMX_OK) return done(rc);
+  }
 #undef SC_CUDA
   p->spec_np = np; p->spec_rlen = rlen; p->spec_self = self; p->spec_rows = cnt;
   p->spec_codes = codes;
+  for (auto& o : offs) o -= (int32_t)(p->row_begin + ref);  // column (local node id) minus the row's own node
+  p->spec_off = offs;
   char key[96];
   snprintf(key, sizeof key, "%016llx_%d_%d_%d", hs[best], np, rlen, self);
   p->spec_key = key;
@@ -662,6 +704,7 @@ void femx_pattern_destroy(femx_pattern* p) {
   cudaFree(p->d_slice_ptr);
   cudaFree(p->d_sell_code);
   cudaFree(p->d_sell_elem);
+  cudaFree(p->d_other_rows);
   delete p;
 }
 
@@ -676,7 +719,7 @@ int femx_pattern_info(const femx_pattern* p, int64_t* n_rows, int64_t* nnz, int6
 int64_t femx_pattern_bytes(const femx_pattern* p) { return p ? p->bytes : 0; }
 
 int femx_pattern_stencil(const femx_pattern* p, int* n_incid, int* row_len, int* self_pos, int64_t* rows,
-                         uint32_t* h_codes, int cap) {
+                         uint32_t* h_codes, int32_t* h_offsets, int cap) {
   if (!p) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_pattern_stencil: pattern is NULL");
   if (n_incid) *n_incid = p->spec_np;
   if (row_len) *row_len = p->spec_rlen;
@@ -684,6 +727,8 @@ int femx_pattern_stencil(const femx_pattern* p, int* n_incid, int* row_len, int*
   if (rows) *rows = p->spec_rows;
   if (h_codes)
     for (int k = 0; k < p->spec_np && k < cap; ++k) h_codes[k] = p->spec_codes[k];
+  if (h_offsets)
+    for (int k = 0; k < p->spec_rlen && k < cap; ++k) h_offsets[k] = p->spec_off[k];
   return FEMX_OK;
 }
 

@@ -362,13 +362,14 @@ class Pattern:
 
     def stencil(self):
         """Dominant stencil class found by the symbolic pass: dict(n_incid, row_len, self_pos, rows,
-        codes); rows == 0 when there is none (unstructured mesh, nd > 1, FEMX_SPEC=0)."""
+        codes, offsets); rows == 0 when there is none (unstructured mesh, nd > 1, FEMX_SPEC=0)."""
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         r = C.c_int64()
         codes = (C.c_uint32 * 32)()
-        self.ctx.check(lib().femx_pattern_stencil(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(r), codes, 32))
+        offs = (C.c_int32 * 32)()
+        self.ctx.check(lib().femx_pattern_stencil(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(r), codes, offs, 32))
         return dict(n_incid=a.value, row_len=b.value, self_pos=c.value, rows=r.value,
-                    codes=[int(codes[k]) for k in range(a.value)])
+                    codes=[int(codes[k]) for k in range(a.value)], offsets=[int(offs[k]) for k in range(b.value)])
 
     def csr(self, index_dtype="int32", stream=None):
         import torch

@@ -231,19 +231,20 @@ int femx_pattern_export_ell(const femx_pattern* pat, int width, int32_t* d_len,
                             int32_t* d_idx, void* stream);
 
 /* Dominant stencil class of a scalar (nd = 1) pattern.  Rows whose incidence count, row length,
- * own position and scatter-code sequence coincide do the same arithmetic on different nodes —
- * every interior row of a structured mesh.  The symbolic pass finds the most frequent class among
+ * own position, scatter-code sequence and column offsets (column - own node) coincide do the same
+ * arithmetic on nodes at the same relative positions — every interior row of a structured mesh.  The symbolic pass finds the most frequent class among
  * evenly spaced sample rows and flags its rows; femx_assemble_csr then runs an NVRTC-generated
- * straight-line body for them (each neighbour's coordinates read once, the row's values accumulated
- * in registers, no scatter codes read) and the generic incidence loop for the others.  Both paths
+ * straight-line body for them (each neighbour's coordinates read once — at own node + offset, issued
+ * before any metadata arrives — the row's values accumulated in registers, no scatter codes or column
+ * lists read) and the generic incidence loop for the others.  Both paths
  * perform the same floating-point operations in the same order, so the result does not depend on
  * which one a row takes.  In the reference the mesh size is baked into the kernel's -D macros
  * (fea_symbolic_nvrtc_sparse.cpp:506-530); here it is the mesh's stencil.
  * n_incid/row_len/self_pos describe the class, rows = how many rows belong to it (0 = none found),
- * h_codes (HOST buffer, cap entries; may be NULL) receives the scatter codes.  FEMX_SPEC=0 in the
- * environment switches detection and use off. */
+ * h_codes / h_offsets (HOST buffers, cap entries each; may be NULL) receive the scatter codes and the
+ * column offsets.  FEMX_SPEC=0 in the environment switches detection and use off. */
 int femx_pattern_stencil(const femx_pattern* pat, int* n_incid, int* row_len, int* self_pos,
-                         int64_t* rows, uint32_t* h_codes, int cap);
+                         int64_t* rows, uint32_t* h_codes, int32_t* h_offsets, int cap);
 /* Diagnostic: NVRTC-compiles the numeric-pass kernel specialised for an explicitly given stencil
  * class (no device needed with a form from femx_form_compile_offline) and returns the cubin. */
 int femx_form_cubin_stencil(femx_form* form, int n_incid, int row_len, int self_pos,

@@ -63,6 +63,7 @@ def test_dominant_class_2d(ctx):
     assert (st["n_incid"], st["row_len"], st["self_pos"]) == (6, 7, 3) == (len(codes), rlen, self_pos)
     assert st["codes"] == codes
     assert st["rows"] == (nR - 1) * (nC - 1)         # every interior node, nothing else
+    assert st["offsets"] == [-(nC + 1), -nC, -1, 0, 1, nC, nC + 1]
     pat.close()
 
 
@@ -77,6 +78,9 @@ def test_dominant_class_3d(ctx):
     assert (st["n_incid"], st["row_len"], st["self_pos"]) == (24, 15, 7)
     assert st["codes"] == codes
     assert st["rows"] == (nx - 1) * (ny - 1) * (nz - 1)
+    px, pxy = nx + 1, (nx + 1) * (ny + 1)
+    half = [1, px, px + 1, pxy, pxy + 1, pxy + px, pxy + px + 1]     # Kuhn: the 7 neighbours "ahead"
+    assert st["offsets"] == sorted([-o for o in half] + [0] + half)
     pat.close()
 
 
