@@ -47,6 +47,13 @@ struct femx_form {
   int integrated = 0;  // entries are final element-matrix expressions (no quadrature applied)
   std::string prologue;
   std::vector<std::string> entries;  // n*n
+  // accumulate form of the built-in scalar entries: acc_pre[li] declares what row li shares, acc_entries[li*n+lj]
+  // is the NEW value of an accumulator written $A (one fma chain: no separate product, no separate add)
+  std::vector<std::string> acc_pre, acc_entries;
+  // 3-D scalar built-ins: the prologue is [edges u2,u3,u4 from vertex 1 | d2 = u4 x u3, d3 = u2 x u4, d4 = u3 x u2 |
+  // prologue_rest]; the specialised pass then computes each face's cross product once (see build_defines)
+  bool shared_faces = false;
+  std::string prologue_rest;
   std::vector<std::string> rhs;      // n load-vector integrands (may be empty)
   int rhs_integrated = 0;
   // the built-in entries are invariant under even permutations of the local vertices (see build_defines)
@@ -82,15 +89,19 @@ namespace {
 //        (= (x1-x3)(y2-y3)-(y1-y3)(x2-x3), fea_symbolic_nvrtc_sparse.cpp:258)
 //   3-D: d2 = u4 x u3, d3 = u2 x u4, d4 = u3 x u2, d1 = -(d2+d3+d4);  jac = u2 . d2
 //        (= det[x1-x4, x2-x4, x3-x4], the Jacobian of X = x1 r + x2 s + x3 t + x4 (1-r-s-t))
-std::string cross_c(const char* a, const char* b, int k) {  // component k of a x b, fused like fma(p, q, -(r*s))
+// Component k of a x b as a difference of two rounded products: swapping a and b flips the sign and
+// nothing else (rn(p) - rn(q) = -(rn(q) - rn(p)) exactly), so the cross product of a face can be shared,
+// negated, by the two tetrahedra on either side of it.  (Fused, fma(p, q, -rn(r s)), it could not.)
+std::string cross_c(const std::string& a, const std::string& b, int k) {
   static const char* ax[3] = {"x", "y", "z"};
   const char *i = ax[(k + 1) % 3], *j = ax[(k + 2) % 3];
   std::ostringstream o;
-  o << "fma(" << a << i << "," << b << j << ",-femx_mul(" << a << j << "," << b << i << "))";
+  o << "(femx_mul(" << a << i << "," << b << j << ")-femx_mul(" << a << j << "," << b << i << "))";
   return o.str();
 }
 
-void emit_geometry(int dim, bool pinned, std::string* pro) {
+// rest (3-D pinned only): what follows the edges u2,u3,u4 and the cross products d2,d3,d4
+void emit_geometry(int dim, bool pinned, std::string* pro, std::string* rest = nullptr) {
   std::ostringstream o;
   if (!pinned) {
     // vector forms (no specialised pass): plain expressions, contraction left to the compiler
@@ -128,9 +139,11 @@ void emit_geometry(int dim, bool pinned, std::string* pro) {
       for (int k = 0; k < 3; ++k) o << (k ? ", " : "") << pr[0] << "xyz"[k] << " = " << cross_c(pr[1], pr[2], k);
       o << ";\n";
     }
-    o << "  const real d1x = -(d2x+d3x+d4x), d1y = -(d2y+d3y+d4y), d1z = -(d2z+d3z+d4z);\n"
-         "  const real jac = fma(u2z,d2z,fma(u2y,d2y,femx_mul(u2x,d2x)));\n"
-         "  const real ijac = femx_rcp(jac);\n";
+    const char* tail = "  const real d1x = -(d2x+d3x+d4x), d1y = -(d2y+d3y+d4y), d1z = -(d2z+d3z+d4z);\n"
+                       "  const real jac = fma(u2z,d2z,fma(u2y,d2y,femx_mul(u2x,d2x)));\n"
+                       "  const real ijac = femx_rcp(jac);\n";
+    o << tail;
+    if (rest) *rest = tail;
   }
   *pro += o.str();
 }
@@ -163,7 +176,8 @@ double phi_at(const femx_form* f, int a, int q) {
 int emit_builtin(femx_form* f, const femx_form_desc* d) {
   const int dim = f->dim, nn = f->nn, nd = f->nd, n = f->n;
   const bool pinned = nd == 1;  // scalar forms: every rounding fixed by the text (see emit_geometry)
-  emit_geometry(dim, pinned, &f->prologue);
+  emit_geometry(dim, pinned, &f->prologue, &f->prologue_rest);
+  f->shared_faces = pinned && dim == 3 && !(getenv("FEMX_SHAREDFACES") && atoi(getenv("FEMX_SHAREDFACES")) == 0);
   f->integrated = 1;
   f->entries.assign((size_t)n * n, "");
   double W = 0.0;
@@ -194,7 +208,10 @@ int emit_builtin(femx_form* f, const femx_form_desc* d) {
   f->rot_ok_matrix = !has_mass || msym;
   f->rot_ok_rhs = vsym;
   std::ostringstream pro;
-  if (pinned) pro << "  const real kq = femx_mul(" << num(W) << ",ijac);\n";
+  if (pinned) {
+    pro << "  const real kq = femx_mul(" << num(W) << ",ijac);\n";
+    f->prologue_rest += pro.str();
+  }
   else pro << "  const real kq = " << num(W) << "*ijac;\n";
   if (d->builtin == FEMX_FORM_ELASTICITY) {
     if (nd != dim) return FEMX_ERR_INVALID;
@@ -231,6 +248,36 @@ int emit_builtin(femx_form* f, const femx_form_desc* d) {
       }
       f->entries[(size_t)li * n + lj] = o.str();
     }
+  // Accumulate form (scalar forms): K_ab added to an accumulator A in one chain,
+  //   A <- d_b . (kq d_a) + (c M_ab jac + A),  with h = kq d_a shared by the row
+  // (3-D only: there the numeric pass is bound by the fp64 pipe; in 2-D it is not, and the form costs the
+  //  generic kernel 8 registers = 2 resident CTAs)
+  if (pinned && dim == 3 && d->builtin != FEMX_FORM_ELASTICITY && !(getenv("FEMX_ACCF") && atoi(getenv("FEMX_ACCF")) == 0)) {
+    f->acc_pre.assign(n, "");
+    f->acc_entries.assign((size_t)n * n, "");
+    for (int a = 0; a < n; ++a) {
+      std::ostringstream pre;
+      if (d->builtin != FEMX_FORM_MASS) {
+        pre << "const real";
+        for (int k = 0; k < dim; ++k) pre << (k ? "," : "") << " h" << AX[k] << " = femx_mul(kq,d" << a + 1 << AX[k] << ")";
+        pre << ";";
+      }
+      f->acc_pre[a] = pre.str();
+      for (int b = 0; b < n; ++b) {
+        std::ostringstream o;
+        std::string inner = "$A";
+        if (d->builtin != FEMX_FORM_POISSON) inner = "fma(" + num((d->builtin == FEMX_FORM_MASS ? 1.0 : cm) * M[a][b]) + ",jac,$A)";
+        if (d->builtin == FEMX_FORM_MASS) {
+          o << inner;
+        } else {
+          for (int k = dim - 1; k >= 0; --k) o << "fma(d" << b + 1 << AX[k] << ",h" << AX[k] << ",";
+          o << inner;
+          for (int k = dim - 1; k >= 0; --k) o << ")";
+        }
+        f->acc_entries[(size_t)a * n + b] = o.str();
+      }
+    }
+  }
   // constant source: b[a,c] = f_c * (sum_q w_q phi_a(q)) * jac, pre-integrated like the matrix
   f->rhs.assign(n, "");
   f->rhs_integrated = 1;
@@ -313,6 +360,8 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
   o << "#define FEMX_MIN_BLOCKS " << (getenv("FEMX_MINBLOCKS") ? atoi(getenv("FEMX_MINBLOCKS")) : min_blocks_default) << "\n";
   o << "#define FEMX_MIDGATHER " << (getenv("FEMX_MIDGATHER") ? atoi(getenv("FEMX_MIDGATHER")) : 1) << "\n";
   o << "#define FEMX_UNROLL " << (getenv("FEMX_UNROLL") ? atoi(getenv("FEMX_UNROLL")) : 1) << "\n";
+  o << "#define FEMX_LISTLAST " << (getenv("FEMX_LISTLAST") ? atoi(getenv("FEMX_LISTLAST")) : 0) << "\n";
+  o << "#define FEMX_RCP3 " << (getenv("FEMX_RCP3") ? atoi(getenv("FEMX_RCP3")) : 0) << "\n";
   o << "#define FEMX_EXPANDED " << (kernel == "csr_x" ? 1 : 0) << "\n";
   o << "#define FEMX_UNIT_STRIDE " << (kernel == "csr" ? 1 : 0) << "\n";
   std::string esc;
@@ -340,6 +389,20 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
     o << "#define FEMX_ROWQ_" << li << "(R,S,T,U,W) { const real r = (R), s = (S), t = (T), u = (U), w = (W); "
          "(void)r; (void)s; (void)t; (void)u; (void)w;" << qd.str() << " }\n";
   }
+  const bool accf = !f->acc_entries.empty();
+  auto subst = [](std::string e, const std::string& acc) {
+    for (size_t p0 = e.find("$A"); p0 != std::string::npos; p0 = e.find("$A", p0 + acc.size())) e.replace(p0, 2, acc);
+    return e;
+  };
+  if (accf)
+    for (int li = 0; li < n; ++li) {
+      o << "#define FEMX_ROWA_" << li << "(";
+      for (int lj = 0; lj < n; ++lj) o << (lj ? "," : "") << "A" << lj;
+      o << ") { " << f->acc_pre[li];
+      for (int lj = 0; lj < n; ++lj)
+        o << " \\\n    A" << lj << " = " << subst(f->acc_entries[(size_t)li * n + lj], "A" + std::to_string(lj)) << ";";
+      o << " }\n";
+    }
   o << "#define FEMX_QUAD(M)";
   for (int q = 0; q < f->nq; ++q)
     o << " \\\n    M(" << num(f->qr[q]) << "," << num(f->qs[q]) << "," << num(f->qt[q]) << ","
@@ -417,7 +480,21 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
         o << " const real " << ax[k] << femx_oth(nn, a, j) + 1 << " = o" << ax[k] << "[" << j << "];";
     }
     o << " \\\n      FEMX_PROLOGUE FEMX_GATHER_NEXT";
-    for (int c = 0; c < nd; ++c) {
+    if (accf) {
+      // accumulate form: the slots' old values (0 on first touch) go through the row's fma chains
+      o << " \\\n      { real t_[" << nn - 1 << "];";
+      for (int j = 0; j < nn - 1; ++j) o << " t_[" << j << "] = FEMX_FIRST(" << j << ") ? real(0) : srow[po[" << j << "]];";
+      o << " \\\n        FEMX_ROWA_" << a << "(";
+      for (int lj = 0; lj < nn; ++lj) {
+        if (lj) o << ",";
+        if (lj == a) o << "dacc[0]";
+        else o << "t_[" << (nn == 4 ? (lj ^ a) - 1 : (lj - a - 1 + 3) % 3) << "]";
+      }
+      o << ")";
+      for (int j = 0; j < nn - 1; ++j) o << " srow[po[" << j << "]] = t_[" << j << "];";
+      o << " }";
+    }
+    for (int c = 0; c < (accf ? 0 : nd); ++c) {
       const int li = a * nd + c;
       o << " \\\n      { real out[NDOF];";
       if (has_q[li]) o << " _Pragma(\"unroll\") for (int j_ = 0; j_ < NDOF; ++j_) out[j_] = real(0);";
@@ -449,43 +526,133 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
   o << "#define FEMX_SPEC " << (sc ? 1 : 0) << "\n";
   if (sc) {
     const int dim = f->dim;
-    o << "#define FEMX_SPEC_LOAD";
-    for (int k = 0; k < sc->rlen; ++k) {
+    // Streaming order: a column's coordinates are loaded `ahead` incidences before its first use and its
+    // accumulator is stored right after its last one, so only the columns of the incidences in flight are
+    // live (7 of 14 neighbours on the Kuhn stencil) — fewer registers, more resident warps.
+    // FEMX_SPEC_AHEAD >= the incidence count loads everything up front.
+    const int ahead = getenv("FEMX_SPEC_AHEAD") ? atoi(getenv("FEMX_SPEC_AHEAD")) : 2;
+    std::vector<int> first(sc->rlen, sc->np), last(sc->rlen, -1);
+    for (int it = 0; it < sc->np; ++it)
+      for (int j = 0; j < nn - 1; ++j) {
+        const int pos = (int)((sc->codes[it] >> (7 * j)) & 127);
+        first[pos] = std::min(first[pos], it);
+        last[pos] = it;
+      }
+    first[sc->self] = 0;
+    auto load_col = [&](int k) {
       o << " \\\n    const i64 q" << k << "_ = (i64)min(max(node_ + soff.v[" << k << "], 0), node_max) * FEMX_CS; const real";
       for (int c = 0; c < dim; ++c)
         o << (c ? "," : "") << " c" << ax[c] << k << " = __ldg(" << "XYZ"[c] << " + q" << k << "_)";
       o << ";";
+    };
+    // 3-D scalar built-ins: every face (own node, p, q) belongs to two incident tetrahedra, which need
+    // u_p x u_q with opposite signs.  The cross product is rounded so that the swap is an exact negation
+    // (cross_c), hence computed once per face and negated for the second tetrahedron — same bits as the
+    // generic loop, which evaluates it in each tetrahedron.
+    const bool faces = f->shared_faces && rotinv && dim == 3;
+    std::map<std::pair<int, int>, bool> face_done;
+    if (faces) {
+      std::string esc2;
+      for (char ch : f->prologue_rest) {
+        if (ch == '\n') esc2 += " \\\n"; else esc2 += ch;
+      }
+      o << "#define FEMX_PROLOGUE_REST " << esc2 << "\n";
     }
+    // Experiment (off: measured slower, the volatile prefetches cost spills): FEMX_SPEC_PREFETCH=1 prefetches
+    // the columns loaded later into L1 at kernel entry, =2 into L2.
+    const int pf = getenv("FEMX_SPEC_PREFETCH") ? atoi(getenv("FEMX_SPEC_PREFETCH")) : 0;
+    o << "#define FEMX_SPEC_LOAD";
+    for (int k = 0; k < sc->rlen; ++k)
+      if (first[k] <= ahead) load_col(k);  // issued at kernel entry, before any metadata has arrived
+    if (pf)
+      for (int k = 0; k < sc->rlen; ++k)
+        if (first[k] > ahead) {
+          o << " \\\n    { const i64 p_ = (i64)min(max(node_ + soff.v[" << k << "], 0), node_max) * FEMX_CS;";
+          for (int c = 0; c < dim; ++c)
+            o << " asm volatile(\"prefetch.global." << (pf == 2 ? "L2" : "L1") << " [%0];\" ::\"l\"(" << "XYZ"[c] << " + p_));";
+          o << " }";
+        }
     o << "\n#define FEMX_SPEC_BODY";
     o << " \\\n    real dacc0_ = real(0);";
-    for (int k = 0; k < sc->rlen; ++k)
-      if (k != sc->self) o << " real a" << k << "_;";
     for (int it = 0; it < sc->np; ++it) {
       const uint32_t code = sc->codes[it];
       const int a = rotinv ? 0 : (int)((code >> 28) & 3);
+      for (int k = 0; k < sc->rlen; ++k) {
+        if (first[k] == it + ahead && first[k] > ahead) load_col(k);
+        if (first[k] == it && k != sc->self) {
+          o << " real a" << k << (accf ? "_ = real(0);" : "_;");
+          if (faces) {  // edge from the own node
+            o << " const real";
+            for (int c = 0; c < dim; ++c)
+              o << (c ? "," : "") << " e" << k << ax[c] << " = c" << ax[c] << k << "-c" << ax[c] << sc->self;
+            o << ";";
+          }
+        }
+      }
+      int P[3] = {0, 0, 0};
+      for (int j = 0; j < nn - 1 && j < 3; ++j) P[j] = (int)((code >> (7 * j)) & 127);  // positions of local vertices 2,3,4
+      static const int fa[3][2] = {{2, 1}, {0, 2}, {1, 0}};  // d2 = u4 x u3, d3 = u2 x u4, d4 = u3 x u2
+      if (faces)
+        for (auto& pq : fa) {
+          const int lo = std::min(P[pq[0]], P[pq[1]]), hi = std::max(P[pq[0]], P[pq[1]]);
+          if (face_done[{lo, hi}]) continue;
+          face_done[{lo, hi}] = true;
+          o << " \\\n    const real";
+          for (int c = 0; c < 3; ++c)
+            o << (c ? "," : "") << " n" << lo << "_" << hi << ax[c] << " = "
+              << cross_c("e" + std::to_string(lo), "e" + std::to_string(hi), c);
+          o << ";";
+        }
       o << " \\\n    {";
-      for (int c = 0; c < dim; ++c) {
-        o << " const real " << ax[c] << a + 1 << " = c" << ax[c] << sc->self << ";";
-        for (int j = 0; j < nn - 1; ++j)
-          o << " const real " << ax[c] << femx_oth(nn, a, j) + 1 << " = c" << ax[c] << ((code >> (7 * j)) & 127) << ";";
+      if (faces) {
+        for (int v = 0; v < 3; ++v) {
+          o << " const real";
+          for (int c = 0; c < 3; ++c) o << (c ? "," : "") << " u" << v + 2 << ax[c] << " = e" << P[v] << ax[c];
+          o << ";";
+        }
+        for (int v = 0; v < 3; ++v) {
+          const int p0 = P[fa[v][0]], q0 = P[fa[v][1]];
+          o << " const real";
+          for (int c = 0; c < 3; ++c)
+            o << (c ? "," : "") << " d" << v + 2 << ax[c] << " = " << (p0 < q0 ? "" : "-") << "n" << std::min(p0, q0) << "_"
+              << std::max(p0, q0) << ax[c];
+          o << ";";
+        }
+      } else {
+        for (int c = 0; c < dim; ++c) {
+          o << " const real " << ax[c] << a + 1 << " = c" << ax[c] << sc->self << ";";
+          for (int j = 0; j < nn - 1; ++j)
+            o << " const real " << ax[c] << femx_oth(nn, a, j) + 1 << " = c" << ax[c] << ((code >> (7 * j)) & 127) << ";";
+        }
       }
-      o << " \\\n      FEMX_PROLOGUE \\\n      { real out[NDOF];";
-      if (has_q[a]) o << " _Pragma(\"unroll\") for (int j_ = 0; j_ < NDOF; ++j_) out[j_] = real(0);";
-      o << " FEMX_ROWC_" << a;
-      if (has_q[a]) o << " FEMX_QUAD(FEMX_ROWQ_" << a << ")";
-      o << " \\\n        dacc0_ += out[" << a << "];";
-      for (int j = 0; j < nn - 1; ++j) {
-        const int pos = (int)((code >> (7 * j)) & 127);
-        o << " a" << pos << "_ = ";
-        if ((code >> (21 + j)) & 1) o << "real(0)"; else o << "a" << pos << "_";
-        o << " + out[" << femx_oth(nn, a, j) << "];";
+      const char* PRO = faces ? "FEMX_PROLOGUE_REST" : "FEMX_PROLOGUE";
+      if (accf) {
+        o << " \\\n      " << PRO << " \\\n      FEMX_ROWA_" << a << "(";
+        for (int lj = 0; lj < nn; ++lj) {
+          if (lj) o << ",";
+          if (lj == a) o << "dacc0_";
+          else o << "a" << ((code >> (7 * (nn == 4 ? (lj ^ a) - 1 : (lj - a - 1 + 3) % 3))) & 127) << "_";
+        }
+        o << ") }";
+      } else {
+        o << " \\\n      " << PRO << " \\\n      { real out[NDOF];";
+        if (has_q[a]) o << " _Pragma(\"unroll\") for (int j_ = 0; j_ < NDOF; ++j_) out[j_] = real(0);";
+        o << " FEMX_ROWC_" << a;
+        if (has_q[a]) o << " FEMX_QUAD(FEMX_ROWQ_" << a << ")";
+        o << " \\\n        dacc0_ += out[" << a << "];";
+        for (int j = 0; j < nn - 1; ++j) {
+          const int pos = (int)((code >> (7 * j)) & 127);
+          o << " a" << pos << "_ = ";
+          if ((code >> (21 + j)) & 1) o << "real(0)"; else o << "a" << pos << "_";
+          o << " + out[" << femx_oth(nn, a, j) << "];";
+        }
+        o << " } }";
       }
-      o << " } }";
+      for (int k = 0; k < sc->rlen; ++k)
+        if (last[k] == it && k != sc->self) o << " srow[" << k << "] = a" << k << "_;";
     }
-    o << " \\\n   ";
-    for (int k = 0; k < sc->rlen; ++k)
-      if (k != sc->self) o << " srow[" << k << "] = a" << k << "_;";
-    o << " srow[" << sc->self << "] = dacc0_;\n";
+    o << " \\\n    srow[" << sc->self << "] = dacc0_;\n";
+
   }
   return o.str();
 }

@@ -32,13 +32,18 @@ __device__ __forceinline__ T femx_pow(T a, double e) { return ::femx_pow(a, e); 
 // Reciprocal for the emitter's prologue: hardware seed (rcp.approx.ftz.f64, >= 20 good bits) and two
 // Newton steps -> relative error far below 1 ulp of a double for normal inputs, branch-free
 // (the compiler's IEEE division adds a slow-path test and a fifth correction FMA per element).
+// FEMX_RCP3: one third-order step instead, x(1 + e + e^2) with e = 1 - a x: error e^3 <= 2^-60, one fma less.
 __device__ __forceinline__ double femx_rcp(double a) {
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
   double e = fma(-a, x, 1.0);
+#if FEMX_RCP3
+  x = fma(x, fma(e, e, e), x);
+#else
   x = fma(x, e, x);
   e = fma(-a, x, 1.0);
   x = fma(x, e, x);
+#endif
   return x;
 }
 __device__ __forceinline__ float femx_rcp(float a) { return 1.0f / a; }
@@ -398,8 +403,14 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   // columns read straight from global memory, no barriers); the others take tiles of class rows.
   // The two kinds write disjoint parts of `vals`.
   const int n_lb = (n_list + FEMX_TILE_NODES - 1) / FEMX_TILE_NODES;
-  if ((int)blockIdx.x < n_lb) {
-    const int k_ = blockIdx.x * FEMX_TILE_NODES + threadIdx.x;
+#if FEMX_LISTLAST
+  const int n_tb = (n_rows + FEMX_TILE_NODES - 1) / FEMX_TILE_NODES;
+  const int lb = (int)blockIdx.x - n_tb, tb = blockIdx.x;
+#else
+  const int lb = (int)blockIdx.x < n_lb ? (int)blockIdx.x : -1, tb = (int)blockIdx.x - n_lb;
+#endif
+  if (lb >= 0) {
+    const int k_ = lb * FEMX_TILE_NODES + threadIdx.x;
     if (k_ >= n_list) return;
     const int row = __ldg(rowlist + k_);
     const int2 r0 = __ldg(&rowinfo[row]);
@@ -414,7 +425,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
     }
     return;
   }
-  const int i0 = (blockIdx.x - n_lb) * FEMX_TILE_NODES;
+  const int i0 = tb * FEMX_TILE_NODES;
 #else
   const int i0 = blockIdx.x * FEMX_TILE_NODES;
 #endif
