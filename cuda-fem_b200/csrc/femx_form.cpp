@@ -530,7 +530,8 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
     // accumulator is stored right after its last one, so only the columns of the incidences in flight are
     // live (7 of 14 neighbours on the Kuhn stencil) — fewer registers, more resident warps.
     // FEMX_SPEC_AHEAD >= the incidence count loads everything up front.
-    const int ahead = getenv("FEMX_SPEC_AHEAD") ? atoi(getenv("FEMX_SPEC_AHEAD")) : 2;
+    // (2-D stencils are small: everything up front measured fastest there)
+    const int ahead = getenv("FEMX_SPEC_AHEAD") ? atoi(getenv("FEMX_SPEC_AHEAD")) : (dim == 2 ? 99 : 2);
     std::vector<int> first(sc->rlen, sc->np), last(sc->rlen, -1);
     for (int it = 0; it < sc->np; ++it)
       for (int j = 0; j < nn - 1; ++j) {
@@ -539,10 +540,11 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
         last[pos] = it;
       }
     first[sc->self] = 0;
-    auto load_col = [&](int k) {
+    const bool pin = !(getenv("FEMX_SPEC_PIN") && atoi(getenv("FEMX_SPEC_PIN")) == 0);
+    auto load_col = [&](int k, bool entry) {
       o << " \\\n    const i64 q" << k << "_ = (i64)min(max(node_ + soff.v[" << k << "], 0), node_max) * FEMX_CS; const real";
       for (int c = 0; c < dim; ++c)
-        o << (c ? "," : "") << " c" << ax[c] << k << " = __ldg(" << "XYZ"[c] << " + q" << k << "_)";
+        o << (c ? "," : "") << " c" << ax[c] << k << " = " << (entry && pin ? "femx_ldg_pinned(" : "__ldg(") << "XYZ"[c] << " + q" << k << "_)";
       o << ";";
     };
     // 3-D scalar built-ins: every face (own node, p, q) belongs to two incident tetrahedra, which need
@@ -563,7 +565,7 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
     const int pf = getenv("FEMX_SPEC_PREFETCH") ? atoi(getenv("FEMX_SPEC_PREFETCH")) : 0;
     o << "#define FEMX_SPEC_LOAD";
     for (int k = 0; k < sc->rlen; ++k)
-      if (first[k] <= ahead) load_col(k);  // issued at kernel entry, before any metadata has arrived
+      if (first[k] <= ahead) load_col(k, true);  // issued at kernel entry, before any metadata has arrived
     if (pf)
       for (int k = 0; k < sc->rlen; ++k)
         if (first[k] > ahead) {
@@ -578,7 +580,7 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
       const uint32_t code = sc->codes[it];
       const int a = rotinv ? 0 : (int)((code >> 28) & 3);
       for (int k = 0; k < sc->rlen; ++k) {
-        if (first[k] == it + ahead && first[k] > ahead) load_col(k);
+        if (first[k] == it + ahead && first[k] > ahead) load_col(k, false);
         if (first[k] == it && k != sc->self) {
           o << " real a" << k << (accf ? "_ = real(0);" : "_;");
           if (faces) {  // edge from the own node
@@ -649,9 +651,9 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
         o << " } }";
       }
       for (int k = 0; k < sc->rlen; ++k)
-        if (last[k] == it && k != sc->self) o << " srow[" << k << "] = a" << k << "_;";
+        if (last[k] == it && k != sc->self) o << " if (mine) srow[" << k << "] = a" << k << "_;";
     }
-    o << " \\\n    srow[" << sc->self << "] = dacc0_;\n";
+    o << " \\\n    if (mine) srow[" << sc->self << "] = dacc0_;\n";
 
   }
   return o.str();

@@ -233,6 +233,29 @@ __device__ __forceinline__ float femx_ldg_if(const float* p, int pred) {
                : "=f"(v) : "l"(p), "r"(pred));
   return v;
 }
+// read-only global load that stays where it is written: the speculative gathers at kernel entry must
+// not be sunk below the branch on the row's metadata (the compiler does that to a plain __ldg: two
+// serialised memory round trips instead of one)
+__device__ __forceinline__ double femx_ldg_pinned(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float femx_ldg_pinned(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int2 femx_ldg_pinned(const int2* p) {
+  int2 v;
+  asm volatile("ld.global.nc.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int femx_ldg_pinned(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 #if FEMX_UNIT_STRIDE
 #define FEMX_CS 1
 #else
@@ -435,17 +458,26 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   // columns at (own node + constant offset), so their coordinates need neither the row pointers nor
   // the column list.  (Clamped: for a row outside the class the values are simply not used.)
   const int node_ = row_node0 + i0 + min((int)threadIdx.x, nt - 1);
+  // (the row metadata is pinned too: left to the scheduler, its loads end up behind the first use of the
+  //  coordinates — a second serialised round trip)
+  const int ln = threadIdx.x;  // one thread per node row (all ND dof rows of the node)
+  const int rowc = i0 + min(ln, nt - 1);
+  const int2 r0 = femx_ldg_pinned(&rowinfo[rowc]);
+  const int rnext = femx_ldg_pinned(&rowinfo[rowc + 1].x);
+  const int base = femx_ldg_pinned(&rowinfo[i0].x);
+  const int cntn = 0;
   FEMX_SPEC_LOAD
-#endif
+#else
   const int base = __ldg(&rowinfo[i0].x);
   const int cntn = __ldg(&rowinfo[i0 + nt].x) - base;  // node-level nonzeros of the tile
-  const int cnt = cntn * (ND * ND);
-  const i64 vb = (i64)base * (ND * ND);              // first value index of the tile
-  const int vph = (int)(vb & (FEMX_EPV - 1));         // phase of the value run (elements)
   const int ln = threadIdx.x;  // one thread per node row (all ND dof rows of the node)
   const int rowc = i0 + min(ln, nt - 1);
   const int2 r0 = __ldg(&rowinfo[rowc]);
   const int rnext = __ldg(&rowinfo[rowc + 1].x);
+#endif
+  const int cnt = cntn * (ND * ND);
+  const i64 vb = (i64)base * (ND * ND);              // first value index of the tile
+  const int vph = (int)(vb & (FEMX_EPV - 1));         // phase of the value run (elements)
 #if FEMX_SPEC
   // ---- tile of class rows: the straight-line body generated for the class's scatter codes; nothing
   // is staged in (no codes, no column list, no mbarrier).  smem: [class mask of each warp (128 B) | end
@@ -454,15 +486,18 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   unsigned* s_mask = reinterpret_cast<unsigned*>(femx_smem);
   int* s_end = reinterpret_cast<int*>(femx_smem + 128);   // s_end[i]: end of row i's values, relative to the tile
   real* s_vals = reinterpret_cast<real*>(femx_smem + FEMX_SPEC_HDR) + vph;
+  // The body runs for EVERY thread, before the row's metadata is looked at: a branch on `mine` ahead of it
+  // would let the compiler sink the entry gathers below that branch (two serialised memory round trips).
+  // Rows outside the class compute on clamped, meaningless coordinates and store nothing.
   const bool mine = ln < nt && (r0.y & FEMX_ROW_SPEC);
+  {
+    real* srow = s_vals + (r0.x - base) * (ND * ND);
+    FEMX_SPEC_BODY
+  }
   {
     const unsigned wm = __ballot_sync(0xffffffffu, mine);
     if ((ln & 31) == 0) s_mask[ln >> 5] = wm;
     if (ln < nt) s_end[ln] = (rnext - base) * (ND * ND);
-  }
-  if (mine) {
-    real* srow = s_vals + (r0.x - base) * (ND * ND);
-    FEMX_SPEC_BODY
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
