@@ -356,7 +356,9 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
   // (the specialised 3-D body holds 45 coordinates + 15 accumulators per thread: 512 threads per SM keep it at
   //  128 registers without spills, measured faster than the 164 the compiler takes when left alone)
   const int tile_nodes = femx_tile_nodes_for(f->nd);
-  const int min_blocks_default = sc && f->dim == 3 ? 512 / tile_nodes : 0;
+  // (2-D body: 1024 threads per SM = 64 registers; measured 0.27 ms on cfg2 against 0.29-0.31 ms at the 48, 56 or
+  //  68 registers other limits produce — the schedule ptxas finds at this limit, not the occupancy, makes the difference)
+  const int min_blocks_default = !sc ? 0 : (f->dim == 3 ? 512 : 1024) / tile_nodes;
   o << "#define FEMX_MIN_BLOCKS " << (getenv("FEMX_MINBLOCKS") ? atoi(getenv("FEMX_MINBLOCKS")) : min_blocks_default) << "\n";
   o << "#define FEMX_MIDGATHER " << (getenv("FEMX_MIDGATHER") ? atoi(getenv("FEMX_MIDGATHER")) : 1) << "\n";
   o << "#define FEMX_UNROLL " << (getenv("FEMX_UNROLL") ? atoi(getenv("FEMX_UNROLL")) : 1) << "\n";

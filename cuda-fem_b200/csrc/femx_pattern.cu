@@ -326,6 +326,18 @@ __global__ void row_class_hash(const int* __restrict__ pair_ptr, const unsigned*
   hash[r] = h;
 }
 
+// sample rows: one per stride, at a pseudo-random place inside it (an even spacing aliases with the line
+// length of a structured mesh: every sample then lands in the same mesh column, e.g. on the boundary)
+__global__ void sample_rows(const unsigned long long* __restrict__ hash, long long n_rows, int n_samples,
+                            unsigned long long* __restrict__ out_hash, int* __restrict__ out_row) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_samples) return;
+  const long long stride = n_rows / n_samples;
+  const long long r = (long long)i * stride + (long long)(mix64(0x73616d70ull, (unsigned long long)i) % (unsigned long long)stride);
+  out_hash[i] = hash[r];
+  out_row[i] = (int)r;
+}
+
 // flags the rows of the class of row `ref` (full comparison, the hash only filters) and counts them
 __global__ void mark_class(const int* __restrict__ pair_ptr, const unsigned* __restrict__ pair_code,
                            int2* __restrict__ rowinfo, const int* __restrict__ col_idx, int n_rows,
@@ -459,10 +471,22 @@ int detect_stencil_class(femx_ctx* ctx, femx_pattern* p, const int* d_pair_ptr, 
   row_class_hash<<<nblocks(nr, 128), 128, 0, st>>>(d_pair_ptr, d_pair_code, p->d_rowinfo, p->d_col_idx,
                                                    (int)p->row_begin, (int)nr, d_hash);
   const int S = (int)std::min<int64_t>(nr, 256);
-  const int64_t stride = nr / S, start = stride / 2;
   std::vector<unsigned long long> hs(S);
-  SC_CUDA(cudaMemcpy2DAsync(hs.data(), 8, d_hash + start, (size_t)stride * 8, 8, S, cudaMemcpyDeviceToHost, st));
-  SC_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> hrow(S);
+  {
+    unsigned long long* d_sh = nullptr;
+    int* d_sr = nullptr;
+    rc = tmp_alloc(ctx, &d_sh, S, st);
+    if (rc == FEMX_OK) rc = tmp_alloc(ctx, &d_sr, S, st);
+    if (rc != FEMX_OK) { cudaFreeAsync(d_sh, st); cudaFreeAsync(d_sr, st); return done(rc); }
+    sample_rows<<<nblocks(S, 128), 128, 0, st>>>(d_hash, (long long)nr, S, d_sh, d_sr);
+    cudaError_t e1 = cudaMemcpyAsync(hs.data(), d_sh, sizeof(unsigned long long) * S, cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaMemcpyAsync(hrow.data(), d_sr, sizeof(int) * S, cudaMemcpyDeviceToHost, st);
+    cudaError_t e3 = cudaStreamSynchronize(st);
+    cudaFreeAsync(d_sh, st);
+    cudaFreeAsync(d_sr, st);
+    SC_CUDA(e1); SC_CUDA(e2); SC_CUDA(e3);
+  }
   int best = -1, best_cnt = 0;
   for (int i = 0; i < S; ++i) {
     int c = 0;
@@ -470,7 +494,7 @@ int detect_stencil_class(femx_ctx* ctx, femx_pattern* p, const int* d_pair_ptr, 
     if (c > best_cnt) { best_cnt = c; best = i; }
   }
   if (best < 0 || best_cnt * 4 < S) return done(FEMX_OK);  // no class covers a quarter of the samples
-  const int64_t ref = start + best * stride;
+  const int64_t ref = hrow[best];
   int2 ri[2];
   int pp[2];
   SC_CUDA(cudaMemcpyAsync(ri, p->d_rowinfo + ref, sizeof ri, cudaMemcpyDeviceToHost, st));

@@ -68,6 +68,25 @@ def test_dominant_class_2d(ctx):
 
 
 @pytest.mark.gpu
+def test_dominant_class_sampling_does_not_alias_with_the_mesh_lines(ctx):
+    """rows / 256 a multiple of the line length: evenly spaced samples would all sit in one mesh column
+    (the boundary column for the 2-GPU slabs of cfg2) — the samples are jittered inside their stride."""
+    nR, nC = 511, 16            # 512 x 17 nodes, 8704 / 256 = 34 = 2 lines
+    mesh = ctx.rectangle_mesh(0, 1, 0, 1, nR, nC)
+    pat = femx.Pattern(ctx, mesh)
+    st = pat.stencil()
+    assert (st["n_incid"], st["row_len"]) == (6, 7) and st["rows"] == (nR - 1) * (nC - 1)
+    pat.close()
+    # a slab as bench.py builds it for rank 0 of 2: owned rows = whole lines
+    nR, nC = 64, 255            # 256 nodes per line
+    slab = ctx.rectangle_mesh(0, 1, 0, 1, nR, nC, row_lo=0, row_hi=33)
+    pat = femx.Pattern(ctx, slab, row_begin=0, row_end=32 * (nC + 1), col_base=0)
+    st = pat.stencil()
+    assert (st["n_incid"], st["row_len"]) == (6, 7) and st["rows"] == 31 * (nC - 1)
+    pat.close()
+
+
+@pytest.mark.gpu
 def test_dominant_class_3d(ctx):
     nx, ny, nz = 7, 6, 5
     X, Y, Z, conn = orc.box_mesh(nx, ny, nz)
