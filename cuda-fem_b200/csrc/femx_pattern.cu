@@ -548,8 +548,12 @@ int detect_stencil_class(femx_ctx* ctx, femx_pattern* p, const int* d_pair_ptr, 
   p->spec_codes = codes;
   for (auto& o : offs) o -= (int32_t)(p->row_begin + ref);  // column (local node id) minus the row's own node
   p->spec_off = offs;
+  // the kernel cache key covers what the generated code depends on (codes, sizes) — not the offsets,
+  // which are launch parameters: one cubin serves every mesh size with this stencil
+  unsigned long long kh = 1469598103934665603ull;
+  for (int k = 0; k < np; ++k) kh = (kh ^ codes[k]) * 1099511628211ull;
   char key[96];
-  snprintf(key, sizeof key, "%016llx_%d_%d_%d", hs[best], np, rlen, self);
+  snprintf(key, sizeof key, "%016llx_%d_%d_%d", kh, np, rlen, self);
   p->spec_key = key;
   return done(FEMX_OK);
 }
