@@ -522,9 +522,10 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
   o << "\n";
   // Specialised body for one stencil class (scalar forms): the scatter codes are known here, so the
   // incidence loop is unrolled on the host with every column position a literal — the coordinates of
-  // each column are loaded once into named registers, the row's values accumulate in registers
-  // (first touch: 0 + v, exactly as the generic path's shared-memory image) and are stored once.
-  // Per incidence the text is the generic case's: same bindings, same prologue, same row macro.
+  // each column are loaded once into named registers (from own node + the class's constant offset), the
+  // row's values accumulate in registers (first touch: 0 + v, exactly as the generic path's shared-memory
+  // image) and each is stored once, by `if (mine)`: the body itself runs unconditionally.
+  // Per incidence the arithmetic is the generic case's: same bindings, same prologue, same row macro.
   o << "#define FEMX_SPEC " << (sc ? 1 : 0) << "\n";
   if (sc) {
     const int dim = f->dim;

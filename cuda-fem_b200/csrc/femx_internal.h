@@ -88,7 +88,6 @@ struct femx_pattern {
 
 // rowinfo[i].y = #incidences (bits 0-21) | (bit 22 reserved) | FEMX_ROW_SPEC | own position << 24
 #define FEMX_NP_MASK 0x3fffff
-#define FEMX_TILE_SPEC (1 << 22)
 #define FEMX_ROW_SPEC (1 << 23)
 #define FEMX_SPEC_MAX_NP 32    // limits of a specialised stencil (register budget of the straight-line body)
 #define FEMX_SPEC_MAX_RLEN 24

@@ -54,7 +54,6 @@ __device__ __forceinline__ double femx_mul(double a, double b) { return __dmul_r
 __device__ __forceinline__ float femx_mul(float a, float b) { return __fmul_rn(a, b); }
 // rowinfo[i].y = #incidences | FEMX_ROW_SPEC | own position << 24 (femx_internal.h)
 #define FEMX_NP_MASK 0x3fffff
-#define FEMX_TILE_SPEC (1 << 22)
 #define FEMX_ROW_SPEC (1 << 23)
 // column offsets (column - own node) of the pattern's stencil class, passed by value at launch
 struct femx_soff { int v[24]; };
@@ -465,17 +464,16 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   const int2 r0 = femx_ldg_pinned(&rowinfo[rowc]);
   const int rnext = femx_ldg_pinned(&rowinfo[rowc + 1].x);
   const int base = femx_ldg_pinned(&rowinfo[i0].x);
-  const int cntn = 0;
   FEMX_SPEC_LOAD
 #else
   const int base = __ldg(&rowinfo[i0].x);
   const int cntn = __ldg(&rowinfo[i0 + nt].x) - base;  // node-level nonzeros of the tile
+  const int cnt = cntn * (ND * ND);
   const int ln = threadIdx.x;  // one thread per node row (all ND dof rows of the node)
   const int rowc = i0 + min(ln, nt - 1);
   const int2 r0 = __ldg(&rowinfo[rowc]);
   const int rnext = __ldg(&rowinfo[rowc + 1].x);
 #endif
-  const int cnt = cntn * (ND * ND);
   const i64 vb = (i64)base * (ND * ND);              // first value index of the tile
   const int vph = (int)(vb & (FEMX_EPV - 1));         // phase of the value run (elements)
 #if FEMX_SPEC
