@@ -54,6 +54,11 @@ struct femx_form {
   // prologue_rest]; the specialised pass then computes each face's cross product once (see build_defines)
   bool shared_faces = false;
   std::string prologue_rest;
+  // FEMX_ROWSUM=1 (experiment, off by default): the rows of a stiffness matrix sum to zero, so the diagonal is not
+  // accumulated entry by entry but recovered at the end of the row, D = cj * (sum of the incident Jacobians) -
+  // (sum of the row's off-diagonal values), cj = c * sum_b M_ab — 4 fma per incidence become one add
+  bool rowsum = false;
+  double rowsum_cj = 0.0;
   std::vector<std::string> rhs;      // n load-vector integrands (may be empty)
   int rhs_integrated = 0;
   // the built-in entries are invariant under even permutations of the local vertices (see build_defines)
@@ -255,6 +260,10 @@ int emit_builtin(femx_form* f, const femx_form_desc* d) {
   if (pinned && dim == 3 && d->builtin != FEMX_FORM_ELASTICITY && !(getenv("FEMX_ACCF") && atoi(getenv("FEMX_ACCF")) == 0)) {
     f->acc_pre.assign(n, "");
     f->acc_entries.assign((size_t)n * n, "");
+    f->rowsum = f->rot_ok_matrix && (d->builtin == FEMX_FORM_POISSON || d->builtin == FEMX_FORM_POISSON_MASS) &&
+                getenv("FEMX_ROWSUM") && atoi(getenv("FEMX_ROWSUM")) == 1;
+    if (f->rowsum && d->builtin == FEMX_FORM_POISSON_MASS)
+      for (int b = 0; b < nn; ++b) f->rowsum_cj += cm * M[0][b];
     for (int a = 0; a < n; ++a) {
       std::ostringstream pre;
       if (d->builtin != FEMX_FORM_MASS) {
@@ -275,6 +284,7 @@ int emit_builtin(femx_form* f, const femx_form_desc* d) {
           for (int k = dim - 1; k >= 0; --k) o << ")";
         }
         f->acc_entries[(size_t)a * n + b] = o.str();
+        if (f->rowsum && a == b) f->acc_entries[(size_t)a * n + b] = d->builtin == FEMX_FORM_POISSON ? "$A" : "$A+jac";
       }
     }
   }
@@ -362,6 +372,7 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
   o << "#define FEMX_MIN_BLOCKS " << (getenv("FEMX_MINBLOCKS") ? atoi(getenv("FEMX_MINBLOCKS")) : min_blocks_default) << "\n";
   o << "#define FEMX_MIDGATHER " << (getenv("FEMX_MIDGATHER") ? atoi(getenv("FEMX_MIDGATHER")) : 1) << "\n";
   o << "#define FEMX_UNROLL " << (getenv("FEMX_UNROLL") ? atoi(getenv("FEMX_UNROLL")) : 1) << "\n";
+  o << "#define FEMX_ROWSUM " << (f->rowsum ? 1 : 0) << "\n#define FEMX_CJ " << num(f->rowsum_cj) << "\n";
   o << "#define FEMX_LISTLAST " << (getenv("FEMX_LISTLAST") ? atoi(getenv("FEMX_LISTLAST")) : 0) << "\n";
   o << "#define FEMX_RCP3 " << (getenv("FEMX_RCP3") ? atoi(getenv("FEMX_RCP3")) : 0) << "\n";
   o << "#define FEMX_EXPANDED " << (kernel == "csr_x" ? 1 : 0) << "\n";
@@ -655,6 +666,12 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
       }
       for (int k = 0; k < sc->rlen; ++k)
         if (last[k] == it && k != sc->self) o << " if (mine) srow[" << k << "] = a" << k << "_;";
+    }
+    if (f->rowsum) {  // the diagonal from the row sum: the off-diagonal values, read back in ascending position order
+      o << " \\\n    { real S_ = real(0);";
+      for (int k = 0; k < sc->rlen; ++k)
+        if (k != sc->self) o << " S_ += srow[" << k << "];";
+      o << " dacc0_ = fma(FEMX_CJ, dacc0_, -S_); }";
     }
     o << " \\\n    if (mine) srow[" << sc->self << "] = dacc0_;\n";
 

@@ -405,6 +405,15 @@ __device__ __forceinline__ void femx_generic_row(const int2 r0, const int np, co
   }
 #undef FEMX_GATHER_NEXT
 #endif
+#if FEMX_ROWSUM
+  {  // stiffness rows sum to zero: diagonal = cj * (sum of the incident Jacobians) - (sum of the off-diagonal values)
+    real S_ = real(0);
+    const int rl_ = rstride / ND, sp_ = ps / ND;
+    for (int k = 0; k < rl_; ++k)
+      if (k != sp_) S_ += srow[k];
+    dacc[0] = fma(FEMX_CJ, dacc[0], -S_);
+  }
+#endif
 #pragma unroll
   for (int c = 0; c < ND; ++c)
 #pragma unroll

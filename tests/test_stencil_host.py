@@ -88,6 +88,14 @@ int main(int argc, char** argv) {
           FEMX_CSR_CASES
         }
       }
+#if FEMX_ROWSUM
+      {  // (femx_generic_row's row-sum diagonal)
+        real S_ = real(0);
+        for (int k = 0; k < rlen; ++k)
+          if (k != self) S_ += srow[k];
+        dacc[0] = fma(FEMX_CJ, dacc[0], -S_);
+      }
+#endif
       srow[self] = dacc[0];
     }
     {  // ---- the specialised body, exactly as the kernel runs it
@@ -171,9 +179,21 @@ def _run_case(tmp_path, dim, form, dtype="f64", env=None):
 @pytest.mark.parametrize("dim,builtin", [(2, "POISSON"), (2, "POISSON_MASS"), (2, "MASS"),
                                          (3, "POISSON"), (3, "POISSON_MASS"), (3, "MASS")])
 @pytest.mark.parametrize("env", [None, {"FEMX_SPEC_AHEAD": "99"}, {"FEMX_SHAREDFACES": "0", "FEMX_ACCF": "0"},
-                                 {"FEMX_SPEC_AHEAD": "0"}])
+                                 {"FEMX_SPEC_AHEAD": "0"}, {"FEMX_ROWSUM": "1", "FEMX_RCP3": "1"}])
 def test_generated_specialised_body_equals_generic_loop_on_the_host(tmp_path, dim, builtin, env):
-    form = femx.Form(None, dim, getattr(femx, builtin), params=(1.5,), offline=True)
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})          # some knobs are read when the form is created
+    try:
+        form = femx.Form(None, dim, getattr(femx, builtin), params=(1.5,), offline=True)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    if env and env.get("FEMX_ROWSUM") == "1" and dim == 3 and builtin != "MASS":
+        form.cubin_stencil(*__import__("tools.stencil_offline", fromlist=["x"]).interior_class(3))
+        assert "#define FEMX_ROWSUM 1" in form.source
     X, Y, Z, conn, rp, ci, interior, gen = _run_case(tmp_path, dim, form, env=env)
     form.close()
     # ... and both are the operator the oracle assembles (host reciprocal = IEEE division here)
