@@ -194,7 +194,7 @@ def test_specialised_pass_custom_strings_fmad_off(ctx, golden_dir):
 
 
 @pytest.mark.gpu
-def test_specialised_pass_strided_coordinates_and_partial_tiles(ctx):
+def test_specialised_pass_partial_and_mixed_tiles(ctx):
     """Mesh sizes that leave ragged tiles and mixed (boundary + interior) tiles everywhere."""
     import torch
     for nR, nC in ((3, 3), (5, 200), (129, 2), (64, 127)):
