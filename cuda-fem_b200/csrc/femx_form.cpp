@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <set>
 #include <sstream>
 
 #include "femx_internal.h"
@@ -66,6 +67,7 @@ struct femx_form {
   int nq = 0;
   std::vector<double> qw, qr, qs, qt, qu;
   std::map<std::string, Variant> variants;
+  std::set<std::string> spec_failed;  // stencil classes whose specialised kernel did not compile
   std::string last_source, last_log;
   mutable std::string err;
 };
@@ -1056,16 +1058,29 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   const size_t rs = form->dtype == FEMX_F32 ? 4 : 8;
   // (the row-list CTAs of that kernel keep one private value segment per thread in shared memory:
   //  patterns whose rows outside the class are very long stay on the generic kernel)
-  const bool spec = pat->spec_np > 0 && pat->spec_rows * 2 >= pat->n_rows && form->nd == 1 && !expanded &&
-                    (form->builtin != FEMX_FORM_CUSTOM || !form->fmad) &&
-                    (size_t)pat->tile_nodes * pat->max_row_other * rs <= 64 * 1024 &&
-                    !(getenv("FEMX_SPEC") && atoi(getenv("FEMX_SPEC")) == 0);
+  bool spec = pat->spec_np > 0 && pat->spec_rows * 2 >= pat->n_rows && form->nd == 1 && !expanded &&
+              (form->builtin != FEMX_FORM_CUSTOM || !form->fmad) &&
+              (size_t)pat->tile_nodes * pat->max_row_other * rs <= 64 * 1024 &&
+              form->spec_failed.count(pat->spec_key) == 0 &&
+              !(getenv("FEMX_SPEC") && atoi(getenv("FEMX_SPEC")) == 0);
+  const char* kname = expanded ? "csr_x" : (cs == 1 ? "csr" : "csr_s");
   if (spec) {
     sc.np = pat->spec_np; sc.rlen = pat->spec_rlen; sc.self = pat->spec_self;
     sc.codes = pat->spec_codes; sc.key = pat->spec_key;
+    st = compile_variant(form, kname, &v, true, &sc);
+    if (st == FEMX_ERR_NVRTC) {
+      // a class body the compiler rejects must not take the operator down: remember it, use the generic kernel
+      // (femx_form_log keeps the compiler's message)
+      form->spec_failed.insert(pat->spec_key);
+      spec = false;
+    } else if (st != FEMX_OK) {
+      return st;
+    }
   }
-  st = compile_variant(form, expanded ? "csr_x" : (cs == 1 ? "csr" : "csr_s"), &v, true, spec ? &sc : nullptr);
-  if (st != FEMX_OK) return st;
+  if (!spec) {
+    st = compile_variant(form, kname, &v, true, nullptr);
+    if (st != FEMX_OK) return st;
+  }
   const femx_driver* drv = femx_get_driver(nullptr);
   // generic kernel: [mbarrier 128 B | codes | values (+16 B phase pad) | columns (+32 B phase pad)];
   // stencil-class kernel: [warp masks 128 B | row ends | values (+16 B phase pad)], or one value segment per thread
