@@ -15,6 +15,8 @@ __global__ void k(double* out, int iters, double a, double b) {
       if (MIX == 0) x[i] = fma(x[i], a, b);
       else if (MIX == 2) { x[i] = fma(x[(i + 1) % ILP], x[(i + 3) % ILP], x[i]); }   // three distinct register operands
       else if (MIX == 3) { x[i] = fma(x[(i + 1) % ILP], x[(i + 3) % ILP], x[i]); x[i] = __dmul_rn(x[(i + 2) % ILP], x[(i + 5) % ILP]); x[i] = __dadd_rn(x[(i + 4) % ILP], x[i]); }
+      else if (MIX == 4) { x[i] = fma(x[(i + 1) % ILP], a, x[i]); }                    // two distinct registers + one shared by consecutive DFMAs (.reuse)
+      else if (MIX == 5) { x[i] = __dmul_rn(x[(i + 1) % ILP], x[(i + 3) % ILP]); }       // DMUL, two distinct registers
       else if (MIX == 1) { x[i] = fma(x[i], a, b); x[i] = __dmul_rn(x[i], a); x[i] = fma(x[i], a, b); x[i] = __dadd_rn(x[i], b); x[i] = __dmul_rn(x[i], b); x[i] = fma(x[i], b, a); }
     }
   }
@@ -40,7 +42,7 @@ void run(int warps_per_sm, int sms, double clk_ghz) {
   cudaEventSynchronize(e1);
   float ms;
   cudaEventElapsedTime(&ms, e0, e1);
-  double per_thread = (double)iters * ILP * (MIX == 0 || MIX == 2 ? 1 : (MIX == 3 ? 3 : 6));
+  double per_thread = (double)iters * ILP * (MIX == 0 || MIX == 2 || MIX == 4 || MIX == 5 ? 1 : (MIX == 3 ? 3 : 6));
   double total = per_thread * threads * blocks;
   double per_clk_sm = total / (ms * 1e-3) / (clk_ghz * 1e9) / sms;
   printf("mix=%d warps/SM=%2d ILP=%2d : %.2f ms, %.1f DP thread-inst/clk/SM (at %.3f GHz), %.2f T inst/s\n", MIX, warps_per_sm, ILP, ms,
@@ -60,5 +62,6 @@ int main() {
   run<4, 0>(8, sms, ghz); run<4, 0>(32, sms, ghz); run<8, 0>(64, sms, ghz);
   run<1, 1>(16, sms, ghz); run<2, 1>(16, sms, ghz); run<4, 1>(16, sms, ghz); run<8, 1>(16, sms, ghz); run<4, 1>(32, sms, ghz);
   run<8, 2>(16, sms, ghz); run<16, 2>(16, sms, ghz); run<8, 2>(20, sms, ghz); run<8, 3>(16, sms, ghz); run<16, 3>(16, sms, ghz); run<16, 3>(20, sms, ghz);
+  run<8, 4>(16, sms, ghz); run<16, 4>(16, sms, ghz); run<8, 5>(16, sms, ghz); run<16, 5>(16, sms, ghz);
   return 0;
 }
