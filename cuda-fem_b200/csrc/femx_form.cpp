@@ -51,6 +51,9 @@ struct femx_form {
   // accumulate form of the built-in scalar entries: acc_pre[li] declares what row li shares, acc_entries[li*n+lj]
   // is the NEW value of an accumulator written $A (one fma chain: no separate product, no separate add)
   std::vector<std::string> acc_pre, acc_entries;
+  // the same chains step by step (FEMX_CHAINORDER=1, experiment): acc_steps[li] lists statements over A0..A{n-1}
+  // in the order mass, x, y, z for all entries at once, so that consecutive fma share hx / hy / hz (.reuse)
+  std::vector<std::string> acc_steps;
   // 3-D scalar built-ins: the prologue is [edges u2,u3,u4 from vertex 1 | d2 = u4 x u3, d3 = u2 x u4, d4 = u3 x u2 |
   // prologue_rest]; the specialised pass then computes each face's cross product once (see build_defines)
   bool shared_faces = false;
@@ -289,6 +292,20 @@ int emit_builtin(femx_form* f, const femx_form_desc* d) {
         if (f->rowsum && a == b) f->acc_entries[(size_t)a * n + b] = d->builtin == FEMX_FORM_POISSON ? "$A" : "$A+jac";
       }
     }
+    if (d->builtin != FEMX_FORM_MASS && getenv("FEMX_CHAINORDER") && atoi(getenv("FEMX_CHAINORDER")) == 1) {
+      f->acc_steps.assign(n, "");
+      for (int a = 0; a < n; ++a) {
+        std::ostringstream o;
+        auto skip = [&](int b) { return f->rowsum && a == b; };
+        for (int b = 0; b < n; ++b)
+          if (skip(b)) { if (d->builtin == FEMX_FORM_POISSON_MASS) o << " A" << b << " = A" << b << "+jac;"; }
+          else if (d->builtin == FEMX_FORM_POISSON_MASS) o << " A" << b << " = fma(" << num(cm * M[a][b]) << ",jac,A" << b << ");";
+        for (int k = 0; k < dim; ++k)
+          for (int b = 0; b < n; ++b)
+            if (!skip(b)) o << " A" << b << " = fma(d" << b + 1 << AX[k] << ",h" << AX[k] << ",A" << b << ");";
+        f->acc_steps[a] = o.str();
+      }
+    }
   }
   // constant source: b[a,c] = f_c * (sum_q w_q phi_a(q)) * jac, pre-integrated like the matrix
   f->rhs.assign(n, "");
@@ -414,8 +431,12 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
       o << "#define FEMX_ROWA_" << li << "(";
       for (int lj = 0; lj < n; ++lj) o << (lj ? "," : "") << "A" << lj;
       o << ") { " << f->acc_pre[li];
-      for (int lj = 0; lj < n; ++lj)
-        o << " \\\n    A" << lj << " = " << subst(f->acc_entries[(size_t)li * n + lj], "A" + std::to_string(lj)) << ";";
+      if (!f->acc_steps.empty()) {
+        o << " \\\n   " << f->acc_steps[li];
+      } else {
+        for (int lj = 0; lj < n; ++lj)
+          o << " \\\n    A" << lj << " = " << subst(f->acc_entries[(size_t)li * n + lj], "A" + std::to_string(lj)) << ";";
+      }
       o << " }\n";
     }
   o << "#define FEMX_QUAD(M)";

@@ -179,7 +179,8 @@ def _run_case(tmp_path, dim, form, dtype="f64", env=None):
 @pytest.mark.parametrize("dim,builtin", [(2, "POISSON"), (2, "POISSON_MASS"), (2, "MASS"),
                                          (3, "POISSON"), (3, "POISSON_MASS"), (3, "MASS")])
 @pytest.mark.parametrize("env", [None, {"FEMX_SPEC_AHEAD": "99"}, {"FEMX_SHAREDFACES": "0", "FEMX_ACCF": "0"},
-                                 {"FEMX_SPEC_AHEAD": "0"}, {"FEMX_ROWSUM": "1", "FEMX_RCP3": "1"}])
+                                 {"FEMX_SPEC_AHEAD": "0"}, {"FEMX_ROWSUM": "1", "FEMX_RCP3": "1"},
+                                 {"FEMX_CHAINORDER": "1"}, {"FEMX_CHAINORDER": "1", "FEMX_ROWSUM": "1"}])
 def test_generated_specialised_body_equals_generic_loop_on_the_host(tmp_path, dim, builtin, env):
     old = {k: os.environ.get(k) for k in (env or {})}
     os.environ.update(env or {})          # some knobs are read when the form is created

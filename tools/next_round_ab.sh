@@ -6,7 +6,7 @@
 cd "$(dirname "$0")/.."
 bash tools/sweep_all.sh cfg3 "A=baseline" "FEMX_ROWSUM=1" "FEMX_RCP3=1" "FEMX_ROWSUM=1 FEMX_RCP3=1" \
      "FEMX_ROWSUM=1 FEMX_RCP3=1 FEMX_SPEC_AHEAD=1" "FEMX_ROWSUM=1 FEMX_RCP3=1 FEMX_SPEC_AHEAD=3" \
-     "FEMX_ROWSUM=1 FEMX_RCP3=1 FEMX_MINBLOCKS=5" "FEMX_ROWSUM=1 FEMX_RCP3=1 FEMX_TILE=64 FEMX_MINBLOCKS=8"
+     "FEMX_CHAINORDER=1" "FEMX_CHAINORDER=1 FEMX_ROWSUM=1 FEMX_RCP3=1" "FEMX_ROWSUM=1 FEMX_RCP3=1 FEMX_MINBLOCKS=5" "FEMX_ROWSUM=1 FEMX_RCP3=1 FEMX_TILE=64 FEMX_MINBLOCKS=8"
 bash tools/sweep_all.sh cfg2 "A=baseline" "FEMX_MINBLOCKS=7" "FEMX_MINBLOCKS=9" "FEMX_SPEC_AHEAD=2" "FEMX_TILE=64 FEMX_MINBLOCKS=16"
 # fp64 issue rates incl. the shared-operand (.reuse) and DMUL variants (build first: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/micro/fp64_peak tools/micro/fp64_peak.cu)
 [ -x tools/micro/fp64_peak ] && tools/micro/fp64_peak | grep 'mix=[245]'
