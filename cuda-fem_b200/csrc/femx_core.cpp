@@ -20,6 +20,44 @@ int femx_fail(const femx_ctx* ctx, int status, const char* fmt, ...) {
   return status;
 }
 
+namespace {
+struct knob_entry { const char* env; const char* name; int femx_knobs::*field; };
+const knob_entry kKnobs[] = {
+    {"FEMX_TILE", "tile", &femx_knobs::tile}, {"FEMX_CARVEOUT", "carveout", &femx_knobs::carveout},
+    {"FEMX_MINBLOCKS", "minblocks", &femx_knobs::minblocks}, {"FEMX_MIDGATHER", "midgather", &femx_knobs::midgather},
+    {"FEMX_UNROLL", "unroll", &femx_knobs::unroll}, {"FEMX_ROTINV", "rotinv", &femx_knobs::rotinv},
+    {"FEMX_SPEC", "spec", &femx_knobs::spec}, {"FEMX_SPEC_AHEAD", "spec_ahead", &femx_knobs::spec_ahead},
+    {"FEMX_SHAREDFACES", "sharedfaces", &femx_knobs::sharedfaces}, {"FEMX_ACCF", "accf", &femx_knobs::accf},
+    {"FEMX_RCP3", "rcp3", &femx_knobs::rcp3}, {"FEMX_SPEC_PREFETCH", "spec_prefetch", &femx_knobs::spec_prefetch},
+    {"FEMX_SPEC_PIN", "spec_pin", &femx_knobs::spec_pin}, {"FEMX_LISTLAST", "listlast", &femx_knobs::listlast},
+    {"FEMX_ROWSUM", "rowsum", &femx_knobs::rowsum}, {"FEMX_CHAINORDER", "chainorder", &femx_knobs::chainorder},
+    {"FEMX_LATTICE", "lattice", &femx_knobs::lattice}, {"FEMX_LT_TX", "lt_tx", &femx_knobs::lt_tx},
+    {"FEMX_LT_TY", "lt_ty", &femx_knobs::lt_ty}, {"FEMX_LT_KC", "lt_kc", &femx_knobs::lt_kc},
+    {"FEMX_LT_MINB", "lt_minb", &femx_knobs::lt_minb}, {"FEMX_LT_REGS", "lt_regs", &femx_knobs::lt_regs},
+};
+}  // namespace
+
+femx_knobs femx_knobs_from_env() {
+  femx_knobs k;
+  for (auto& e : kKnobs)
+    if (const char* v = getenv(e.env))
+      if (*v) k.*(e.field) = atoi(v);
+  if (const char* d = getenv("FEMX_JIT_DUMP")) k.jit_dump = d;
+  return k;
+}
+
+bool femx_knobs_set(femx_knobs* k, const char* name, int value) {
+  for (auto& e : kKnobs)
+    if (!strcmp(name, e.name) || !strcmp(name, e.env)) { k->*(e.field) = value; return true; }
+  return false;
+}
+
+std::string femx_knobs::key() const {
+  std::string s;
+  for (auto& e : kKnobs) s += std::to_string(this->*(e.field)) + ",";
+  return s;
+}
+
 const femx_driver* femx_get_driver(std::string* why) {
   static femx_driver drv;
   static std::string err;
@@ -90,6 +128,7 @@ int femx_ctx_create(int device, femx_ctx** out) {
   if (!femx_get_driver(&why))
     return femx_fail(nullptr, FEMX_ERR_CUDA, "femx_ctx_create: %s", why.c_str());
   femx_ctx* c = new femx_ctx();
+  c->knobs = femx_knobs_from_env();
   c->device = device;
   c->sm_count = p.multiProcessorCount;
   c->smem_optin = p.sharedMemPerBlockOptin;
@@ -108,6 +147,13 @@ int femx_ctx_create(int device, femx_ctx** out) {
     }
   }
   *out = c;
+  return FEMX_OK;
+}
+
+int femx_ctx_set_option(femx_ctx* ctx, const char* name, int value) {
+  if (!ctx || !name) return femx_fail(ctx, FEMX_ERR_INVALID, "femx_ctx_set_option: NULL argument");
+  if (!femx_knobs_set(&ctx->knobs, name, value))
+    return femx_fail(ctx, FEMX_ERR_INVALID, "femx_ctx_set_option: unknown option '%s'", name);
   return FEMX_OK;
 }
 

@@ -8,26 +8,13 @@
 #include <set>
 #include <sstream>
 
-#include "femx_internal.h"
+#include "femx_form_internal.h"
 #include "femx_jit_src.h"
 
 namespace {
 
-struct Variant {
-  std::string source, log;
-  std::vector<char> cubin;
-  CUmodule module = nullptr;
-  CUfunction fn = nullptr;
-  int smem_set = 0;
-  int carveout_set = 0;
-};
-
-// a stencil class handed to the JIT (femx_pattern's dominant class, or an explicit one)
-struct StencilClass {
-  int np = 0, rlen = 0, self = 0;
-  std::vector<uint32_t> codes;
-  std::string key;
-};
+typedef femx_variant Variant;
+typedef femx_stencil_class StencilClass;
 
 std::string num(double v) {
   char b[64];
@@ -40,40 +27,6 @@ std::string num(double v) {
 const char* AX[3] = {"x", "y", "z"};
 
 }  // namespace
-
-struct femx_form {
-  femx_ctx* ctx = nullptr;
-  int dim = 2, nn = 3, nd = 1, dtype = FEMX_F64, builtin = 0, fmad = 1;
-  int n = 3;  // nn*nd
-  int integrated = 0;  // entries are final element-matrix expressions (no quadrature applied)
-  std::string prologue;
-  std::vector<std::string> entries;  // n*n
-  // accumulate form of the built-in scalar entries: acc_pre[li] declares what row li shares, acc_entries[li*n+lj]
-  // is the NEW value of an accumulator written $A (one fma chain: no separate product, no separate add)
-  std::vector<std::string> acc_pre, acc_entries;
-  // the same chains step by step (FEMX_CHAINORDER=1, experiment): acc_steps[li] lists statements over A0..A{n-1}
-  // in the order mass, x, y, z for all entries at once, so that consecutive fma share hx / hy / hz (.reuse)
-  std::vector<std::string> acc_steps;
-  // 3-D scalar built-ins: the prologue is [edges u2,u3,u4 from vertex 1 | d2 = u4 x u3, d3 = u2 x u4, d4 = u3 x u2 |
-  // prologue_rest]; the specialised pass then computes each face's cross product once (see build_defines)
-  bool shared_faces = false;
-  std::string prologue_rest;
-  // FEMX_ROWSUM=1 (experiment, off by default): the rows of a stiffness matrix sum to zero, so the diagonal is not
-  // accumulated entry by entry but recovered at the end of the row, D = cj * (sum of the incident Jacobians) -
-  // (sum of the row's off-diagonal values), cj = c * sum_b M_ab — 4 fma per incidence become one add
-  bool rowsum = false;
-  double rowsum_cj = 0.0;
-  std::vector<std::string> rhs;      // n load-vector integrands (may be empty)
-  int rhs_integrated = 0;
-  // the built-in entries are invariant under even permutations of the local vertices (see build_defines)
-  bool rot_ok_matrix = false, rot_ok_rhs = false;
-  int nq = 0;
-  std::vector<double> qw, qr, qs, qt, qu;
-  std::map<std::string, Variant> variants;
-  std::set<std::string> spec_failed;  // stencil classes whose specialised kernel did not compile
-  std::string last_source, last_log;
-  mutable std::string err;
-};
 
 namespace {
 
@@ -187,7 +140,7 @@ int emit_builtin(femx_form* f, const femx_form_desc* d) {
   const int dim = f->dim, nn = f->nn, nd = f->nd, n = f->n;
   const bool pinned = nd == 1;  // scalar forms: every rounding fixed by the text (see emit_geometry)
   emit_geometry(dim, pinned, &f->prologue, &f->prologue_rest);
-  f->shared_faces = pinned && dim == 3 && !(getenv("FEMX_SHAREDFACES") && atoi(getenv("FEMX_SHAREDFACES")) == 0);
+  f->shared_faces = pinned && dim == 3 && f->knobs.sharedfaces != 0;
   f->integrated = 1;
   f->entries.assign((size_t)n * n, "");
   double W = 0.0;
@@ -217,6 +170,16 @@ int emit_builtin(femx_form* f, const femx_form_desc* d) {
   const bool has_mass = d->builtin == FEMX_FORM_POISSON_MASS || d->builtin == FEMX_FORM_MASS;
   f->rot_ok_matrix = !has_mass || msym;
   f->rot_ok_rhs = vsym;
+  if (pinned && dim == 3 && f->rot_ok_matrix && d->builtin != FEMX_FORM_ELASTICITY) {
+    // element-once lattice pass (femx_lattice.cpp): symmetric entries, diagonal from the zero row sum of the
+    // stiffness part: K_aa = c (sum_b M_ab) jac - sum_{b != a} K_ab
+    const double cmass = d->builtin == FEMX_FORM_POISSON ? 0.0 : (d->builtin == FEMX_FORM_MASS ? 1.0 : (d->params[0] != 0.0 ? d->params[0] : 1.0));
+    f->lt_ok = true;
+    f->lt_W = W;
+    f->lt_moff = cmass * M[0][1];
+    f->lt_cj = 0.0;
+    for (int b = 0; b < nn; ++b) f->lt_cj += cmass * M[0][b];
+  }
   std::ostringstream pro;
   if (pinned) {
     pro << "  const real kq = femx_mul(" << num(W) << ",ijac);\n";
@@ -262,11 +225,11 @@ int emit_builtin(femx_form* f, const femx_form_desc* d) {
   //   A <- d_b . (kq d_a) + (c M_ab jac + A),  with h = kq d_a shared by the row
   // (3-D only: there the numeric pass is bound by the fp64 pipe; in 2-D it is not, and the form costs the
   //  generic kernel 8 registers = 2 resident CTAs)
-  if (pinned && dim == 3 && d->builtin != FEMX_FORM_ELASTICITY && !(getenv("FEMX_ACCF") && atoi(getenv("FEMX_ACCF")) == 0)) {
+  if (pinned && dim == 3 && d->builtin != FEMX_FORM_ELASTICITY && f->knobs.accf != 0) {
     f->acc_pre.assign(n, "");
     f->acc_entries.assign((size_t)n * n, "");
     f->rowsum = f->rot_ok_matrix && (d->builtin == FEMX_FORM_POISSON || d->builtin == FEMX_FORM_POISSON_MASS) &&
-                getenv("FEMX_ROWSUM") && atoi(getenv("FEMX_ROWSUM")) == 1;
+                f->knobs.rowsum == 1;
     if (f->rowsum && d->builtin == FEMX_FORM_POISSON_MASS)
       for (int b = 0; b < nn; ++b) f->rowsum_cj += cm * M[0][b];
     for (int a = 0; a < n; ++a) {
@@ -292,7 +255,7 @@ int emit_builtin(femx_form* f, const femx_form_desc* d) {
         if (f->rowsum && a == b) f->acc_entries[(size_t)a * n + b] = d->builtin == FEMX_FORM_POISSON ? "$A" : "$A+jac";
       }
     }
-    if (d->builtin != FEMX_FORM_MASS && getenv("FEMX_CHAINORDER") && atoi(getenv("FEMX_CHAINORDER")) == 1) {
+    if (d->builtin != FEMX_FORM_MASS && f->knobs.chainorder == 1) {
       f->acc_steps.assign(n, "");
       for (int a = 0; a < n; ++a) {
         std::ostringstream o;
@@ -376,24 +339,26 @@ bool depends_on_q(const std::string& e) {
 //   FEMX_ROWC_<li>              entries that do not depend on the quadrature point:
 //                               out[lj] = E (pre-integrated) or out[lj] = (sum_q w_q) * E
 //   FEMX_ROWQ_<li>(R,S,T,U,W)   one quadrature-point update of the entries that do
-std::string build_defines(const femx_form* f, const std::string& kernel, const StencilClass* sc) {
+// tile_nodes: threads per CTA of the numeric pass (the pattern's tile, or the lattice pass's CTA size)
+std::string build_defines(const femx_form* f, const std::string& kernel, const StencilClass* sc, int tile_nodes) {
   std::ostringstream o;
   const int n = f->n;
+  const femx_knobs& K = f->knobs;
+  if (tile_nodes <= 0) tile_nodes = femx_tile_nodes_for(f->nd, K);
   o << "#define FEMX_REAL " << (f->dtype == FEMX_F32 ? "float" : "double") << "\n";
   o << "#define NN " << f->nn << "\n#define ND " << f->nd << "\n#define DIM " << f->dim
-    << "\n#define FEMX_TILE_NODES " << femx_tile_nodes_for(f->nd) << "\n";
+    << "\n#define FEMX_TILE_NODES " << tile_nodes << "\n";
   // (the specialised 3-D body holds 45 coordinates + 15 accumulators per thread: 512 threads per SM keep it at
   //  128 registers without spills, measured faster than the 164 the compiler takes when left alone)
-  const int tile_nodes = femx_tile_nodes_for(f->nd);
   // (2-D body: 1024 threads per SM = 64 registers; measured 0.27 ms on cfg2 against 0.29-0.31 ms at the 48, 56 or
   //  68 registers other limits produce — the schedule ptxas finds at this limit, not the occupancy, makes the difference)
   const int min_blocks_default = !sc ? 0 : (f->dim == 3 ? 512 : 1024) / tile_nodes;
-  o << "#define FEMX_MIN_BLOCKS " << (getenv("FEMX_MINBLOCKS") ? atoi(getenv("FEMX_MINBLOCKS")) : min_blocks_default) << "\n";
-  o << "#define FEMX_MIDGATHER " << (getenv("FEMX_MIDGATHER") ? atoi(getenv("FEMX_MIDGATHER")) : 1) << "\n";
-  o << "#define FEMX_UNROLL " << (getenv("FEMX_UNROLL") ? atoi(getenv("FEMX_UNROLL")) : 1) << "\n";
+  o << "#define FEMX_MIN_BLOCKS " << (K.minblocks >= 0 ? K.minblocks : min_blocks_default) << "\n";
+  o << "#define FEMX_MIDGATHER " << K.midgather << "\n";
+  o << "#define FEMX_UNROLL " << K.unroll << "\n";
   o << "#define FEMX_ROWSUM " << (f->rowsum ? 1 : 0) << "\n#define FEMX_CJ " << num(f->rowsum_cj) << "\n";
-  o << "#define FEMX_LISTLAST " << (getenv("FEMX_LISTLAST") ? atoi(getenv("FEMX_LISTLAST")) : 0) << "\n";
-  o << "#define FEMX_RCP3 " << (getenv("FEMX_RCP3") ? atoi(getenv("FEMX_RCP3")) : 0) << "\n";
+  o << "#define FEMX_LISTLAST " << K.listlast << "\n";
+  o << "#define FEMX_RCP3 " << K.rcp3 << "\n";
   o << "#define FEMX_EXPANDED " << (kernel == "csr_x" ? 1 : 0) << "\n";
   o << "#define FEMX_UNIT_STRIDE " << (kernel == "csr" ? 1 : 0) << "\n";
   std::string esc;
@@ -455,7 +420,7 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
   // can be evaluated as "row 0 of the element (own node, others...)" — an even permutation of the
   // element, same signed Jacobian: one case, no switch, no divergence on unstructured meshes.
   // Custom strings name local vertices explicitly and keep one case per li.
-  const bool rot_allowed = f->builtin != FEMX_FORM_CUSTOM && !(getenv("FEMX_ROTINV") && atoi(getenv("FEMX_ROTINV")) == 0);
+  const bool rot_allowed = f->builtin != FEMX_FORM_CUSTOM && K.rotinv != 0;
   const bool is_rhs = kernel == "rhs";
   const bool rotinv = rot_allowed && (is_rhs ? (f->rot_ok_rhs && f->rhs_integrated) : f->rot_ok_matrix);
   o << "#define FEMX_ROTINV " << (rotinv ? 1 : 0) << "\n";
@@ -568,7 +533,7 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
     // live (7 of 14 neighbours on the Kuhn stencil) — fewer registers, more resident warps.
     // FEMX_SPEC_AHEAD >= the incidence count loads everything up front.
     // (2-D stencils are small: everything up front measured fastest there)
-    const int ahead = getenv("FEMX_SPEC_AHEAD") ? atoi(getenv("FEMX_SPEC_AHEAD")) : (dim == 2 ? 99 : 2);
+    const int ahead = K.spec_ahead >= 0 ? K.spec_ahead : (dim == 2 ? 99 : 2);
     std::vector<int> first(sc->rlen, sc->np), last(sc->rlen, -1);
     for (int it = 0; it < sc->np; ++it)
       for (int j = 0; j < nn - 1; ++j) {
@@ -577,7 +542,7 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
         last[pos] = it;
       }
     first[sc->self] = 0;
-    const bool pin = !(getenv("FEMX_SPEC_PIN") && atoi(getenv("FEMX_SPEC_PIN")) == 0);
+    const bool pin = K.spec_pin != 0;
     auto load_col = [&](int k, bool entry) {
       o << " \\\n    const i64 q" << k << "_ = (i64)min(max(node_ + soff.v[" << k << "], 0), node_max) * FEMX_CS; const real";
       for (int c = 0; c < dim; ++c)
@@ -599,7 +564,7 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
     }
     // Experiment (off: measured slower, the volatile prefetches cost spills): FEMX_SPEC_PREFETCH=1 prefetches
     // the columns loaded later into L1 at kernel entry, =2 into L2.
-    const int pf = getenv("FEMX_SPEC_PREFETCH") ? atoi(getenv("FEMX_SPEC_PREFETCH")) : 0;
+    const int pf = K.spec_prefetch;
     o << "#define FEMX_SPEC_LOAD";
     for (int k = 0; k < sc->rlen; ++k)
       if (first[k] <= ahead) load_col(k, true);  // issued at kernel entry, before any metadata has arrived
@@ -704,28 +669,40 @@ std::string build_defines(const femx_form* f, const std::string& kernel, const S
 
 // kernel: "coo", "coo_e", "rhs", "csr" (unit node stride), "csr_s" (strided), "csr_x" (element-expanded
 // coordinates); sc != NULL: the csr kernel for a pattern with that stencil class (specialised body for
-// the class rows, row-list CTAs for the others)
+// the class rows, row-list CTAs for the others); lat/plan != NULL: the element-once lattice pass for the
+// class rows of a lattice mesh.  tile = threads per CTA the kernel is compiled for (0: the form's default).
 int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, bool load,
-                    const StencilClass* sc = nullptr) {
-  const std::string vkey = sc ? kernel + "@" + sc->key : kernel;
+                    const StencilClass* sc = nullptr, int tile = 0, const femx_lattice* lat = nullptr,
+                    femx_lattice_plan* plan = nullptr, const std::string& lat_key = std::string()) {
+  std::string vkey = kernel;
+  if (lat) vkey += "@L" + lat_key;
+  else if (sc) vkey += "@" + sc->key;
+  if (tile > 0) vkey += "#" + std::to_string(tile);
   auto it = f->variants.find(vkey);
   if (it == f->variants.end()) {
     Variant v;
-    const char* body = nullptr;
+    const bool is_csr = kernel == "csr" || kernel == "csr_x" || kernel == "csr_s";
+    std::string body;
     if (kernel == "coo") body = kFemxJitCoo;
     else if (kernel == "coo_e") body = kFemxJitCooElem;
     else if (kernel == "rhs") body = kFemxJitRhs;
-    else if (kernel == "csr" || kernel == "csr_x" || kernel == "csr_s") body = kFemxJitCsr;
+    else if (is_csr) body = std::string(kFemxJitCsrRow) + (lat ? kFemxJitLattice : kFemxJitCsr);
     else return femx_fail(f->ctx, FEMX_ERR_INVALID, "unknown kernel variant '%s'", kernel.c_str());
-    if (sc && kernel != "csr" && kernel != "csr_s")
+    if ((sc || lat) && kernel != "csr" && kernel != "csr_s")
       return femx_fail(f->ctx, FEMX_ERR_INVALID, "kernel '%s' has no specialised form", kernel.c_str());
-    v.source = "// femx JIT kernel '" + vkey + "' (generated)\n" + build_defines(f, kernel, sc) +
-               kFemxJitCommon + body;
+    std::string defs = build_defines(f, kernel, lat ? nullptr : sc, lat ? plan->threads : tile);
+    if (lat) {
+      const std::string ld = femx_lattice_defines(f, *lat, plan);
+      if (ld.empty())
+        return femx_fail(f->ctx, FEMX_ERR_UNSUPPORTED, "lattice pass: %s", plan->fallback.c_str());
+      defs += ld;
+    }
+    v.source = "// femx JIT kernel '" + vkey + "' (generated)\n" + defs + kFemxJitCommon + body;
     nvrtcProgram prog;
-    std::string fname = "femx_" + kernel + (sc ? "_spec" : "") + ".cu";
-    if (const char* dump = getenv("FEMX_JIT_DUMP")) {  // keep the source on disk (ncu --import-source)
-      fname = std::string(dump) + "/" + fname;
-      if (FILE* fp = fopen(fname.c_str(), "w")) { fwrite(v.source.data(), 1, v.source.size(), fp); fclose(fp); }
+    std::string fname = "femx_" + kernel + (lat ? "_lattice" : (sc ? "_spec" : "")) + ".cu";
+    if (!f->knobs.jit_dump.empty()) {  // keep the source on disk (ncu --import-source)
+      fname = f->knobs.jit_dump + "/" + fname;
+        if (FILE* fp = fopen(fname.c_str(), "w")) { fwrite(v.source.data(), 1, v.source.size(), fp); fclose(fp); }
     }
     nvrtcResult r = nvrtcCreateProgram(&prog, v.source.c_str(), fname.c_str(), 0, nullptr, nullptr);
     if (r != NVRTC_SUCCESS)
@@ -794,6 +771,7 @@ int make_form(femx_ctx* ctx, const femx_form_desc* d, femx_form** out) {
     return femx_fail(ctx, FEMX_ERR_INVALID, "femx_form_compile: bad dtype %d", d->dtype);
   femx_form* f = new femx_form();
   f->ctx = ctx;
+  f->knobs = ctx ? ctx->knobs : femx_knobs_from_env();
   f->dim = d->dim; f->nn = d->nn; f->nd = d->nd; f->dtype = d->dtype;
   f->builtin = d->builtin; f->fmad = d->fmad ? 1 : 0;
   f->n = d->nn * d->nd;
@@ -901,6 +879,7 @@ int femx_form_compile_offline(const femx_form_desc* desc, femx_form** out) {
 void femx_form_destroy(femx_form* form) {
   if (!form) return;
   const femx_driver* drv = femx_get_driver(nullptr);
+  if (form->ctx) cudaSetDevice(form->ctx->device);
   for (auto& kv : form->variants)
     if (kv.second.module && drv) drv->ModuleUnload(kv.second.module);
   delete form;
@@ -960,6 +939,35 @@ int femx_form_cubin_stencil(femx_form* form, int n_incid, int row_len, int self_
   return FEMX_OK;
 }
 
+int femx_form_cubin_lattice(femx_form* form, int n_per_cell, const int32_t* h_corners, int64_t stride_y,
+                            int64_t stride_z, int row_len, int self_pos, const int32_t* h_offsets,
+                            const void** cubin, size_t* size, int* h_info) {
+  if (!form || !h_corners || !h_offsets)
+    return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_form_cubin_lattice: NULL argument");
+  if (n_per_cell < 1 || n_per_cell > 8 || row_len < 2 || row_len > 32 || self_pos < 0 || self_pos >= row_len)
+    return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_form_cubin_lattice: bad sizes");
+  femx_lattice L;
+  L.ok = true; L.dim = form->dim; L.P = n_per_cell;
+  L.cn[0] = L.cn[1] = L.cn[2] = 64;  // nominal extents: only the tile shape depends on them
+  L.s[0] = 1; L.s[1] = stride_y; L.s[2] = stride_z;
+  for (int t = 0; t < n_per_cell; ++t)
+    for (int a = 0; a < form->nn; ++a) L.corner[t][a] = (unsigned char)(h_corners[t * form->nn + a] & 7);
+  std::vector<int32_t> off(h_offsets, h_offsets + row_len);
+  femx_lattice_plan plan;
+  std::string why;
+  if (!femx_lattice_plan_make(form, L, row_len, self_pos, off, form->knobs, &plan, &why))
+    return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED, "femx_form_cubin_lattice: %s", why.c_str());
+  Variant* v = nullptr;
+  int st = compile_variant(form, "csr", &v, false, nullptr, 0, &L, &plan, femx_lattice_key(L, plan));
+  if (st != FEMX_OK) return st;
+  form->last_source = v->source;
+  form->last_log = v->log;
+  if (cubin) *cubin = v->cubin.data();
+  if (size) *size = v->cubin.size();
+  if (h_info) { h_info[0] = plan.tx; h_info[1] = plan.ty; h_info[2] = plan.threads; h_info[3] = plan.nslot; h_info[4] = (int)plan.smem; h_info[5] = plan.minb; }
+  return FEMX_OK;
+}
+
 int femx_assemble_coo(femx_form* form, const femx_mesh_view* mesh, void* d_A, int32_t* d_rowA,
                       int32_t* d_colA, void* stream) {
   if (!form) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_assemble_coo: form is NULL");
@@ -967,6 +975,9 @@ int femx_assemble_coo(femx_form* form, const femx_mesh_view* mesh, void* d_A, in
   int st = check_mesh(form, mesh, &expanded);
   if (st != FEMX_OK) return st;
   if (mesh->n_elems == 0) return FEMX_OK;
+  if (form->ctx) FEMX_CUDA_OK(form->ctx, cudaSetDevice(form->ctx->device));
+  if (((uintptr_t)d_A | (uintptr_t)d_rowA | (uintptr_t)d_colA) % 16)
+    return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_coo: d_A, d_rowA and d_colA must be 16-byte aligned");
   if (!mesh->d_conn && (!expanded || d_rowA || d_colA))
     return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_coo: connectivity is NULL");
   // scalar forms: one thread per element, TMA bulk stores; vector forms: one thread per (element, row)
@@ -1026,8 +1037,11 @@ int femx_assemble_rhs(femx_form* form, const femx_pattern* pat, const femx_mesh_
     return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_rhs: pattern does not match the form");
   if (mesh->n_nodes != pat->n_nodes || mesh->n_elems != pat->n_elems)
     return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_rhs: mesh sizes differ from the pattern's");
+  if (!form->ctx || !pat->ctx || form->ctx->device != pat->ctx->device)
+    return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_rhs: form and pattern belong to different devices");
   if (pat->n_rows == 0) return FEMX_OK;
   if (!d_rhs) return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_rhs: d_rhs is NULL");
+  FEMX_CUDA_OK(form->ctx, cudaSetDevice(form->ctx->device));
   Variant* v = nullptr;
   st = compile_variant(form, "rhs", &v, true);
   if (st != FEMX_OK) return st;
@@ -1071,7 +1085,12 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
     return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_csr: d_values is NULL");
   if (pat->n_rows == 0 || pat->nnz_node == 0) return FEMX_OK;
   long long cs = mesh->node_stride ? mesh->node_stride : 1;
+  FEMX_CUDA_OK(form->ctx, cudaSetDevice(form->ctx->device));
+  // the tile / run / element-tile stores are 16-byte bulk copies whose phase is derived from the value INDEX
+  if ((uintptr_t)d_values % 16)
+    return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_csr: d_values must be 16-byte aligned");
   Variant* v = nullptr;
+  const femx_knobs& live = form->ctx->knobs;  // spec / lattice / carveout can be switched per call (femx_ctx_set_option)
   // The pattern's dominant stencil class gets a straight-line body when it covers most rows.  Only
   // where both paths are certain to round identically: built-in forms (every fma spelled out) or
   // strings compiled with --fmad=false.
@@ -1082,47 +1101,34 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   bool spec = pat->spec_np > 0 && pat->spec_rows * 2 >= pat->n_rows && form->nd == 1 && !expanded &&
               (form->builtin != FEMX_FORM_CUSTOM || !form->fmad) &&
               (size_t)pat->tile_nodes * pat->max_row_other * rs <= 64 * 1024 &&
-              form->spec_failed.count(pat->spec_key) == 0 &&
-              !(getenv("FEMX_SPEC") && atoi(getenv("FEMX_SPEC")) == 0);
+              form->spec_failed.count(pat->spec_key) == 0 && live.spec != 0;
   const char* kname = expanded ? "csr_x" : (cs == 1 ? "csr" : "csr_s");
-  if (spec) {
-    sc.np = pat->spec_np; sc.rlen = pat->spec_rlen; sc.self = pat->spec_self;
-    sc.codes = pat->spec_codes; sc.key = pat->spec_key;
-    st = compile_variant(form, kname, &v, true, &sc);
-    if (st == FEMX_ERR_NVRTC) {
-      // a class body the compiler rejects must not take the operator down: remember it, use the generic kernel
-      // (femx_form_log keeps the compiler's message)
-      form->spec_failed.insert(pat->spec_key);
-      spec = false;
-    } else if (st != FEMX_OK) {
-      return st;
+  // Lattice meshes (3-D, symmetric built-in forms): the element-once pass takes the class rows.
+  femx_lattice_plan plan;
+  bool lattice = false;
+  std::string lat_key;
+  if (spec && pat->lat.ok && form->lt_ok && live.lattice != 0) {
+    std::string why;
+    femx_knobs kk = form->knobs;
+    kk.lt_tx = live.lt_tx; kk.lt_ty = live.lt_ty; kk.lt_kc = live.lt_kc; kk.lt_minb = live.lt_minb;
+    if (femx_lattice_plan_make(form, pat->lat, pat->spec_rlen, pat->spec_self, pat->spec_off, kk, &plan, &why)) {
+      lat_key = femx_lattice_key(pat->lat, plan);
+      if (!form->lt_failed.count(lat_key)) {
+        st = compile_variant(form, kname, &v, true, nullptr, 0, &pat->lat, &plan, lat_key);
+        if (st == FEMX_ERR_NVRTC || st == FEMX_ERR_UNSUPPORTED) form->lt_failed.insert(lat_key);  // stencil-class kernel instead
+        else if (st != FEMX_OK) return st;
+        else lattice = true;
+      }
     }
   }
-  if (!spec) {
-    st = compile_variant(form, kname, &v, true, nullptr);
-    if (st != FEMX_OK) return st;
-  }
   const femx_driver* drv = femx_get_driver(nullptr);
-  // generic kernel: [mbarrier 128 B | codes | values (+16 B phase pad) | columns (+32 B phase pad)];
-  // stencil-class kernel: [warp masks 128 B | row ends | values (+16 B phase pad)], or one value segment per thread
-  // in the row-list CTAs
-  const size_t img = (((size_t)pat->max_tile_nnz * form->nd * form->nd * rs + 15) / 16) * 16 + 32;
-  const int seg = pat->max_row_other * form->nd * form->nd;
-  const size_t spec_hdr = 128 + (((size_t)pat->tile_nodes * 4 + 127) / 128) * 128;  // FEMX_SPEC_HDR
-  size_t smem = spec ? std::max(spec_hdr + img, (size_t)pat->tile_nodes * seg * rs)
-                     : 128 + (size_t)pat->max_tile_codes * 4 + img + (size_t)pat->max_tile_nnz * 4 + 32;
-  if (smem > form->ctx->smem_optin)
-    return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED,
-                     "femx_assemble_csr: a %d-row tile needs %zu B of shared memory (> %zu)",
-                     pat->tile_nodes, smem, form->ctx->smem_optin);
   auto prepare = [&](Variant* vv, size_t bytes, int threads) -> int {
     if (!vv->carveout_set || (int)bytes > vv->smem_set) {
       // Shared-memory carve-out: just enough for the CTAs that registers/threads allow, the rest
-      // stays L1 for the coordinate gathers.  (FEMX_CARVEOUT=percent overrides: experiments.)
+      // stays L1 for the coordinate gathers.  (knob carveout = percent overrides: experiments.)
       int pct = 0;
-      const char* cv = getenv("FEMX_CARVEOUT");
-      if (cv && *cv) {
-        pct = atoi(cv);
+      if (live.carveout >= 0) {
+        pct = live.carveout;
       } else {
         int regs = 64;
         drv->FuncGetAttribute(&regs, CU_FUNC_ATTRIBUTE_NUM_REGS, vv->fn);
@@ -1144,8 +1150,6 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
     }
     return FEMX_OK;
   };
-  st = prepare(v, smem, pat->tile_nodes);
-  if (st != FEMX_OK) return st;
   const void* const* c = expanded ? mesh->d_elem_xyz : mesh->d_node_xyz;
   const void* X = c[0]; const void* Y = c[1]; const void* Z = c[2];
   int n_rows = (int)pat->n_rows;
@@ -1155,17 +1159,79 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   const uint32_t* code = pat->d_sell_code;
   const int32_t* pelem = pat->d_sell_elem;
   int row_node0 = (int)pat->row_begin, node_max = (int)pat->n_nodes - 1;
-  struct { int v[24]; } soff = {};
-  if (spec)
-    for (int k = 0; k < pat->spec_rlen; ++k) soff.v[k] = pat->spec_off[k];
   const int32_t* rowlist = pat->d_other_rows;
-  int n_list = spec ? (int)pat->n_other : 0;
+  const int seg = pat->max_row_other * form->nd * form->nd;
   int seg_arg = seg;
-  void* args[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &n_rows,
-                  &row_node0, &node_max, &soff, &rowlist, &n_list, &seg_arg};
-  unsigned threads = (unsigned)pat->tile_nodes;  // one thread per node row
-  unsigned blocks = (unsigned)((pat->n_rows + pat->tile_nodes - 1) / pat->tile_nodes) + (n_list + threads - 1) / threads;
-  CUresult cr = drv->LaunchKernel(v->fn, blocks, 1, 1, threads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
+  CUresult cr;
+  if (lattice) {
+    const femx_lattice& L = pat->lat;
+    struct { int cnx, cny, cnz, sy, sz, node0, klo, khi, ntx, nty, kc; } lat;
+    lat.cnx = L.cn[0]; lat.cny = L.cn[1]; lat.cnz = L.cn[2];
+    lat.sy = (int)L.s[1]; lat.sz = (int)L.s[2]; lat.node0 = (int)L.node0;
+    // node planes that hold owned class rows
+    long long klo = 1, khi = L.cn[2] - 1;
+    if (pat->row_begin > L.node0) klo = std::max<long long>(klo, (pat->row_begin - L.node0) / L.s[2]);
+    if (pat->row_end - 1 >= L.node0) khi = std::min<long long>(khi, (pat->row_end - 1 - L.node0) / L.s[2]);
+    else khi = 0;
+    lat.klo = (int)klo; lat.khi = (int)khi;
+    lat.ntx = (L.cn[0] - 1 + plan.tx - 2) / (plan.tx - 1);
+    lat.nty = (L.cn[1] - 1 + plan.ty - 2) / (plan.ty - 1);
+    lat.kc = plan.kc;
+    const long long ntz = khi >= klo ? (khi - klo + 1 + plan.kc - 1) / plan.kc : 0;
+    int n_list = (int)pat->n_other;
+    const size_t smem = std::max(plan.smem, (size_t)plan.threads * seg * rs);
+    if (smem > form->ctx->smem_optin)
+      return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED, "femx_assemble_csr: the lattice pass needs %zu B of shared memory (> %zu)",
+                       smem, form->ctx->smem_optin);
+    st = prepare(v, smem, plan.threads);
+    if (st != FEMX_OK) return st;
+    void* args[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &n_rows,
+                    &row_node0, &lat, &rowlist, &n_list, &seg_arg};
+    const long long blocks = (long long)lat.ntx * lat.nty * ntz + (n_list + plan.threads - 1) / plan.threads;
+    if (blocks > 2147483647LL) return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED, "femx_assemble_csr: %lld blocks exceed the grid limit", blocks);
+    if (blocks == 0) return FEMX_OK;
+    cr = drv->LaunchKernel(v->fn, (unsigned)blocks, 1, 1, (unsigned)plan.threads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
+  } else {
+    if (spec) {
+      sc.np = pat->spec_np; sc.rlen = pat->spec_rlen; sc.self = pat->spec_self;
+      sc.codes = pat->spec_codes; sc.key = pat->spec_key;
+      st = compile_variant(form, kname, &v, true, &sc, pat->tile_nodes);
+      if (st == FEMX_ERR_NVRTC) {
+        // a class body the compiler rejects must not take the operator down: remember it, use the generic kernel
+        // (femx_form_log keeps the compiler's message)
+        form->spec_failed.insert(pat->spec_key);
+        spec = false;
+      } else if (st != FEMX_OK) {
+        return st;
+      }
+    }
+    if (!spec) {
+      st = compile_variant(form, kname, &v, true, nullptr, pat->tile_nodes);
+      if (st != FEMX_OK) return st;
+    }
+    // generic kernel: [mbarrier 128 B | codes | values (+16 B phase pad) | columns (+32 B phase pad)];
+    // stencil-class kernel: [warp masks 128 B | row ends | values (+16 B phase pad)], or one value segment per thread
+    // in the row-list CTAs
+    const size_t img = (((size_t)pat->max_tile_nnz * form->nd * form->nd * rs + 15) / 16) * 16 + 32;
+    const size_t spec_hdr = 128 + (((size_t)pat->tile_nodes * 4 + 127) / 128) * 128;  // FEMX_SPEC_HDR
+    size_t smem = spec ? std::max(spec_hdr + img, (size_t)pat->tile_nodes * seg * rs)
+                       : 128 + (size_t)pat->max_tile_codes * 4 + img + (size_t)pat->max_tile_nnz * 4 + 32;
+    if (smem > form->ctx->smem_optin)
+      return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED,
+                       "femx_assemble_csr: a %d-row tile needs %zu B of shared memory (> %zu)",
+                       pat->tile_nodes, smem, form->ctx->smem_optin);
+    st = prepare(v, smem, pat->tile_nodes);
+    if (st != FEMX_OK) return st;
+    struct { int v[24]; } soff = {};
+    if (spec)
+      for (int k = 0; k < pat->spec_rlen; ++k) soff.v[k] = pat->spec_off[k];
+    int n_list = spec ? (int)pat->n_other : 0;
+    void* args[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &n_rows,
+                    &row_node0, &node_max, &soff, &rowlist, &n_list, &seg_arg};
+    unsigned threads = (unsigned)pat->tile_nodes;  // one thread per node row
+    unsigned blocks = (unsigned)((pat->n_rows + pat->tile_nodes - 1) / pat->tile_nodes) + (n_list + threads - 1) / threads;
+    cr = drv->LaunchKernel(v->fn, blocks, 1, 1, threads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
+  }
   if (cr != CUDA_SUCCESS) {
     const char* es = nullptr;
     drv->GetErrorString(cr, &es);

@@ -12,7 +12,27 @@
 
 #include "femx.h"
 
+// Tuning knobs (experiments; the defaults are what DESIGN.md measures).  Read from the environment
+// ONCE — at femx_ctx_create, or at femx_form_compile_offline for forms without a context — and
+// changed at run time only through femx_ctx_set_option: no getenv in any launch path.
+struct femx_knobs {
+  int tile = 0;         // FEMX_TILE      node rows per CTA of the generic pass (0 = default)
+  int carveout = -1;    // FEMX_CARVEOUT  shared-memory carve-out % (-1 = derived from occupancy)
+  int minblocks = -1;   // FEMX_MINBLOCKS __launch_bounds__ min blocks (-1 = default)
+  int midgather = 1, unroll = 1, rotinv = 1;
+  int spec = 1;         // FEMX_SPEC      stencil-class detection and use
+  int spec_ahead = -1, sharedfaces = 1, accf = 1, rcp3 = 0, spec_prefetch = 0, spec_pin = 1, listlast = 0;
+  int rowsum = 0, chainorder = 0;
+  int lattice = 1;      // FEMX_LATTICE   element-once lattice pass on structured 3-D meshes
+  int lt_tx = 0, lt_ty = 0, lt_kc = 0, lt_minb = 0, lt_regs = 0;  // FEMX_LT_*: tile shape / k-chunk / occupancy of that pass
+  std::string jit_dump; // FEMX_JIT_DUMP  directory that receives the generated sources
+  std::string key() const;
+};
+femx_knobs femx_knobs_from_env();
+bool femx_knobs_set(femx_knobs* k, const char* name, int value);
+
 struct femx_ctx {
+  femx_knobs knobs;
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
@@ -47,6 +67,20 @@ void femx_set_global_error(const std::string& s);
       return femx_fail((ctx), FEMX_ERR_CUDA, "%s failed: %s (%s:%d)", #call,      \
                        cudaGetErrorString(e__), __FILE__, __LINE__);               \
   } while (0)
+
+// ---- lattice structure of a mesh (femx_pattern.cu: detect_lattice) ---------------------------
+// The elements come in cells of P consecutive elements, cell c = ci + cn[0]*(cj + cn[1]*ck), and every
+// cell is a translate of cell 0: vertex a of element c*P + t is lattice node (ci,cj,ck) + corner[t][a],
+// node id = node0 + i + j*s[1] + k*s[2].  What RectangleMesh::generate / femx_mesh_box (and any
+// structured generator that numbers cell-major) produce; verified element by element on the device.
+struct femx_lattice {
+  bool ok = false;
+  int dim = 0, P = 0;
+  int cn[3] = {1, 1, 1};             // cells per axis
+  long long s[3] = {1, 0, 0};        // node strides (local node ids)
+  long long node0 = 0;               // local id of lattice node (0,0,0)
+  unsigned char corner[8][4] = {};   // bit 0 = dx, bit 1 = dy, bit 2 = dz
+};
 
 // ---- pattern object (femx_pattern.cu) -------------------------------------
 // Node-level CSR + scatter map.  All arrays are device memory owned by the
@@ -84,6 +118,8 @@ struct femx_pattern {
   int32_t* d_other_rows = nullptr;   // [n_other] rows outside the class, ascending (device)
   int64_t n_other = 0;
   int max_row_other = 0;             // longest of those rows
+  femx_lattice lat;                  // lattice structure of the mesh, if it has one (and a class was found)
+  int64_t lat_rows = 0;              // class rows = lattice-interior nodes among the owned rows (checked)
 };
 
 // rowinfo[i].y = #incidences (bits 0-21) | (bit 22 reserved) | FEMX_ROW_SPEC | own position << 24
@@ -102,11 +138,8 @@ static inline __host__ __device__ int femx_oth(int nn, int li, int j) {
   return nn == 4 ? (li ^ (j + 1)) : (li + 1 + j) % 3;
 }
 
-// node rows per CTA of the numeric pass (FEMX_TILE overrides: tuning experiments only)
-static inline int femx_tile_nodes_for(int nd) {
-  if (const char* e = getenv("FEMX_TILE")) {
-    int t = atoi(e);
-    if (t >= 32 && t <= 1024 && t % 32 == 0) return t;
-  }
+// node rows per CTA of the generic numeric pass (knob `tile` overrides: tuning experiments only)
+static inline int femx_tile_nodes_for(int nd, const femx_knobs& k) {
+  if (k.tile >= 32 && k.tile <= 1024 && k.tile % 32 == 0) return k.tile;
   return nd == 1 ? 128 : 32;
 }

@@ -33,6 +33,7 @@ __device__ __forceinline__ T femx_pow(T a, double e) { return ::femx_pow(a, e); 
 // Newton steps -> relative error far below 1 ulp of a double for normal inputs, branch-free
 // (the compiler's IEEE division adds a slow-path test and a fifth correction FMA per element).
 // FEMX_RCP3: one third-order step instead, x(1 + e + e^2) with e = 1 - a x: error e^3 <= 2^-60, one fma less.
+#ifndef FEMX_HOST_EMU  // (tests compile the lattice kernel for the host: tests/test_lattice_host.py)
 __device__ __forceinline__ double femx_rcp(double a) {
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
@@ -52,6 +53,7 @@ __device__ __forceinline__ float femx_rcp(float a) { return 1.0f / a; }
 // the compiler and the specialised and the generic numeric pass round identically.
 __device__ __forceinline__ double femx_mul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ float femx_mul(float a, float b) { return __fmul_rn(a, b); }
+#endif
 // rowinfo[i].y = #incidences | FEMX_ROW_SPEC | own position << 24 (femx_internal.h)
 #define FEMX_NP_MASK 0x3fffff
 #define FEMX_ROW_SPEC (1 << 23)
@@ -216,7 +218,8 @@ femx_coo(const int* __restrict__ conn, const real* __restrict__ X,
 // [32s, 32s+32), entry (row, it) at slice_ptr[s] + 32*it + row%32, so a warp
 // reads one contiguous 128-byte line per incidence.  Node ids come from the
 // tile's column list staged in shared memory, so connectivity is not re-read.
-static const char* const kFemxJitCsr = R"FEMX(
+static const char* const kFemxJitCsrRow = R"FEMX(
+#ifndef FEMX_HOST_EMU
 // predicated read-only global load: keeps the gathers of the software pipeline
 // branch-free so that they are issued before the current incidence is evaluated
 // (when the predicate is off the result is never used)
@@ -255,6 +258,7 @@ __device__ __forceinline__ int femx_ldg_pinned(const int* p) {
   asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
+#endif
 #if FEMX_UNIT_STRIDE
 #define FEMX_CS 1
 #else
@@ -292,6 +296,7 @@ __device__ __forceinline__ int femx_ldg_pinned(const int* p) {
 //   srow  the row's value segment (private to the thread), rstride = row length * ND
 // Tile mode passes shared-memory copies of codes and columns (staged by TMA), row-list mode reads
 // them straight from global memory; the arithmetic — and therefore every bit of the result — is the same.
+#ifndef FEMX_HOST_EMU
 __device__ __forceinline__ void femx_generic_row(const int2 r0, const int np, const int rstride, real* srow,
                                                  const unsigned* sc, const int* scol, const int* pelem,
                                                  const real* __restrict__ X, const real* __restrict__ Y,
@@ -420,6 +425,11 @@ __device__ __forceinline__ void femx_generic_row(const int2 r0, const int np, co
     for (int d = 0; d < ND; ++d) srow[c * rstride + ps + d] = dacc[c * ND + d];
 }
 
+#endif  // !FEMX_HOST_EMU
+)FEMX";
+
+// the tile / stencil-class kernel (appended to kFemxJitCsrRow)
+static const char* const kFemxJitCsr = R"FEMX(
 extern "C" __global__ void FEMX_BOUNDS
 femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
          const int* __restrict__ col_loc, const unsigned* __restrict__ sell_code,
@@ -601,6 +611,147 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
     if (threadIdx.x == 0 && mid > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 #endif
+}
+)FEMX";
+
+static const char* const kFemxJitLattice = R"FEMX(
+// ---- kernel ABI #2, lattice mode: every element evaluated ONCE per tile --------------------
+// (appended to kFemxJitCsrRow; macros FEMX_LT_* generated by femx_lattice.cpp.)
+// A CTA owns (FEMX_LT_TX-1) x (FEMX_LT_TY-1) node columns of a lattice mesh and marches through node planes
+// [k0, k1).  Thread (ix, iy) holds the column with lower-corner node (i, j): per plane it evaluates the cell
+// (i, j, kc) — its P elements, each ONCE — reduces them to one value per cell edge and one Jacobian sum per
+// corner, adds what the cell below left for the shared plane (register carry), and publishes the sums other
+// columns need ("fields") to shared memory.  After the barrier the thread gathers the values of row (i, j, kc):
+// each off-diagonal entry is the sum of the fields of the cells around its edge, the diagonal follows from the
+// zero row sum of the stiffness part.  Rows go to a shared-memory image and leave through one bulk store per
+// run of consecutive class rows.  Column ix = 0 / iy = 0 is the halo (cells only, no rows).  Rows outside the
+// stencil class (the mesh boundary) are taken by row-list CTAs with the generic incidence loop, as in the
+// stencil-class kernel.
+struct femx_lat {
+  int cnx, cny, cnz;  // cells per axis
+  int sy, sz;         // node strides (x stride 1)
+  int node0;          // node id of lattice node (0,0,0)
+  int klo, khi;       // node planes to produce: [klo, khi]
+  int ntx, nty;       // tiles per plane
+  int kc;             // node planes per CTA
+};
+#define LT_NT FEMX_TILE_NODES
+#define LT_F(SLOT) (lt_F + (SLOT) * LT_NT)
+#ifndef FEMX_HOST_EMU
+#define FEMX_TID ((int)threadIdx.x)
+#define FEMX_BID ((int)blockIdx.x)
+#define FEMX_LT_SYNC() __syncthreads()
+#define FEMX_LT_KERNEL extern "C" __global__ void __launch_bounds__(LT_NT, FEMX_LT_MINB)
+__device__ __forceinline__ void femx_lt_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void femx_lt_bulk_store(real* dst, const real* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst), "r"((unsigned)__cvta_generic_to_shared(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void femx_lt_bulk_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+#endif
+
+#define LT_LOAD_PLANE(K, A, B, C, D)                                                          \
+  {                                                                                           \
+    const i64 p_ = (i64)(nb + (K) * lat.sz) * FEMX_CS, q_ = p_ + (i64)lat.sy * FEMX_CS;       \
+    cx##A = __ldg(X + p_); cx##B = __ldg(X + p_ + FEMX_CS);                                   \
+    cx##C = __ldg(X + q_); cx##D = __ldg(X + q_ + FEMX_CS);                                   \
+    cy##A = __ldg(Y + p_); cy##B = __ldg(Y + p_ + FEMX_CS);                                   \
+    cy##C = __ldg(Y + q_); cy##D = __ldg(Y + q_ + FEMX_CS);                                   \
+    cz##A = __ldg(Z + p_); cz##B = __ldg(Z + p_ + FEMX_CS);                                   \
+    cz##C = __ldg(Z + q_); cz##D = __ldg(Z + q_ + FEMX_CS);                                   \
+  }
+
+FEMX_LT_KERNEL
+femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
+         const int* __restrict__ col_loc, const unsigned* __restrict__ sell_code,
+         const int* __restrict__ sell_elem, const real* __restrict__ X,
+         const real* __restrict__ Y, const real* __restrict__ Z, const i64 cs,
+         real* __restrict__ vals, const int n_rows, const int row_node0, const femx_lat lat,
+         const int* __restrict__ rowlist, const int n_list, const int seg) {
+#ifndef FEMX_HOST_EMU
+  extern __shared__ __align__(128) unsigned char femx_smem[];
+  // ---- the first CTAs take the rows OUTSIDE the class: compacted list, one thread each, generic loop
+  const int n_lb = (n_list + LT_NT - 1) / LT_NT;
+  if (FEMX_BID < n_lb) {
+    const int k_ = FEMX_BID * LT_NT + FEMX_TID;
+    if (k_ >= n_list) return;
+    const int row = __ldg(rowlist + k_);
+    const int2 r0 = __ldg(&rowinfo[row]);
+    const int rlen = __ldg(&rowinfo[row + 1].x) - r0.x;
+    const int np = r0.y & FEMX_NP_MASK;
+    real* srow = reinterpret_cast<real*>(femx_smem) + (size_t)FEMX_TID * seg;
+    if (np > 0) {
+      const int sp = __ldg(slice_ptr + (row >> 5)) + (row & 31);
+      femx_generic_row(r0, np, rlen * ND, srow, sell_code + sp, col_loc + r0.x, sell_elem + sp, X, Y, Z, cs);
+      real* dst = vals + (i64)r0.x * (ND * ND);
+      for (int j = 0; j < rlen * (ND * ND); ++j) dst[j] = srow[j];
+    }
+    return;
+  }
+  const int b = FEMX_BID - n_lb;
+#else
+  unsigned char* femx_smem = femx_emu_smem();
+  const int b = FEMX_BID;
+#endif
+  const int t = FEMX_TID;
+  const int tx = b % lat.ntx, ty = (b / lat.ntx) % lat.nty, tz = b / (lat.ntx * lat.nty);
+  const int ix = t % FEMX_LT_TX, iy = t / FEMX_LT_TX;
+  const int iu = tx * (FEMX_LT_TX - 1) + ix, ju = ty * (FEMX_LT_TY - 1) + iy;  // the column: lower-corner node (iu, ju)
+  // columns beyond the lattice (and the padding threads of the last warp) evaluate a clamped duplicate, unused
+  const int i = min(iu, lat.cnx - 1), j = min(ju, lat.cny - 1);
+  const bool own_col = ix >= 1 && iy >= 1 && iy < FEMX_LT_TY && iu < lat.cnx && ju < lat.cny;
+  const int k0 = lat.klo + tz * lat.kc, k1 = min(k0 + lat.kc, lat.khi + 1);
+  real* lt_F = reinterpret_cast<real*>(femx_smem);                                          // fields [FEMX_LT_NSLOT][LT_NT]
+  real* lt_img = lt_F + FEMX_LT_NSLOT * LT_NT;                                              // value image [LT_NT][RLEN] (+ phase slack)
+  unsigned char* lt_cls = reinterpret_cast<unsigned char*>(lt_img + LT_NT * FEMX_LT_RLEN + 4);  // class flag per thread
+  const int nb = lat.node0 + i + j * lat.sy;  // node id of the column at plane 0
+  // corner c = dx | dy << 1 | dz << 2 of the current cell: c0..c3 on node plane kc, c4..c7 on plane kc + 1
+  real cx0, cx1, cx2, cx3, cx4, cx5, cx6, cx7, cy0, cy1, cy2, cy3, cy4, cy5, cy6, cy7, cz0, cz1, cz2, cz3, cz4, cz5, cz6, cz7;
+  LT_LOAD_PLANE(k0 - 1, 0, 1, 2, 3)
+  LT_LOAD_PLANE(k0, 4, 5, 6, 7)
+  FEMX_LT_CARRY_DECL
+  for (int kc = k0 - 1; kc < k1; ++kc) {
+    const int par = kc & 1;
+    // metadata of row (i, j, kc): needed after the cell, issued before it
+    const int row = nb + kc * lat.sz - row_node0;
+    const bool rowok = own_col && kc >= k0 && row >= 0 && row < n_rows;
+    int2 r0 = make_int2(0, 0);
+    if (rowok) r0 = __ldg(&rowinfo[row]);
+    FEMX_LT_EDGES
+    // roll the planes; the loads of the next top plane fly during the cell's arithmetic
+    cx0 = cx4; cx1 = cx5; cx2 = cx6; cx3 = cx7; cy0 = cy4; cy1 = cy5; cy2 = cy6; cy3 = cy7;
+    cz0 = cz4; cz1 = cz5; cz2 = cz6; cz3 = cz7;
+    if (kc + 1 < k1) LT_LOAD_PLANE(kc + 2, 4, 5, 6, 7)
+    FEMX_LT_CELL
+    FEMX_LT_FIELDS
+    femx_lt_bulk_wait();  // the bulk stores of the previous plane have read the image
+    if (kc >= k0) { FEMX_LT_PUBLISH(par) } else { FEMX_LT_PUBLISH_UP(par) }
+    FEMX_LT_SYNC();
+    if (kc >= k0) {
+      const bool mine = rowok && (r0.y & FEMX_ROW_SPEC);
+      // the row's place in the image carries the 16-byte phase of its global address (aligned bulk stores);
+      // the phase is the same for all rows of a run of consecutive class rows
+      real* lt_row = lt_img + t * FEMX_LT_RLEN + ((r0.x - t * FEMX_LT_RLEN) & (FEMX_EPV - 1));
+      if (mine) { FEMX_LT_GATHER(par) }
+      lt_cls[t] = mine ? 1 : 0;
+      femx_lt_fence();
+      FEMX_LT_SYNC();
+      if (mine && (ix == 1 || !lt_cls[t - 1])) {  // first row of a run: one bulk store for the whole run
+        int len = 1;
+        while (ix + len < FEMX_LT_TX && lt_cls[t + len]) ++len;
+        const int n = len * FEMX_LT_RLEN;
+        real* dst = vals + (i64)r0.x;
+        const real* src = lt_row;
+        const int head = min(n, (FEMX_EPV - (int)(r0.x & (FEMX_EPV - 1))) & (FEMX_EPV - 1));
+        const int mid = (n - head) & ~(FEMX_EPV - 1);
+        if (mid > 0) femx_lt_bulk_store(dst + head, src + head, (unsigned)(mid * sizeof(real)));
+        for (int q = 0; q < head; ++q) dst[q] = src[q];  // ragged ends: < 16 bytes each
+        for (int q = head + mid; q < n; ++q) dst[q] = src[q];
+      }
+    }
+  }
+  femx_lt_bulk_wait();
 }
 )FEMX";
 

@@ -11,6 +11,7 @@
 //   6. column fill + per-incidence position codes (the element-slot → CSR-offset map)
 // The output is bit-identical to the reference's sorted std::set rows.
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <vector>
 
@@ -558,6 +559,136 @@ int detect_stencil_class(femx_ctx* ctx, femx_pattern* p, const int* d_pair_ptr, 
   return done(FEMX_OK);
 }
 
+
+// ------------------------------------------------------------------ lattice ---
+// Is the mesh a lattice (femx_internal.h: femx_lattice)?  Hypothesis from the first two cells, the extents
+// from the first place where translation invariance breaks, then every element is checked.
+struct lat_desc {
+  int P, nn, cnx, cny;
+  long long sy, sz;
+  int node0;
+  int off[32];  // node offset of vertex a of element t from the cell's lower corner
+};
+
+// smallest c in [1, n) with conn[c * stride] - conn[0] != c * step  (n if there is none)
+__global__ void lattice_first_break(const int* __restrict__ conn, long long n, long long stride, long long step,
+                                    int* __restrict__ out) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (c >= n) return;
+  if ((long long)conn[c * stride] - (long long)conn[0] != c * step) atomicMin(out, (int)c);
+}
+
+__global__ void lattice_verify(const int* __restrict__ conn, long long n_elems, lat_desc d, int* __restrict__ bad) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elems) return;
+  const long long c = e / d.P;
+  const int t = (int)(e - c * d.P);
+  const long long ci = c % d.cnx, cj = (c / d.cnx) % d.cny, ck = c / ((long long)d.cnx * d.cny);
+  const long long base = d.node0 + ci + cj * d.sy + ck * d.sz;
+  bool ok = true;
+  for (int a = 0; a < d.nn; ++a) ok = ok && (long long)conn[e * d.nn + a] == base + d.off[t * d.nn + a];
+  if (!ok) atomicAdd(bad, 1);
+}
+
+int detect_lattice(femx_ctx* ctx, femx_pattern* p, const int* d_conn, cudaStream_t st) {
+  p->lat = femx_lattice();
+  const int nn = p->nn, dim = nn - 1;
+  const int64_t ne = p->n_elems;
+  if (ne < 2 || ne * nn >= (1LL << 31)) return FEMX_OK;
+  int head[64];
+  const int nh = (int)std::min<int64_t>(ne * nn, 64);
+  int* d_tmp = nullptr;
+  int rc = tmp_alloc(ctx, &d_tmp, 2, st);
+  if (rc != FEMX_OK) return rc;
+  auto done = [&](int code) { cudaFreeAsync(d_tmp, st); return code; };
+#define LT_CUDA(call)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return done(femx_fail(ctx, FEMX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)));    \
+  } while (0)
+  LT_CUDA(cudaMemcpyAsync(head, d_conn, sizeof(int) * nh, cudaMemcpyDeviceToHost, st));
+  LT_CUDA(cudaStreamSynchronize(st));
+  // period: the smallest P such that cell 1 is cell 0 shifted by one node
+  int P = 0;
+  for (int q = 1; q <= 8 && 2 * q * nn <= nh && !P; ++q) {
+    bool ok = true;
+    for (int k = 0; k < q * nn; ++k) ok = ok && head[q * nn + k] - head[k] == 1;
+    if (ok) P = q;
+  }
+  if (!P || ne % P) return done(FEMX_OK);
+  // strides from the distinct node offsets of cell 0: {0, 1, sy, sy+1 [, sz, sz+1, sz+sy, sz+sy+1]}
+  int b0 = head[0];
+  for (int k = 1; k < P * nn; ++k) b0 = std::min(b0, head[k]);
+  std::vector<long long> u;
+  for (int k = 0; k < P * nn; ++k) u.push_back(head[k] - b0);
+  std::sort(u.begin(), u.end());
+  u.erase(std::unique(u.begin(), u.end()), u.end());
+  if ((int)u.size() != (1 << dim) || u[1] != 1 || u[3] != u[2] + 1 || u[2] < 3) return done(FEMX_OK);
+  const long long sy = u[2];
+  long long sz = 0;
+  if (dim == 3) {
+    sz = u[4];
+    if (u[5] != sz + 1 || u[6] != sz + sy || u[7] != sz + sy + 1) return done(FEMX_OK);
+  }
+  femx_lattice L;
+  L.dim = dim; L.P = P; L.node0 = b0; L.s[0] = 1; L.s[1] = sy; L.s[2] = sz;
+  lat_desc d = {};
+  d.P = P; d.nn = nn; d.sy = sy; d.sz = sz; d.node0 = b0;
+  for (int t = 0; t < P; ++t)
+    for (int a = 0; a < nn; ++a) {
+      const long long off = head[t * nn + a] - b0;
+      const int c = (int)(std::find(u.begin(), u.end(), off) - u.begin());
+      L.corner[t][a] = (unsigned char)c;   // u is sorted: index = dx | dy << 1 | dz << 2
+      d.off[t * nn + a] = (int)off;
+    }
+  // extents
+  const long long n_cells = ne / P;
+  int h_tmp[2] = {(int)std::min<long long>(n_cells, INT_MAX), 0};
+  LT_CUDA(cudaMemcpyAsync(d_tmp, h_tmp, sizeof h_tmp, cudaMemcpyHostToDevice, st));
+  lattice_first_break<<<nblocks(n_cells, 256), 256, 0, st>>>(d_conn, n_cells, (long long)P * nn, 1, d_tmp);
+  LT_CUDA(cudaMemcpyAsync(h_tmp, d_tmp, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LT_CUDA(cudaStreamSynchronize(st));
+  const long long cnx = h_tmp[0];
+  if (cnx < 2 || n_cells % cnx || cnx + 1 > sy) return done(FEMX_OK);
+  const long long n_lines = n_cells / cnx;
+  long long cny = n_lines, cnz = 1;
+  if (dim == 3) {
+    h_tmp[0] = (int)n_lines;
+    LT_CUDA(cudaMemcpyAsync(d_tmp, h_tmp, sizeof(int), cudaMemcpyHostToDevice, st));
+    lattice_first_break<<<nblocks(n_lines, 256), 256, 0, st>>>(d_conn, n_lines, cnx * P * nn, sy, d_tmp);
+    LT_CUDA(cudaMemcpyAsync(h_tmp, d_tmp, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LT_CUDA(cudaStreamSynchronize(st));
+    cny = h_tmp[0];
+    if (cny < 1 || n_lines % cny || cny * sy + cnx + 1 > sz) return done(FEMX_OK);
+    cnz = n_lines / cny;
+  }
+  L.cn[0] = (int)cnx; L.cn[1] = (int)cny; L.cn[2] = (int)cnz;
+  if (b0 + cnx + cny * sy + cnz * sz >= p->n_nodes) return done(FEMX_OK);
+  d.cnx = (int)cnx; d.cny = (int)cny;
+  LT_CUDA(cudaMemsetAsync(d_tmp + 1, 0, sizeof(int), st));
+  lattice_verify<<<nblocks(ne, 256), 256, 0, st>>>(d_conn, ne, d, d_tmp + 1);
+  LT_CUDA(cudaMemcpyAsync(h_tmp, d_tmp + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LT_CUDA(cudaStreamSynchronize(st));
+  LT_CUDA(cudaGetLastError());
+  if (h_tmp[0] != 0) return done(FEMX_OK);
+  // the class rows must be exactly the lattice-interior nodes among the owned rows (every one of them is then
+  // written by the lattice pass, every other row by the row list)
+  long long interior = 0;
+  for (long long k = 1; k < (dim == 3 ? cnz : 2); ++k)
+    for (long long j = 1; j < cny; ++j) {
+      const long long n0 = b0 + 1 + j * sy + (dim == 3 ? k * sz : 0), n1 = n0 + cnx - 1;  // nodes [n0, n1) of this line
+      const long long lo = std::max<long long>(n0, p->row_begin), hi = std::min<long long>(n1, p->row_end);
+      if (hi > lo) interior += hi - lo;
+    }
+  if (interior != p->spec_rows) return done(FEMX_OK);
+  L.ok = true;
+  p->lat = L;
+  p->lat_rows = interior;
+  return done(FEMX_OK);
+#undef LT_CUDA
+}
+
 }  // namespace
 
 extern "C" {
@@ -586,7 +717,7 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
   p->ctx = ctx; p->nn = nn; p->nd = nd; p->n_nodes = n_nodes; p->n_elems = n_elems;
   p->row_begin = row_begin; p->row_end = row_end; p->col_base = col_base;
   p->n_rows = row_end - row_begin;
-  p->tile_nodes = femx_tile_nodes_for(nd);
+  p->tile_nodes = femx_tile_nodes_for(nd, ctx->knobs);
   const int64_t nr = p->n_rows, total = n_elems * nn;
   int *d_cnt = nullptr, *d_pair_ptr = nullptr, *d_row_ptr = nullptr, *d_flags = nullptr;
   int* d_pair_elem = nullptr;       // CSR-style incidence lists (temporary)
@@ -711,8 +842,10 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
     tile_max<<<nblocks(ntiles, 128), 128, 0, st>>>(p->d_rowinfo, p->d_slice_ptr, (int)nr, p->tile_nodes, d_flags + 2);
   }
   // dominant stencil class (scalar problems; FEMX_SPEC=0 switches the detection off)
-  if (nd == 1 && nr > 0 && n_pairs > 0 && !(getenv("FEMX_SPEC") && atoi(getenv("FEMX_SPEC")) == 0))
+  if (nd == 1 && nr > 0 && n_pairs > 0 && ctx->knobs.spec != 0) {
     PB_TRY(detect_stencil_class(ctx, p, d_pair_ptr, d_pair_code, st));
+    if (p->spec_np > 0 && ctx->knobs.lattice != 0) PB_TRY(detect_lattice(ctx, p, d_conn, st));
+  }
   PB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
   PB_CUDA(cudaStreamSynchronize(st));
   PB_CUDA(cudaGetLastError());
@@ -757,6 +890,23 @@ int femx_pattern_stencil(const femx_pattern* p, int* n_incid, int* row_len, int*
     for (int k = 0; k < p->spec_np && k < cap; ++k) h_codes[k] = p->spec_codes[k];
   if (h_offsets)
     for (int k = 0; k < p->spec_rlen && k < cap; ++k) h_offsets[k] = p->spec_off[k];
+  return FEMX_OK;
+}
+
+int femx_pattern_lattice(const femx_pattern* p, int* n_per_cell, int64_t* h_cells, int64_t* h_strides, int64_t* node0,
+                         int32_t* h_corners) {
+  if (!p) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_pattern_lattice: pattern is NULL");
+  const femx_lattice& L = p->lat;
+  if (n_per_cell) *n_per_cell = L.ok ? L.P : 0;
+  if (!L.ok) return FEMX_OK;
+  for (int k = 0; k < 3; ++k) {
+    if (h_cells) h_cells[k] = L.cn[k];
+    if (h_strides) h_strides[k] = L.s[k];
+  }
+  if (node0) *node0 = L.node0;
+  if (h_corners)
+    for (int t = 0; t < L.P; ++t)
+      for (int a = 0; a < p->nn; ++a) h_corners[t * p->nn + a] = L.corner[t][a];
   return FEMX_OK;
 }
 

@@ -47,7 +47,8 @@ class _MeshView(C.Structure):
 
 # every symbol include/femx.h declares (tests check the library exports them all)
 SYMBOLS = [
-    "femx_ctx_create", "femx_ctx_destroy", "femx_last_error", "femx_version",
+    "femx_ctx_create", "femx_ctx_destroy", "femx_last_error", "femx_version", "femx_ctx_set_option",
+    "femx_pattern_lattice", "femx_form_cubin_lattice",
     "femx_form_compile", "femx_form_compile_offline", "femx_form_destroy", "femx_form_source",
     "femx_form_log", "femx_form_entry", "femx_form_prologue", "femx_form_cubin",
     "femx_mesh_rectangle", "femx_mesh_expand", "femx_mesh_box",
@@ -122,6 +123,10 @@ class Context:
     def check(self, st):
         if st:
             raise FemxError(st, lib().femx_last_error(self.h).decode())
+
+    def set_option(self, name, value):
+        """Tuning option (femx_ctx_set_option): "spec", "lattice", "lt_tx", ... — experiments and tests."""
+        self.check(lib().femx_ctx_set_option(self.h, name.encode(), int(value)))
 
     def close(self):
         if self.h:
@@ -297,6 +302,20 @@ class Form:
                                                   C.byref(p), C.byref(n)))
         return C.string_at(p.value, n.value)
 
+    def cubin_lattice(self, corners, stride_y, stride_z, offsets, self_pos):
+        """Element-once lattice pass for an explicit lattice cell (diagnostic; works offline).
+        Returns (cubin, info dict)."""
+        flat = [int(c) for t in corners for c in t]
+        carr = (C.c_int32 * len(flat))(*flat)
+        oarr = (C.c_int32 * len(offsets))(*[int(v) for v in offsets])
+        info = (C.c_int * 6)()
+        p = C.c_void_p()
+        n = C.c_size_t()
+        self._check(lib().femx_form_cubin_lattice(self.h, len(corners), carr, _i64(stride_y), _i64(stride_z),
+                                                  len(offsets), int(self_pos), oarr, C.byref(p), C.byref(n), info))
+        return C.string_at(p.value, n.value), dict(tx=info[0], ty=info[1], threads=info[2], nslot=info[3],
+                                                   smem=info[4], minb=info[5])
+
     def _tdtype(self):
         import torch
         return torch.float64 if self.dtype == F64 else torch.float32
@@ -370,6 +389,19 @@ class Pattern:
         self.ctx.check(lib().femx_pattern_stencil(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(r), codes, offs, 32))
         return dict(n_incid=a.value, row_len=b.value, self_pos=c.value, rows=r.value,
                     codes=[int(codes[k]) for k in range(a.value)], offsets=[int(offs[k]) for k in range(b.value)])
+
+    def lattice(self):
+        """Lattice structure found by the symbolic pass (femx_pattern_lattice), or None."""
+        P = C.c_int()
+        cells, strides = (C.c_int64 * 3)(), (C.c_int64 * 3)()
+        node0 = C.c_int64()
+        corners = (C.c_int32 * 32)()
+        self.ctx.check(lib().femx_pattern_lattice(self.h, C.byref(P), cells, strides, C.byref(node0), corners))
+        if P.value == 0:
+            return None
+        nn = len(self.stencil()["codes"]) and (4 if any(strides[k] for k in (2,)) else 3)
+        return dict(n_per_cell=P.value, cells=list(cells), strides=list(strides), node0=node0.value,
+                    corners=[[int(corners[t * nn + a]) for a in range(nn)] for t in range(P.value)])
 
     def csr(self, index_dtype="int32", stream=None):
         import torch

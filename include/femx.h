@@ -73,6 +73,13 @@ void femx_ctx_destroy(femx_ctx* ctx);
  * fea_symbolic_nvrtc_sparse.cpp:534-542).  ctx == NULL → last global error. */
 const char* femx_last_error(const femx_ctx* ctx);
 const char* femx_version(void);
+/* Tuning options of a context (experiments; the defaults are the measured configuration).  They are read
+ * from the environment (FEMX_<NAME>) once, when the context is created; this call changes one afterwards.
+ * No entry point reads the environment on a launch path.  name: "spec" (stencil-class pass on/off),
+ * "lattice" (element-once lattice pass on/off), "tile", "carveout", "lt_tx", "lt_ty", "lt_kc", ...
+ * (csrc/femx_core.cpp: kKnobs).  Options that shape generated code apply to forms compiled afterwards;
+ * spec / lattice / carveout / lt_* are looked at by every femx_assemble_csr call. */
+int femx_ctx_set_option(femx_ctx* ctx, const char* name, int value);
 
 /* -------------------------------------------------------------------- forms */
 
@@ -250,11 +257,33 @@ int femx_pattern_stencil(const femx_pattern* pat, int* n_incid, int* row_len, in
 int femx_form_cubin_stencil(femx_form* form, int n_incid, int row_len, int self_pos,
                             const uint32_t* h_codes, const void** cubin, size_t* size);
 
+/* Lattice structure of the mesh the pattern was built from (found and verified element by element by the
+ * symbolic pass): elements come in cells of *n_per_cell consecutive elements, cell c = ci + cells[0]*(cj +
+ * cells[1]*ck), each cell a translate of cell 0; vertex a of element c*P+t is lattice node (ci,cj,ck) +
+ * corner (bit 0 = dx, bit 1 = dy, bit 2 = dz) h_corners[t*nn + a]; node id = *node0 + i*strides[0] + j*strides[1] +
+ * k*strides[2].  This is what RectangleMesh::generate produces (fea_symbolic_nvrtc_sparse.cpp:170-216) and
+ * what femx_mesh_box produces in 3-D.  *n_per_cell = 0: no lattice (unstructured mesh, or no stencil class).
+ * On 3-D lattices femx_assemble_csr runs the element-once pass for symmetric built-in forms.
+ * h_cells / h_strides: 3 entries each; h_corners: 8*nn entries; any pointer may be NULL. */
+int femx_pattern_lattice(const femx_pattern* pat, int* n_per_cell, int64_t* h_cells, int64_t* h_strides,
+                         int64_t* node0, int32_t* h_corners);
+/* Diagnostic: NVRTC-compiles the element-once lattice pass for an explicitly given lattice cell (n_per_cell
+ * elements, h_corners as above), node strides and stencil class (row_len sorted column offsets h_offsets, own
+ * position self_pos); no device needed with a form from femx_form_compile_offline.  h_info (6 ints, may be NULL)
+ * receives tile threads x, y, threads per CTA, shared-memory field slots, shared-memory bytes, min blocks. */
+int femx_form_cubin_lattice(femx_form* form, int n_per_cell, const int32_t* h_corners, int64_t stride_y,
+                            int64_t stride_z, int row_len, int self_pos, const int32_t* h_offsets,
+                            const void** cubin, size_t* size, int* h_info);
+
 /* The numeric pass.  Replaces fea_kernel (ELL + global atomicAdd variant,
  * fea_symbolic_nvrtc_sparse2.cpp:475-547): d_values[k] is the sum of all element
  * contributions to CSR slot k, accumulated in ascending element order by the
  * one thread that owns the row — no atomics, bitwise reproducible.
- * d_values has nnz entries of the form's dtype and is fully overwritten. */
+ * d_values has nnz entries of the form's dtype and is fully overwritten; it must be 16-byte aligned
+ * (the tiles leave shared memory through cp.async.bulk stores), as must d_A/d_rowA/d_colA of
+ * femx_assemble_coo — FEMX_ERR_INVALID otherwise.
+ * Limits: rows of more than 127 node columns and more than 2^31 - 1 incidences / node-level nonzeros per
+ * device are rejected by femx_pattern_build (FEMX_ERR_UNSUPPORTED: shard the mesh); P1 simplices only. */
 int femx_assemble_csr(femx_form* form, const femx_pattern* pat,
                       const femx_mesh_view* mesh, void* d_values, void* stream);
 /* Load vector b[dof] = sum over incident elements of the integrated rhs entry, accumulated in
