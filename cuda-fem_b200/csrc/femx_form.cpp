@@ -709,6 +709,11 @@ int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, boo
       return femx_fail(f->ctx, FEMX_ERR_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
     std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--diag-suppress=550", "--diag-suppress=177",
                                      f->fmad ? "--fmad=true" : "--fmad=false"};
+    std::string regopt;
+    if (lat && plan->regs > 0) {
+      regopt = "--maxrregcount=" + std::to_string(plan->regs);
+      opts.push_back(regopt.c_str());
+    }
     r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
     size_t ls = 0;
     nvrtcGetProgramLogSize(prog, &ls);
@@ -1098,19 +1103,20 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   const size_t rs = form->dtype == FEMX_F32 ? 4 : 8;
   // (the row-list CTAs of that kernel keep one private value segment per thread in shared memory:
   //  patterns whose rows outside the class are very long stay on the generic kernel)
-  bool spec = pat->spec_np > 0 && pat->spec_rows * 2 >= pat->n_rows && form->nd == 1 && !expanded &&
-              (form->builtin != FEMX_FORM_CUSTOM || !form->fmad) &&
-              (size_t)pat->tile_nodes * pat->max_row_other * rs <= 64 * 1024 &&
-              form->spec_failed.count(pat->spec_key) == 0 && live.spec != 0;
+  const bool cls = pat->spec_np > 0 && form->nd == 1 && !expanded && (form->builtin != FEMX_FORM_CUSTOM || !form->fmad) &&
+                   live.spec != 0;
+  bool spec = cls && pat->spec_rows * 2 >= pat->n_rows && (size_t)pat->tile_nodes * pat->max_row_other * rs <= 64 * 1024 &&
+              form->spec_failed.count(pat->spec_key) == 0;
   const char* kname = expanded ? "csr_x" : (cs == 1 ? "csr" : "csr_s");
   // Lattice meshes (3-D, symmetric built-in forms): the element-once pass takes the class rows.
   femx_lattice_plan plan;
   bool lattice = false;
   std::string lat_key;
-  if (spec && pat->lat.ok && form->lt_ok && live.lattice != 0) {
+  if (cls && pat->lat.ok && form->lt_ok && live.lattice != 0) {
     std::string why;
     femx_knobs kk = form->knobs;
     kk.lt_tx = live.lt_tx; kk.lt_ty = live.lt_ty; kk.lt_kc = live.lt_kc; kk.lt_minb = live.lt_minb;
+    kk.lt_regs = live.lt_regs; kk.lt_pf = live.lt_pf;
     if (femx_lattice_plan_make(form, pat->lat, pat->spec_rlen, pat->spec_self, pat->spec_off, kk, &plan, &why)) {
       lat_key = femx_lattice_key(pat->lat, plan);
       if (!form->lt_failed.count(lat_key)) {

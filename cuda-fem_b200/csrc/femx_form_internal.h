@@ -31,6 +31,8 @@ struct femx_lattice_plan {
   int threads = 256;         // tx*ty rounded up to whole warps
   int kc = 32;               // node planes per CTA
   int minb = 1;              // __launch_bounds__ min blocks
+  int regs = 0;              // --maxrregcount (0: none)
+  int pf = 1;                // 1: the next plane is prefetched into L1 and loaded when needed; 0: loaded one cell ahead
   int nslot = 0;             // shared-memory field slots
   int rlen = 0, self = 0;    // the stencil class
   std::vector<int> pos;      // row position of offset (ox,oy,oz): index (oz+1)*9 + (oy+1)*3 + (ox+1), -1 = none

@@ -649,6 +649,7 @@ __device__ __forceinline__ void femx_lt_bulk_store(real* dst, const real* src, u
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void femx_lt_bulk_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void femx_lt_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #endif
 
 #define LT_LOAD_PLANE(K, A, B, C, D)                                                          \
@@ -660,6 +661,14 @@ __device__ __forceinline__ void femx_lt_bulk_wait() { asm volatile("cp.async.bul
     cy##C = __ldg(Y + q_); cy##D = __ldg(Y + q_ + FEMX_CS);                                   \
     cz##A = __ldg(Z + p_); cz##B = __ldg(Z + p_ + FEMX_CS);                                   \
     cz##C = __ldg(Z + q_); cz##D = __ldg(Z + q_ + FEMX_CS);                                   \
+  }
+
+#define LT_PREFETCH_PLANE(K)                                                                   \
+  {                                                                                           \
+    const i64 p_ = (i64)(nb + (K) * lat.sz) * FEMX_CS, q_ = p_ + (i64)lat.sy * FEMX_CS;       \
+    femx_lt_prefetch(X + p_); femx_lt_prefetch(X + p_ + FEMX_CS); femx_lt_prefetch(X + q_); femx_lt_prefetch(X + q_ + FEMX_CS); \
+    femx_lt_prefetch(Y + p_); femx_lt_prefetch(Y + p_ + FEMX_CS); femx_lt_prefetch(Y + q_); femx_lt_prefetch(Y + q_ + FEMX_CS); \
+    femx_lt_prefetch(Z + p_); femx_lt_prefetch(Z + p_ + FEMX_CS); femx_lt_prefetch(Z + q_); femx_lt_prefetch(Z + q_ + FEMX_CS); \
   }
 
 FEMX_LT_KERNEL
@@ -709,10 +718,19 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   // corner c = dx | dy << 1 | dz << 2 of the current cell: c0..c3 on node plane kc, c4..c7 on plane kc + 1
   real cx0, cx1, cx2, cx3, cx4, cx5, cx6, cx7, cy0, cy1, cy2, cy3, cy4, cy5, cy6, cy7, cz0, cz1, cz2, cz3, cz4, cz5, cz6, cz7;
   LT_LOAD_PLANE(k0 - 1, 0, 1, 2, 3)
+#if FEMX_LT_PF
+  LT_PREFETCH_PLANE(k0)
+#else
   LT_LOAD_PLANE(k0, 4, 5, 6, 7)
+#endif
   FEMX_LT_CARRY_DECL
   for (int kc = k0 - 1; kc < k1; ++kc) {
     const int par = kc & 1;
+#if FEMX_LT_PF
+    // the top plane was prefetched into L1 one cell ago; the plane after it is requested now
+    LT_LOAD_PLANE(kc + 1, 4, 5, 6, 7)
+    if (kc + 1 < k1) LT_PREFETCH_PLANE(kc + 2)
+#endif
     // metadata of row (i, j, kc): needed after the cell, issued before it
     const int row = nb + kc * lat.sz - row_node0;
     const bool rowok = own_col && kc >= k0 && row >= 0 && row < n_rows;
@@ -722,7 +740,9 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
     // roll the planes; the loads of the next top plane fly during the cell's arithmetic
     cx0 = cx4; cx1 = cx5; cx2 = cx6; cx3 = cx7; cy0 = cy4; cy1 = cy5; cy2 = cy6; cy3 = cy7;
     cz0 = cz4; cz1 = cz5; cz2 = cz6; cz3 = cz7;
+#if !FEMX_LT_PF
     if (kc + 1 < k1) LT_LOAD_PLANE(kc + 2, 4, 5, 6, 7)
+#endif
     FEMX_LT_CELL
     FEMX_LT_FIELDS
     femx_lt_bulk_wait();  // the bulk stores of the previous plane have read the image

@@ -129,6 +129,8 @@ bool femx_lattice_plan_make(const femx_form* f, const femx_lattice& L, int rlen,
   plan->threads = ((tx * ty + 31) / 32) * 32;
   plan->kc = K.lt_kc > 0 ? K.lt_kc : 32;
   plan->minb = K.lt_minb > 0 ? K.lt_minb : (plan->threads <= 256 ? 2 : 1);
+  plan->regs = K.lt_regs;
+  plan->pf = K.lt_pf;
   plan->ok = true;
   return true;
 }
@@ -140,7 +142,7 @@ std::string femx_lattice_key(const femx_lattice& L, const femx_lattice_plan& pla
     for (int a = 0; a <= L.dim; ++a) k << (int)L.corner[t][a];
   k << ".";
   for (int v : plan.pos) k << (v < 0 ? std::string("x") : std::to_string(v)) << ",";
-  k << plan.rlen << "." << plan.self << "." << plan.tx << "x" << plan.ty << "m" << plan.minb;
+  k << plan.rlen << "." << plan.self << "." << plan.tx << "x" << plan.ty << "m" << plan.minb << "r" << plan.regs << "p" << plan.pf;
   return k.str();
 }
 
@@ -368,7 +370,7 @@ std::string femx_lattice_defines(const femx_form* f, const femx_lattice& L, femx
     if (p != plan->self) o << " S_ += v" << p << ";";
   o << " lt_row[" << plan->self << "] = fma(" << lnum(f->lt_cj) << ", SJ, -S_); }\n";
   o << "#define FEMX_LT_TX " << plan->tx << "\n#define FEMX_LT_TY " << plan->ty << "\n#define FEMX_LT_NSLOT " << plan->nslot
-    << "\n#define FEMX_LT_RLEN " << plan->rlen << "\n#define FEMX_LT_MINB " << plan->minb << "\n#define FEMX_LATTICE 1\n";
+    << "\n#define FEMX_LT_RLEN " << plan->rlen << "\n#define FEMX_LT_MINB " << plan->minb << "\n#define FEMX_LT_PF " << plan->pf << "\n#define FEMX_LATTICE 1\n";
   // bytes of dynamic shared memory: fields | value image (+ alignment slack) | class flags
   const size_t rs = f->dtype == FEMX_F32 ? 4 : 8;
   plan->smem = ((size_t)plan->nslot * plan->threads + (size_t)plan->threads * plan->rlen + 4) * rs + plan->threads + 16;

@@ -366,6 +366,7 @@ class Pattern:
     def __init__(self, ctx, mesh, nd=1, row_begin=0, row_end=None, col_base=0, stream=None):
         self.ctx = ctx
         self.nd = nd
+        self.nn = mesh.nn
         row_end = mesh.n_nodes if row_end is None else row_end
         self.h = C.c_void_p()
         ctx.check(lib().femx_pattern_build(ctx.h, mesh.nn, nd, _i64(mesh.n_nodes), _i64(mesh.n_elems),
@@ -399,7 +400,7 @@ class Pattern:
         self.ctx.check(lib().femx_pattern_lattice(self.h, C.byref(P), cells, strides, C.byref(node0), corners))
         if P.value == 0:
             return None
-        nn = len(self.stencil()["codes"]) and (4 if any(strides[k] for k in (2,)) else 3)
+        nn = self.nn
         return dict(n_per_cell=P.value, cells=list(cells), strides=list(strides), node0=node0.value,
                     corners=[[int(corners[t * nn + a]) for a in range(nn)] for t in range(P.value)])
 

@@ -50,6 +50,7 @@ static std::barrier<>* emu_bar = nullptr;
 static inline unsigned char* femx_emu_smem() { return emu_smem; }
 static inline void femx_lt_fence() {}
 static inline void femx_lt_bulk_wait() {}
+static inline void femx_lt_prefetch(const void*) {}
 '''
 
 HARNESS_POST = r'''

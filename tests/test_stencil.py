@@ -121,19 +121,20 @@ def test_no_class_on_unstructured_or_vector_patterns(ctx):
 
 
 def _both_paths(ctx, form, pat, mesh):
-    """assemble_csr with the specialised body and with FEMX_SPEC=0 (generic loop for every row)."""
+    """assemble_csr with the specialised body and with the stencil-class pass switched off (generic loop for
+    every row).  The element-once lattice pass (tests/test_lattice.py) is switched off for both: it is a
+    different summation order, equal to these to rounding, not to the bit."""
     import torch
-    old = os.environ.pop("FEMX_SPEC", None)
+    ctx.set_option("lattice", 0)
     try:
         v_spec = form.assemble_csr(pat, mesh)
         n_variants = form.source.count("#define FEMX_SPEC 1")
-        os.environ["FEMX_SPEC"] = "0"
+        ctx.set_option("spec", 0)
         v_gen = form.assemble_csr(pat, mesh)
         assert "#define FEMX_SPEC 0" in form.source
     finally:
-        os.environ.pop("FEMX_SPEC", None)
-        if old is not None:
-            os.environ["FEMX_SPEC"] = old
+        ctx.set_option("spec", 1)
+        ctx.set_option("lattice", 1)
     torch.cuda.synchronize()
     assert n_variants == 1, "the specialised kernel was not the one launched"
     return v_spec, v_gen
@@ -201,12 +202,11 @@ def test_specialised_pass_partial_and_mixed_tiles(ctx):
         mesh = ctx.rectangle_mesh(0, 1, 0, 2, nR, nC)
         pat = femx.Pattern(ctx, mesh)
         form = femx.Form(ctx, 2, femx.POISSON_MASS)
-        old = os.environ.pop("FEMX_SPEC", None)
         v1 = form.assemble_csr(pat, mesh)
-        os.environ["FEMX_SPEC"] = "0"
-        v0 = form.assemble_csr(pat, mesh)
-        os.environ.pop("FEMX_SPEC")
-        if old is not None:
-            os.environ["FEMX_SPEC"] = old
+        ctx.set_option("spec", 0)
+        try:
+            v0 = form.assemble_csr(pat, mesh)
+        finally:
+            ctx.set_option("spec", 1)
         assert torch.equal(v0, v1), (nR, nC)
         form.close(); pat.close()

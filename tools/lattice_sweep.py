@@ -1,0 +1,80 @@
+"""Times the numeric pass of a 3-D workload for a list of lattice-pass configurations (one process, one
+pattern).  python tools/lattice_sweep.py [n=256] [steps=20]  — prints one line per configuration."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "cuda-fem_b200")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+import femx  # noqa: E402
+
+CONFIGS = [
+    # tx, ty, minb, kc, pf, regs, rcp3
+    dict(lattice=0),
+    dict(),
+    dict(lt_pf=0),
+    dict(lt_tx=16, lt_ty=16, lt_minb=2),
+    dict(lt_tx=16, lt_ty=16, lt_minb=2, lt_pf=0),
+    dict(lt_tx=16, lt_ty=16, lt_minb=1),
+    dict(lt_tx=18, lt_ty=16, lt_minb=1),
+    dict(lt_tx=18, lt_ty=16, lt_minb=2),
+    dict(lt_tx=12, lt_ty=16, lt_minb=2),
+    dict(lt_tx=10, lt_ty=16, lt_minb=2),
+    dict(lt_tx=8, lt_ty=16, lt_minb=3),
+    dict(lt_tx=24, lt_ty=16, lt_minb=1),
+    dict(lt_tx=32, lt_ty=16, lt_minb=1),
+    dict(lt_tx=16, lt_ty=16, lt_minb=2, lt_kc=16),
+    dict(lt_tx=16, lt_ty=16, lt_minb=2, lt_kc=64),
+    dict(lt_tx=16, lt_ty=16, lt_minb=2, lt_kc=255),
+    dict(lt_tx=12, lt_ty=16, lt_minb=2, lt_kc=64),
+    dict(lt_tx=52, lt_ty=6, lt_minb=1),
+    dict(lt_tx=16, lt_ty=16, lt_minb=2, carveout=100),
+    dict(lt_tx=12, lt_ty=16, lt_minb=2, carveout=100),
+]
+DEFAULTS = dict(lattice=1, lt_tx=0, lt_ty=0, lt_minb=0, lt_kc=0, lt_pf=1, lt_regs=0, carveout=-1)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    ctx = femx.Context(0)
+    mesh = ctx.box_mesh(n, n, n)
+    pat = femx.Pattern(ctx, mesh)
+    b_alg = mesh.n_elems * 16 + mesh.n_nodes * 24 + pat.nnz * 8
+    print(json.dumps(dict(n=n, elems=mesh.n_elems, nnz=pat.nnz, lattice=pat.lattice() is not None)), flush=True)
+    ref = None
+    for cfg in CONFIGS:
+        opts = dict(DEFAULTS)
+        opts.update(cfg)
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        form = femx.Form(ctx, 3, femx.POISSON_MASS)
+        vals = torch.empty(pat.nnz, dtype=torch.float64, device="cuda")
+        try:
+            for _ in range(3):
+                form.assemble_csr(pat, mesh, vals)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                form.assemble_csr(pat, mesh, vals)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            if ref is None:
+                ref = vals.clone()
+                err = 0.0
+            else:
+                err = float(torch.linalg.norm(vals - ref) / torch.linalg.norm(ref))
+            print(json.dumps(dict(cfg=cfg, ms=round(ms, 4), frac=round(b_alg / (ms * 1e-3) / 6.544e12, 4), relerr_vs_first=err)), flush=True)
+        except Exception as e:  # a configuration that does not fit must not stop the sweep
+            print(json.dumps(dict(cfg=cfg, error=str(e)[:200])), flush=True)
+        form.close()
+    pat.close(); ctx.close()
+
+
+if __name__ == "__main__":
+    main()
