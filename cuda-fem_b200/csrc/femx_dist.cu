@@ -1,0 +1,521 @@
+// Multi-GPU layer behind the C ABI (BASELINE configs 3-5): one femx_dist per rank
+// (one process per GPU), NCCL over NVLink for the ONLY two exchanges the path has —
+//   * the halo of the SpMV operand (grouped ncclSend/ncclRecv with the two slab neighbours), and
+//   * one fused 2-double all-reduce per CG iteration (Chronopoulos-Gear single-reduction CG) —
+// assembly itself needs none (owned rows + ghost elements).  The SpMV of the rows that read no ghost
+// column runs on the compute stream while the halo travels on a second stream; one CG iteration is
+// captured in a CUDA graph and replayed.  No reference counterpart (the reference is single-GPU:
+// job.pbs:4,24 launches one rank).
+//
+// NCCL is resolved at run time (dlopen "libnccl.so.2": the copy already mapped into the process — torch's —
+// or the system's), so libfemx.so loads on a box without NCCL and never brings a second copy in.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "femx_internal.h"
+
+int femx_spmv_range(const femx_pattern* p, int dtype, const void* d_values, const void* d_x, int64_t x_base, void* d_y,
+                    int64_t row_lo, int64_t row_hi, void* stream);
+
+namespace {
+
+struct nccl_api {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+  std::string err;
+};
+
+const nccl_api* get_nccl() {
+  static nccl_api api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { api.err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return; }
+    struct { const char* name; void** slot; } syms[] = {
+        {"ncclGetUniqueId", (void**)&api.GetUniqueId}, {"ncclCommInitRank", (void**)&api.CommInitRank},
+        {"ncclCommDestroy", (void**)&api.CommDestroy}, {"ncclGroupStart", (void**)&api.GroupStart},
+        {"ncclGroupEnd", (void**)&api.GroupEnd},       {"ncclSend", (void**)&api.Send},
+        {"ncclRecv", (void**)&api.Recv},               {"ncclAllReduce", (void**)&api.AllReduce},
+        {"ncclGetErrorString", (void**)&api.GetErrorString},
+    };
+    for (auto& s : syms) {
+      *s.slot = dlsym(h, s.name);
+      if (!*s.slot) { api.err = std::string("NCCL symbol missing: ") + s.name; return; }
+    }
+    api.ok = true;
+  });
+  return &api;
+}
+
+}  // namespace
+
+struct femx_dist {
+  femx_ctx* ctx = nullptr;
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  cudaStream_t s_comm = nullptr;   // the halo travels here while interior rows are multiplied on the caller's stream
+  cudaEvent_t e_ready = nullptr, e_halo = nullptr;
+};
+
+struct femx_dist_op {
+  femx_dist* d = nullptr;
+  const femx_pattern* pat = nullptr;
+  int dtype = FEMX_F64;
+  const void* vals = nullptr;
+  int64_t n_owned = 0;               // dof rows owned
+  int64_t ghost_lo = 0, ghost_hi = 0;  // operand entries below / above the owned range (local layout [lo | owned | hi])
+  int64_t send_lo = 0, send_hi = 0;    // leading / trailing owned entries the neighbours need
+  int64_t int_lo = 0, int_hi = 0;      // node rows [int_lo, int_hi) read no ghost column
+  void* x_ext = nullptr;               // operand with ghost zones (SpMV entry point)
+  // CG work vectors: r and w,p,s,x; r lives inside an extended buffer (it is the SpMV operand)
+  void *r_ext = nullptr, *w = nullptr, *p = nullptr, *s = nullptr;
+  double* d_sc = nullptr;     // [0] gamma [1] delta [2] gamma_old [3] alpha_old [4] alpha [5] beta
+  double* d_hist = nullptr;   // residual history (gamma per iteration)
+  int hist_cap = 0;
+  int* d_it = nullptr;
+  double* d_part = nullptr;   // partial sums of the dot products (private: no race with femx_dot2 users)
+  cudaGraphExec_t graph = nullptr;
+  const void* graph_x = nullptr;
+  int use_graph = 1;
+};
+
+namespace {
+
+#define ND_OK(d, call)                                                                                   \
+  do {                                                                                                   \
+    ncclResult_t r__ = (call);                                                                           \
+    if (r__ != ncclSuccess)                                                                              \
+      return femx_fail((d)->ctx, FEMX_ERR_CUDA, "%s failed: %s", #call, get_nccl()->GetErrorString(r__)); \
+  } while (0)
+
+size_t esize(int dtype) { return dtype == FEMX_F64 ? 8 : 4; }
+ncclDataType_t ntype(int dtype) { return dtype == FEMX_F64 ? ncclDouble : ncclFloat; }
+
+// rows that read a ghost column: the sorted column list starts below row_begin or ends at / above row_end
+__global__ void interior_range_k(const int2* __restrict__ rowinfo, const int* __restrict__ col, int n_rows, int row_begin,
+                                 int row_end, int* __restrict__ out) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int lo = rowinfo[r].x, hi = rowinfo[r + 1].x;
+  if (hi <= lo) return;
+  if (col[lo] < row_begin) atomicMax(out, r + 1);   // interior starts after the last such row
+  if (col[hi - 1] >= row_end) atomicMin(out + 1, r); // and ends at the first of these
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) dot2_part_k(int64_t n, const T* __restrict__ a, const T* __restrict__ b,
+                                                   const T* __restrict__ c, double* __restrict__ part) {
+  // part[blk] = sum a*a, part[1024 + blk] = sum b*c   (fixed grid, fixed tree: deterministic)
+  double s0 = 0.0, s1 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double av = (double)a[i];
+    s0 += av * av;
+    s1 += (double)b[i] * (double)c[i];
+  }
+  __shared__ double sh0[256], sh1[256];
+  sh0[threadIdx.x] = s0; sh1[threadIdx.x] = s1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh0[threadIdx.x] += sh0[threadIdx.x + o]; sh1[threadIdx.x] += sh1[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { part[blockIdx.x] = sh0[0]; part[FEMX_DOT_BLOCKS + blockIdx.x] = sh1[0]; }
+}
+
+__global__ void __launch_bounds__(256) dot2_fin_k(const double* __restrict__ part, int nblocks, double* __restrict__ out) {
+  __shared__ double sh0[256], sh1[256];
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) { s0 += part[i]; s1 += part[FEMX_DOT_BLOCKS + i]; }
+  sh0[threadIdx.x] = s0; sh1[threadIdx.x] = s1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh0[threadIdx.x] += sh0[threadIdx.x + o]; sh1[threadIdx.x] += sh1[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = sh0[0]; out[1] = sh1[0]; }
+}
+
+// Chronopoulos-Gear recurrences from the reduced gamma = (r,r), delta = (w,r); records gamma
+__global__ void cg_scalars_k(double* __restrict__ sc, double* __restrict__ hist, int* __restrict__ it) {
+  const int k = *it;
+  const double gamma = sc[0], delta = sc[1];
+  double beta = 0.0, alpha;
+  if (k == 0) {
+    alpha = gamma / delta;
+  } else {
+    beta = gamma / sc[2];
+    alpha = gamma / (delta - beta * gamma / sc[3]);
+  }
+  hist[k] = gamma;
+  sc[2] = gamma; sc[3] = alpha; sc[4] = alpha; sc[5] = beta;
+  *it = k + 1;
+}
+
+__global__ void cg_final_k(const double* __restrict__ sc, double* __restrict__ hist, const int* __restrict__ it) { hist[*it] = sc[0]; }
+
+// p = r + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s
+template <class T>
+__global__ void cg_update_k(int64_t n, const double* __restrict__ sc, T* __restrict__ r, const T* __restrict__ w,
+                            T* __restrict__ p, T* __restrict__ s, T* __restrict__ x) {
+  const double alpha = sc[4], beta = sc[5];
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double pn = (double)r[i] + beta * (double)p[i];
+  const double sn = (double)w[i] + beta * (double)s[i];
+  p[i] = (T)pn;
+  s[i] = (T)sn;
+  x[i] = (T)((double)x[i] + alpha * pn);
+  r[i] = (T)((double)r[i] - alpha * sn);
+}
+
+inline unsigned nb256(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+// ghost zones of `ext` (layout [ghost_lo | owned | ghost_hi]) from the neighbours, on the comm stream
+int halo_exchange(femx_dist_op* op, void* ext) {
+  femx_dist* d = op->d;
+  const nccl_api* nc = get_nccl();
+  const size_t es = esize(op->dtype);
+  char* base = (char*)ext;
+  char* own = base + op->ghost_lo * es;
+  ND_OK(d, nc->GroupStart());
+  if (op->ghost_lo > 0 && d->rank > 0) {
+    ND_OK(d, nc->Send(own, (size_t)op->send_lo, ntype(op->dtype), d->rank - 1, d->comm, d->s_comm));
+    ND_OK(d, nc->Recv(base, (size_t)op->ghost_lo, ntype(op->dtype), d->rank - 1, d->comm, d->s_comm));
+  }
+  if (op->ghost_hi > 0 && d->rank < d->world - 1) {
+    ND_OK(d, nc->Send(own + (op->n_owned - op->send_hi) * es, (size_t)op->send_hi, ntype(op->dtype), d->rank + 1, d->comm, d->s_comm));
+    ND_OK(d, nc->Recv(own + op->n_owned * es, (size_t)op->ghost_hi, ntype(op->dtype), d->rank + 1, d->comm, d->s_comm));
+  }
+  ND_OK(d, nc->GroupEnd());
+  return FEMX_OK;
+}
+
+// y = A[owned rows] ext, the halo of `ext` exchanged on the way: interior rows overlap the exchange
+int spmv_overlapped(femx_dist_op* op, void* ext, void* y, cudaStream_t st) {
+  femx_dist* d = op->d;
+  const femx_pattern* p = op->pat;
+  const int64_t xb = (int64_t)p->col_base * p->nd;  // operand index = global dof - col_base*nd
+  const bool comm = d->world > 1 && (op->ghost_lo > 0 || op->ghost_hi > 0);
+  if (comm) {
+    FEMX_CUDA_OK(d->ctx, cudaEventRecord(d->e_ready, st));          // the owned part of ext is final
+    FEMX_CUDA_OK(d->ctx, cudaStreamWaitEvent(d->s_comm, d->e_ready, 0));
+    int rc = halo_exchange(op, ext);
+    if (rc != FEMX_OK) return rc;
+    FEMX_CUDA_OK(d->ctx, cudaEventRecord(d->e_halo, d->s_comm));
+  }
+  int rc = FEMX_OK;
+  if (op->int_hi > op->int_lo) rc = femx_spmv_range(p, op->dtype, op->vals, ext, xb, y, op->int_lo, op->int_hi, st);
+  if (rc != FEMX_OK) return rc;
+  if (comm) FEMX_CUDA_OK(d->ctx, cudaStreamWaitEvent(st, d->e_halo, 0));
+  if (op->int_lo > 0) rc = femx_spmv_range(p, op->dtype, op->vals, ext, xb, y, 0, op->int_lo, st);
+  if (rc == FEMX_OK && op->int_hi < p->n_rows) rc = femx_spmv_range(p, op->dtype, op->vals, ext, xb, y, op->int_hi, p->n_rows, st);
+  return rc;
+}
+
+int reduce2(femx_dist_op* op, const void* r, const void* w, cudaStream_t st) {
+  femx_dist* d = op->d;
+  const int64_t n = op->n_owned;
+  const int blocks = (int)std::min<int64_t>(FEMX_DOT_BLOCKS, std::max<int64_t>(1, (n + 255) / 256));
+  if (op->dtype == FEMX_F64)
+    dot2_part_k<double><<<blocks, 256, 0, st>>>(n, (const double*)r, (const double*)w, (const double*)r, op->d_part);
+  else
+    dot2_part_k<float><<<blocks, 256, 0, st>>>(n, (const float*)r, (const float*)w, (const float*)r, op->d_part);
+  dot2_fin_k<<<1, 256, 0, st>>>(op->d_part, blocks, op->d_sc);
+  FEMX_CUDA_OK(d->ctx, cudaGetLastError());
+  if (d->world > 1) ND_OK(d, get_nccl()->AllReduce(op->d_sc, op->d_sc, 2, ncclDouble, ncclSum, d->comm, st));  // ONE per iteration
+  return FEMX_OK;
+}
+
+int cg_iteration(femx_dist_op* op, void* x, cudaStream_t st) {
+  femx_dist* d = op->d;
+  const int64_t n = op->n_owned;
+  const size_t es = esize(op->dtype);
+  void* r = (char*)op->r_ext + op->ghost_lo * es;
+  cg_scalars_k<<<1, 1, 0, st>>>(op->d_sc, op->d_hist, op->d_it);
+  if (op->dtype == FEMX_F64)
+    cg_update_k<double><<<nb256(n), 256, 0, st>>>(n, op->d_sc, (double*)r, (const double*)op->w, (double*)op->p, (double*)op->s, (double*)x);
+  else
+    cg_update_k<float><<<nb256(n), 256, 0, st>>>(n, op->d_sc, (float*)r, (const float*)op->w, (float*)op->p, (float*)op->s, (float*)x);
+  FEMX_CUDA_OK(d->ctx, cudaGetLastError());
+  int rc = spmv_overlapped(op, op->r_ext, op->w, st);
+  if (rc != FEMX_OK) return rc;
+  return reduce2(op, r, op->w, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int femx_dist_unique_id(void* h_id) {
+  if (!h_id) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_dist_unique_id: NULL argument");
+  const nccl_api* nc = get_nccl();
+  if (!nc->ok) return femx_fail(nullptr, FEMX_ERR_UNSUPPORTED, "femx_dist_unique_id: %s", nc->err.c_str());
+  static_assert(sizeof(ncclUniqueId) == FEMX_DIST_ID_BYTES, "ncclUniqueId size");
+  ncclResult_t r = nc->GetUniqueId((ncclUniqueId*)h_id);
+  if (r != ncclSuccess) return femx_fail(nullptr, FEMX_ERR_CUDA, "ncclGetUniqueId: %s", nc->GetErrorString(r));
+  return FEMX_OK;
+}
+
+int femx_dist_create(femx_ctx* ctx, int rank, int world, const void* h_id, femx_dist** out) {
+  if (!ctx || !out) return femx_fail(ctx, FEMX_ERR_INVALID, "femx_dist_create: NULL argument");
+  *out = nullptr;
+  if (world < 1 || rank < 0 || rank >= world) return femx_fail(ctx, FEMX_ERR_INVALID, "femx_dist_create: rank %d of %d", rank, world);
+  FEMX_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  femx_dist* d = new femx_dist();
+  d->ctx = ctx; d->rank = rank; d->world = world;
+  if (world > 1) {
+    const nccl_api* nc = get_nccl();
+    if (!nc->ok || !h_id) {
+      delete d;
+      return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_dist_create: %s", !h_id ? "unique id is NULL" : nc->err.c_str());
+    }
+    ncclUniqueId id;
+    memcpy(&id, h_id, sizeof id);
+    ncclResult_t r = nc->CommInitRank(&d->comm, world, id, rank);
+    if (r != ncclSuccess) {
+      delete d;
+      return femx_fail(ctx, FEMX_ERR_CUDA, "ncclCommInitRank: %s", nc->GetErrorString(r));
+    }
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&d->s_comm, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->e_ready, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->e_halo, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    femx_dist_destroy(d);
+    return femx_fail(ctx, FEMX_ERR_CUDA, "femx_dist_create: %s", cudaGetErrorString(e));
+  }
+  *out = d;
+  return FEMX_OK;
+}
+
+void femx_dist_destroy(femx_dist* d) {
+  if (!d) return;
+  if (d->comm) get_nccl()->CommDestroy(d->comm);
+  if (d->s_comm) cudaStreamDestroy(d->s_comm);
+  if (d->e_ready) cudaEventDestroy(d->e_ready);
+  if (d->e_halo) cudaEventDestroy(d->e_halo);
+  delete d;
+}
+
+int femx_dist_slab(int64_t n_planes, int world, int rank, int64_t* r0, int64_t* r1, int64_t* lo, int64_t* hi) {
+  if (world < 1 || rank < 0 || rank >= world || n_planes < world)
+    return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_dist_slab: cannot split %lld node planes over %d ranks (rank %d)",
+                     (long long)n_planes, world, rank);
+  const int64_t a = (rank * n_planes) / world, b = ((rank + 1) * n_planes) / world;
+  if (r0) *r0 = a;
+  if (r1) *r1 = b;
+  if (lo) *lo = std::max<int64_t>(a - 1, 0);
+  if (hi) *hi = std::min<int64_t>(b, n_planes - 1);
+  return FEMX_OK;
+}
+
+int femx_dist_allreduce(femx_dist* d, double* d_buf, int n, int op_max, void* stream) {
+  if (!d || !d_buf) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_dist_allreduce: NULL argument");
+  if (d->world == 1) return FEMX_OK;
+  ND_OK(d, get_nccl()->AllReduce(d_buf, d_buf, (size_t)n, ncclDouble, op_max ? ncclMax : ncclSum, d->comm, (cudaStream_t)stream));
+  return FEMX_OK;
+}
+
+int femx_dist_op_create(femx_dist* d, const femx_pattern* pat, int dtype, const void* d_values, femx_dist_op** out) {
+  if (!d || !pat || !d_values || !out) return femx_fail(d ? d->ctx : nullptr, FEMX_ERR_INVALID, "femx_dist_op_create: NULL argument");
+  *out = nullptr;
+  femx_ctx* ctx = d->ctx;
+  if (pat->ctx != ctx) return femx_fail(ctx, FEMX_ERR_INVALID, "femx_dist_op_create: pattern belongs to another context");
+  FEMX_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  femx_dist_op* op = new femx_dist_op();
+  op->d = d; op->pat = pat; op->dtype = dtype; op->vals = d_values;
+  const int nd = pat->nd;
+  op->n_owned = pat->n_rows * nd;
+  op->ghost_lo = pat->row_begin * nd;
+  op->ghost_hi = (pat->n_nodes - pat->row_end) * nd;
+  op->use_graph = ctx->knobs.dist_graph;
+  const size_t es = esize(dtype);
+  const int64_t n_ext = op->ghost_lo + op->n_owned + op->ghost_hi;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes ? bytes : 8); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes ? bytes : 8); } };
+  alloc(&op->x_ext, n_ext * es);
+  alloc(&op->r_ext, n_ext * es);
+  alloc(&op->w, op->n_owned * es);
+  alloc(&op->p, op->n_owned * es);
+  alloc(&op->s, op->n_owned * es);
+  alloc((void**)&op->d_sc, 8 * sizeof(double));
+  alloc((void**)&op->d_it, 4 * sizeof(int));
+  alloc((void**)&op->d_part, 2 * FEMX_DOT_BLOCKS * sizeof(double));
+  if (e != cudaSuccess) {
+    femx_dist_op_destroy(op);
+    return femx_fail(ctx, FEMX_ERR_NOMEM, "femx_dist_op_create: %s", cudaGetErrorString(e));
+  }
+  // rows that read no ghost column: [int_lo, int_hi)
+  {
+    int h[2] = {0, (int)pat->n_rows};
+    cudaMemcpy(op->d_it + 2, h, sizeof h, cudaMemcpyHostToDevice);
+    if (pat->n_rows > 0)
+      interior_range_k<<<nb256(pat->n_rows), 256>>>(pat->d_rowinfo, pat->d_col_idx, (int)pat->n_rows, (int)pat->row_begin,
+                                                    (int)pat->row_end, op->d_it + 2);
+    e = cudaMemcpy(h, op->d_it + 2, sizeof h, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+      femx_dist_op_destroy(op);
+      return femx_fail(ctx, FEMX_ERR_CUDA, "femx_dist_op_create: %s", cudaGetErrorString(e));
+    }
+    op->int_lo = h[0]; op->int_hi = std::max(h[0], h[1]);
+  }
+  // what the neighbours need from this rank: their ghost zone sizes (one int64 each way, through NCCL)
+  op->send_lo = op->send_hi = 0;
+  if (d->world > 1) {
+    long long* d_cnt = nullptr;
+    e = cudaMalloc((void**)&d_cnt, 4 * sizeof(long long));
+    long long h[4] = {op->ghost_lo, op->ghost_hi, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(d_cnt, h, sizeof h, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { femx_dist_op_destroy(op); return femx_fail(ctx, FEMX_ERR_CUDA, "femx_dist_op_create: %s", cudaGetErrorString(e)); }
+    const nccl_api* nc = get_nccl();
+    ncclResult_t r = nc->GroupStart();
+    if (d->rank > 0) {  // lower neighbour: tell it my ghost_lo (= what it must send up), learn its ghost_hi
+      if (r == ncclSuccess) r = nc->Send(d_cnt + 0, 1, ncclInt64, d->rank - 1, d->comm, d->s_comm);
+      if (r == ncclSuccess) r = nc->Recv(d_cnt + 2, 1, ncclInt64, d->rank - 1, d->comm, d->s_comm);
+    }
+    if (d->rank < d->world - 1) {
+      if (r == ncclSuccess) r = nc->Send(d_cnt + 1, 1, ncclInt64, d->rank + 1, d->comm, d->s_comm);
+      if (r == ncclSuccess) r = nc->Recv(d_cnt + 3, 1, ncclInt64, d->rank + 1, d->comm, d->s_comm);
+    }
+    if (r == ncclSuccess) r = nc->GroupEnd();
+    if (r == ncclSuccess) {
+      e = cudaStreamSynchronize(d->s_comm);
+      if (e == cudaSuccess) e = cudaMemcpy(h, d_cnt, sizeof h, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_cnt);
+    if (r != ncclSuccess || e != cudaSuccess) {
+      femx_dist_op_destroy(op);
+      return femx_fail(ctx, FEMX_ERR_CUDA, "femx_dist_op_create: halo size exchange failed: %s",
+                       r != ncclSuccess ? nc->GetErrorString(r) : cudaGetErrorString(e));
+    }
+    op->send_lo = d->rank > 0 ? h[2] : 0;                // lower neighbour's ghost_hi = my leading owned entries
+    op->send_hi = d->rank < d->world - 1 ? h[3] : 0;     // upper neighbour's ghost_lo = my trailing owned entries
+    if (op->send_lo > op->n_owned || op->send_hi > op->n_owned) {
+      femx_dist_op_destroy(op);
+      return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_dist_op_create: a neighbour's ghost zone is larger than this rank's owned range");
+    }
+  }
+  *out = op;
+  return FEMX_OK;
+}
+
+void femx_dist_op_destroy(femx_dist_op* op) {
+  if (!op) return;
+  if (op->graph) cudaGraphExecDestroy(op->graph);
+  cudaFree(op->x_ext); cudaFree(op->r_ext); cudaFree(op->w); cudaFree(op->p); cudaFree(op->s);
+  cudaFree(op->d_sc); cudaFree(op->d_it); cudaFree(op->d_part); cudaFree(op->d_hist);
+  delete op;
+}
+
+int femx_dist_op_info(const femx_dist_op* op, int64_t* n_owned, int64_t* ghost_lo, int64_t* ghost_hi, int64_t* interior_lo,
+                      int64_t* interior_hi) {
+  if (!op) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_dist_op_info: NULL argument");
+  if (n_owned) *n_owned = op->n_owned;
+  if (ghost_lo) *ghost_lo = op->ghost_lo;
+  if (ghost_hi) *ghost_hi = op->ghost_hi;
+  if (interior_lo) *interior_lo = op->int_lo;
+  if (interior_hi) *interior_hi = op->int_hi;
+  return FEMX_OK;
+}
+
+int femx_dist_spmv(femx_dist_op* op, const void* d_x_owned, void* d_y_owned, void* stream) {
+  if (!op || !d_x_owned || !d_y_owned) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_dist_spmv: NULL argument");
+  femx_ctx* ctx = op->d->ctx;
+  FEMX_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = esize(op->dtype);
+  FEMX_CUDA_OK(ctx, cudaMemcpyAsync((char*)op->x_ext + op->ghost_lo * es, d_x_owned, op->n_owned * es, cudaMemcpyDeviceToDevice, st));
+  return spmv_overlapped(op, op->x_ext, d_y_owned, st);
+}
+
+int femx_dist_cg(femx_dist_op* op, const void* d_b_owned, void* d_x_owned, int iters, double* h_residuals, float* h_ms,
+                 void* stream) {
+  if (!op || !d_b_owned || !d_x_owned || iters < 0) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_dist_cg: bad argument");
+  femx_dist* d = op->d;
+  femx_ctx* ctx = d->ctx;
+  FEMX_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = esize(op->dtype);
+  const int64_t n = op->n_owned;
+  if (op->hist_cap < iters + 1) {
+    cudaFree(op->d_hist);
+    op->d_hist = nullptr;
+    FEMX_CUDA_OK(ctx, cudaMalloc((void**)&op->d_hist, sizeof(double) * (iters + 1)));
+    op->hist_cap = iters + 1;
+  }
+  void* r = (char*)op->r_ext + op->ghost_lo * es;
+  cudaEvent_t t0, t1;
+  FEMX_CUDA_OK(ctx, cudaEventCreate(&t0));
+  FEMX_CUDA_OK(ctx, cudaEventCreate(&t1));
+  auto fail = [&](int code) { cudaEventDestroy(t0); cudaEventDestroy(t1); return code; };
+#define CG_CUDA(call)                                                                                         \
+  do {                                                                                                        \
+    cudaError_t e__ = (call);                                                                                 \
+    if (e__ != cudaSuccess) return fail(femx_fail(ctx, FEMX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__))); \
+  } while (0)
+  // x0 = 0, r = b, w = A r, (gamma, delta) = ((r,r), (w,r))
+  CG_CUDA(cudaMemsetAsync(d_x_owned, 0, n * es, st));
+  CG_CUDA(cudaMemsetAsync(op->p, 0, n * es, st));
+  CG_CUDA(cudaMemsetAsync(op->s, 0, n * es, st));
+  CG_CUDA(cudaMemsetAsync(op->d_it, 0, sizeof(int), st));
+  CG_CUDA(cudaMemcpyAsync(r, d_b_owned, n * es, cudaMemcpyDeviceToDevice, st));
+  CG_CUDA(cudaEventRecord(t0, st));
+  int rc = spmv_overlapped(op, op->r_ext, op->w, st);
+  if (rc == FEMX_OK) rc = reduce2(op, r, op->w, st);
+  if (rc != FEMX_OK) return fail(rc);
+  if (iters > 0 && op->use_graph && (!op->graph || op->graph_x != d_x_owned)) {
+    // one iteration, two streams (the halo travels on s_comm), captured once and replayed; the captured
+    // iteration writes the x it was captured with
+    if (op->graph) { cudaGraphExecDestroy(op->graph); op->graph = nullptr; }
+    cudaGraph_t g = nullptr;
+    CG_CUDA(cudaStreamSynchronize(st));
+    CG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = cg_iteration(op, d_x_owned, st);
+    cudaError_t ce = cudaStreamEndCapture(st, &g);
+    if (rc == FEMX_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&op->graph, g, 0) == cudaSuccess) {
+      op->graph_x = d_x_owned;
+    } else {  // e.g. an NCCL build that cannot be captured: plain launches
+      (void)cudaGetLastError();
+      op->graph = nullptr;
+      op->use_graph = 0;
+    }
+    if (g) cudaGraphDestroy(g);
+  }
+  for (int it = 0; it < iters; ++it) {
+    if (op->graph) {
+      CG_CUDA(cudaGraphLaunch(op->graph, st));
+    } else {
+      rc = cg_iteration(op, d_x_owned, st);
+      if (rc != FEMX_OK) return fail(rc);
+    }
+  }
+  cg_final_k<<<1, 1, 0, st>>>(op->d_sc, op->d_hist, op->d_it);
+  CG_CUDA(cudaEventRecord(t1, st));
+  std::vector<double> hist(iters + 1);
+  CG_CUDA(cudaMemcpyAsync(hist.data(), op->d_hist, sizeof(double) * (iters + 1), cudaMemcpyDeviceToHost, st));
+  CG_CUDA(cudaStreamSynchronize(st));
+  if (h_residuals)
+    for (int k = 0; k <= iters; ++k) h_residuals[k] = std::sqrt(std::max(hist[k], 0.0));
+  if (h_ms) cudaEventElapsedTime(h_ms, t0, t1);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  return FEMX_OK;
+#undef CG_CUDA
+}
+
+}  // extern "C"

@@ -696,6 +696,8 @@ int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, boo
       if (ld.empty())
         return femx_fail(f->ctx, FEMX_ERR_UNSUPPORTED, "lattice pass: %s", plan->fallback.c_str());
       defs += ld;
+      v.lt_smem = plan->smem;
+      v.lt_nslot = plan->nslot;
     }
     v.source = "// femx JIT kernel '" + vkey + "' (generated)\n" + defs + kFemxJitCommon + body;
     nvrtcProgram prog;
@@ -738,6 +740,7 @@ int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, boo
     it = f->variants.emplace(vkey, std::move(v)).first;
   }
   Variant& v = it->second;
+  if (lat && plan) { plan->smem = v.lt_smem; plan->nslot = v.lt_nslot; }  // (cache hit: the generator did not run)
   if (load && !v.fn) {
     if (!f->ctx)
       return femx_fail(nullptr, FEMX_ERR_CUDA,

@@ -15,6 +15,8 @@ struct femx_variant {
   CUfunction fn = nullptr;
   int smem_set = 0;
   int carveout_set = 0;
+  size_t lt_smem = 0;  // lattice variants: dynamic shared memory the generated kernel needs
+  int lt_nslot = 0;
 };
 
 // a stencil class handed to the JIT (femx_pattern's dominant class, or an explicit one)

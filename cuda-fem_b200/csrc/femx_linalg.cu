@@ -8,9 +8,9 @@ namespace {
 // One thread per dof row (i, c).  values are laid out as the dof-level CSR:
 // row start = nd*nd*row_ptr[i] + c*nd*len, entry (p, d) at p*nd + d.
 template <class T>
-__global__ void spmv_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx, int n_rows, int nd,
+__global__ void spmv_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx, int row0, int n_rows, int nd,
                        const T* __restrict__ vals, const T* __restrict__ x, long long x_base, T* __restrict__ y) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t t = (int64_t)row0 * nd + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)n_rows * nd) return;
   int i = (int)(t / nd), c = (int)(t - (int64_t)i * nd);
   int lo = rowinfo[i].x, len = rowinfo[i + 1].x - lo;
@@ -30,10 +30,10 @@ __global__ void spmv_k(const int2* __restrict__ rowinfo, const int* __restrict__
 // memory reads each row with a 15-element stride between lanes.)
 template <class T, int TILE>
 __global__ void __launch_bounds__(TILE) spmv_tile_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx,
-                                                     int n_rows, const T* __restrict__ vals, const T* __restrict__ x,
+                                                     int row0, int n_rows, const T* __restrict__ vals, const T* __restrict__ x,
                                                      long long x_off, T* __restrict__ y) {
   extern __shared__ __align__(16) unsigned char sm[];
-  const int i0 = blockIdx.x * TILE;
+  const int i0 = row0 + blockIdx.x * TILE;   // rows [row0, n_rows)
   const int nt = min(TILE, n_rows - i0);
   const int base = rowinfo[i0].x;
   const int cnt = rowinfo[i0 + nt].x - base;
@@ -142,39 +142,54 @@ inline unsigned nb(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
 
-extern "C" {
-
-int femx_spmv(const femx_pattern* p, int dtype, const void* d_values, const void* d_x, int64_t x_base, void* d_y,
-              void* stream) {
+// y[rows row_lo..row_hi) = A x for a range of NODE rows (the multi-GPU layer multiplies the rows that read no ghost
+// column while the halo is still travelling)
+int femx_spmv_range(const femx_pattern* p, int dtype, const void* d_values, const void* d_x, int64_t x_base, void* d_y,
+                    int64_t row_lo, int64_t row_hi, void* stream) {
   if (!p || !d_values || !d_x || !d_y) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_spmv: NULL argument");
-  if (p->n_rows == 0) return FEMX_OK;
+  if (row_lo < 0 || row_hi > p->n_rows || row_lo > row_hi) return femx_fail(p->ctx, FEMX_ERR_INVALID, "femx_spmv: bad row range");
+  if (row_hi == row_lo) return FEMX_OK;
   FEMX_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
-  int64_t n = p->n_rows * p->nd;
+  const int64_t n = (row_hi - row_lo) * p->nd;
   const long long xb = (long long)x_base - (long long)p->nd * p->col_base;
   const size_t rs = dtype == FEMX_F64 ? 8 : 4;
-  const size_t smem = (size_t)(p->max_tile_nnz + 2) * (rs + 4);
-  if (p->nd == 1 && p->tile_nodes == 128 && smem <= 200 * 1024) {
-    // tile-staged kernel (same 128-row tiles as the numeric pass)
-    const unsigned blocks = (unsigned)((p->n_rows + 127) / 128);
+  // (max_tile_nnz is taken over 128-row tiles starting at multiples of 128; a window that starts elsewhere lies in two of them)
+  const size_t smem = (size_t)(p->max_tile_nnz * (row_lo % 128 ? 2 : 1) + 2) * (rs + 4);
+  if (p->nd == 1 && smem <= 200 * 1024 && p->tile_nodes == 128) {
+    // tile-staged kernel (128-row tiles)
+    const unsigned blocks = (unsigned)((row_hi - row_lo + 127) / 128);
     if (dtype == FEMX_F64) {
       if (smem > 48 * 1024) cudaFuncSetAttribute(spmv_tile_k<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      spmv_tile_k<double, 128><<<blocks, 128, smem, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows,
+      spmv_tile_k<double, 128><<<blocks, 128, smem, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)row_lo, (int)row_hi,
                                                                              (const double*)d_values, (const double*)d_x, xb,
                                                                              (double*)d_y);
     } else {
       if (smem > 48 * 1024) cudaFuncSetAttribute(spmv_tile_k<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      spmv_tile_k<float, 128><<<blocks, 128, smem, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows,
+      spmv_tile_k<float, 128><<<blocks, 128, smem, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)row_lo, (int)row_hi,
                                                                             (const float*)d_values, (const float*)d_x, xb,
                                                                             (float*)d_y);
     }
   } else if (dtype == FEMX_F64)
-    spmv_k<double><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
+    spmv_k<double><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)row_lo, (int)row_hi, p->nd,
                                                             (const double*)d_values, (const double*)d_x, xb, (double*)d_y);
   else
-    spmv_k<float><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
+    spmv_k<float><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)row_lo, (int)row_hi, p->nd,
                                                            (const float*)d_values, (const float*)d_x, xb, (float*)d_y);
   FEMX_CUDA_OK(p->ctx, cudaGetLastError());
   return FEMX_OK;
+}
+
+extern "C" {
+
+int femx_spmv_rows(const femx_pattern* p, int dtype, const void* d_values, const void* d_x, int64_t x_base, void* d_y,
+                   int64_t row_lo, int64_t row_hi, void* stream) {
+  return femx_spmv_range(p, dtype, d_values, d_x, x_base, d_y, row_lo, row_hi, stream);
+}
+
+int femx_spmv(const femx_pattern* p, int dtype, const void* d_values, const void* d_x, int64_t x_base, void* d_y,
+              void* stream) {
+  if (!p) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_spmv: NULL argument");
+  return femx_spmv_range(p, dtype, d_values, d_x, x_base, d_y, 0, p->n_rows, stream);
 }
 
 int femx_apply_dirichlet(const femx_pattern* p, int dtype, const int32_t* d_flag, const void* d_g, void* d_values,
@@ -201,16 +216,20 @@ int femx_dot2(femx_ctx* ctx, int dtype, int64_t n, const void* d_a, const void* 
   if (!ctx || !d_a || !d_b || !d_out || (d_c && !d_d))
     return femx_fail(ctx, FEMX_ERR_INVALID, "femx_dot2: NULL argument");
   FEMX_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-  if (!ctx->d_scratch) FEMX_CUDA_OK(ctx, cudaMalloc(&ctx->d_scratch, sizeof(double) * 2 * FEMX_DOT_BLOCKS));
   cudaStream_t st = (cudaStream_t)stream;
+  // partial sums: stream-ordered scratch per call (two calls on different streams of one ctx do not share it)
+  double* scratch = nullptr;
+  FEMX_CUDA_OK(ctx, ctx->pool ? cudaMallocFromPoolAsync((void**)&scratch, sizeof(double) * 2 * FEMX_DOT_BLOCKS, ctx->pool, st)
+                              : cudaMallocAsync((void**)&scratch, sizeof(double) * 2 * FEMX_DOT_BLOCKS, st));
   int blocks = (int)std::min<int64_t>(FEMX_DOT_BLOCKS, std::max<int64_t>(1, (n + 255) / 256));
   if (dtype == FEMX_F64)
     dot2_partial<double><<<blocks, 256, 0, st>>>(n, (const double*)d_a, (const double*)d_b, (const double*)d_c,
-                                                 (const double*)d_d, ctx->d_scratch);
+                                                 (const double*)d_d, scratch);
   else
     dot2_partial<float><<<blocks, 256, 0, st>>>(n, (const float*)d_a, (const float*)d_b, (const float*)d_c,
-                                                (const float*)d_d, ctx->d_scratch);
-  dot2_final<<<1, 256, 0, st>>>(ctx->d_scratch, blocks, d_out);
+                                                (const float*)d_d, scratch);
+  dot2_final<<<1, 256, 0, st>>>(scratch, blocks, d_out);
+  cudaFreeAsync(scratch, st);
   FEMX_CUDA_OK(ctx, cudaGetLastError());
   return FEMX_OK;
 }

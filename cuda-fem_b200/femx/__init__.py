@@ -49,6 +49,8 @@ class _MeshView(C.Structure):
 SYMBOLS = [
     "femx_ctx_create", "femx_ctx_destroy", "femx_last_error", "femx_version", "femx_ctx_set_option",
     "femx_pattern_lattice", "femx_form_cubin_lattice",
+    "femx_dist_unique_id", "femx_dist_create", "femx_dist_destroy", "femx_dist_slab", "femx_dist_allreduce",
+    "femx_dist_op_create", "femx_dist_op_destroy", "femx_dist_op_info", "femx_dist_spmv", "femx_dist_cg", "femx_spmv_rows",
     "femx_form_compile", "femx_form_compile_offline", "femx_form_destroy", "femx_form_source",
     "femx_form_log", "femx_form_entry", "femx_form_prologue", "femx_form_cubin",
     "femx_mesh_rectangle", "femx_mesh_expand", "femx_mesh_box",
@@ -449,6 +451,106 @@ class Pattern:
     def close(self):
         if self.h:
             lib().femx_pattern_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+DIST_ID_BYTES = 128
+
+
+def dist_slab(n_planes, world, rank):
+    """Owned node planes [r0, r1) and slab planes [lo, hi] of `rank` (femx_dist_slab)."""
+    a, b, c, d = (C.c_int64() for _ in range(4))
+    st = lib().femx_dist_slab(_i64(n_planes), int(world), int(rank), C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+    if st:
+        raise FemxError(st, lib().femx_last_error(None).decode())
+    return a.value, b.value, c.value, d.value
+
+
+def dist_unique_id():
+    """NCCL unique id (bytes) — rank 0 creates it, the launcher's channel carries it to the other ranks."""
+    buf = (C.c_ubyte * DIST_ID_BYTES)()
+    st = lib().femx_dist_unique_id(buf)
+    if st:
+        raise FemxError(st, lib().femx_last_error(None).decode())
+    return bytes(buf)
+
+
+class Dist:
+    """One rank of the multi-GPU layer (femx_dist_*): NCCL communicator + halo stream, in C++ behind the ABI."""
+
+    def __init__(self, ctx, rank=0, world=1, unique_id=None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.h = C.c_void_p()
+        idbuf = None
+        if unique_id is not None:
+            idbuf = (C.c_ubyte * DIST_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        ctx.check(lib().femx_dist_create(ctx.h, int(rank), int(world), idbuf, C.byref(self.h)))
+
+    @staticmethod
+    def from_torch(ctx):
+        """Bootstraps from an initialised torch.distributed group: rank 0's id is broadcast over it."""
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return Dist(ctx)
+        rank, world = dist.get_rank(), dist.get_world_size()
+        dev = torch.device("cuda", ctx.device)
+        t = torch.zeros(DIST_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(dist_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return Dist(ctx, rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    def allreduce(self, t, op="sum", stream=None):
+        """in-place on a float64 device tensor"""
+        self.ctx.check(lib().femx_dist_allreduce(self.h, _vp(t), int(t.numel()), 1 if op == "max" else 0, _stream(stream)))
+        return t
+
+    def operator(self, pattern, values):
+        return DistOp(self, pattern, values)
+
+    def close(self):
+        if self.h:
+            lib().femx_dist_destroy.argtypes = [C.c_void_p]
+            lib().femx_dist_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class DistOp:
+    """This rank's rows of the assembled operator: halo-exchanging SpMV and CG (femx_dist_spmv / femx_dist_cg)."""
+
+    def __init__(self, dist, pattern, values):
+        import torch
+        self.dist, self.pat, self.vals = dist, pattern, values
+        self.dt = F64 if values.dtype == torch.float64 else F32
+        self.h = C.c_void_p()
+        dist.ctx.check(lib().femx_dist_op_create(dist.h, pattern.h, self.dt, _vp(values), C.byref(self.h)))
+        v = [C.c_int64() for _ in range(5)]
+        dist.ctx.check(lib().femx_dist_op_info(self.h, *[C.byref(x) for x in v]))
+        self.n_owned, self.ghost_lo, self.ghost_hi, self.interior_lo, self.interior_hi = (x.value for x in v)
+
+    def spmv(self, x, y=None, stream=None):
+        import torch
+        if y is None:
+            y = torch.empty_like(x)
+        self.dist.ctx.check(lib().femx_dist_spmv(self.h, _vp(x), _vp(y), _stream(stream)))
+        return y
+
+    def cg(self, b, iters, x=None, stream=None):
+        """x (owned part), residual norms (numpy, iters+1), device milliseconds of the solve"""
+        import numpy as np
+        import torch
+        if x is None:
+            x = torch.empty_like(b)
+        res = (C.c_double * (iters + 1))()
+        ms = C.c_float()
+        self.dist.ctx.check(lib().femx_dist_cg(self.h, _vp(b), _vp(x), int(iters), res, C.byref(ms), _stream(stream)))
+        return x, np.array(res[:]), ms.value
+
+    def close(self):
+        if self.h:
+            lib().femx_dist_op_destroy.argtypes = [C.c_void_p]
+            lib().femx_dist_op_destroy(self.h)
             self.h = C.c_void_p()
 
 

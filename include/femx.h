@@ -324,6 +324,48 @@ int femx_axpy_ratio(femx_ctx* ctx, int dtype, int64_t n, const double* d_num,
 int femx_xpby_ratio(femx_ctx* ctx, int dtype, int64_t n, const double* d_num,
                     const double* d_den, const void* d_r, void* d_p, void* stream);
 
+/* ------------------------------------------------------------- multi-GPU layer */
+
+/* One process per GPU.  Assembly shards with NO communication: rank p owns node planes [r0, r1) of the
+ * structured mesh (femx_dist_slab), builds the slab [lo, hi] with one ghost layer per side
+ * (femx_mesh_box / femx_mesh_rectangle with k_lo/k_hi), and femx_pattern_build(row_begin, row_end,
+ * col_base) + femx_assemble_csr produce its rows of the GLOBAL matrix (bit-identical to the single-GPU
+ * rows).  NCCL (resolved at run time from the libnccl.so.2 already in the process, else the system's)
+ * is used only by the validation solver below: grouped ncclSend/ncclRecv for the halo of the SpMV operand
+ * and ONE fused 2-double ncclAllReduce per CG iteration.  No reference counterpart (the reference runs one
+ * rank: job.pbs:4,24). */
+typedef struct femx_dist femx_dist;        /* communicator + streams of one rank          */
+typedef struct femx_dist_op femx_dist_op;  /* this rank's rows of the operator + halo plan */
+#define FEMX_DIST_ID_BYTES 128
+/* Rank 0 creates the NCCL unique id (h_id: FEMX_DIST_ID_BYTES host bytes) and hands it to the other ranks by
+ * whatever out-of-band channel the launcher has (bench.py: a torch.distributed broadcast; C++ clients: MPI / a file). */
+int femx_dist_unique_id(void* h_id);
+int femx_dist_create(femx_ctx* ctx, int rank, int world, const void* h_id, femx_dist** out);  /* world == 1: h_id may be NULL */
+void femx_dist_destroy(femx_dist* d);
+/* Even split of n_planes node planes over `world` ranks: owned planes [r0, r1), slab planes [lo, hi]. */
+int femx_dist_slab(int64_t n_planes, int world, int rank, int64_t* r0, int64_t* r1, int64_t* lo, int64_t* hi);
+/* In-place sum (op_max = 0) or max (1) of n doubles across ranks (timing / checksums of the harness). */
+int femx_dist_allreduce(femx_dist* d, double* d_buf, int n, int op_max, void* stream);
+/* The rank's assembled rows as an operator.  The pattern's local node layout is [ghost | owned rows | ghost]
+ * (row_begin / row_end of femx_pattern_build); the ghost zones of the operand come from ranks rank-1 / rank+1. */
+int femx_dist_op_create(femx_dist* d, const femx_pattern* pat, int dtype, const void* d_values, femx_dist_op** out);
+void femx_dist_op_destroy(femx_dist_op* op);
+/* n_owned dof rows; operand entries below / above the owned range; node rows [interior_lo, interior_hi) read no
+ * ghost column (their SpMV overlaps the halo exchange). */
+int femx_dist_op_info(const femx_dist_op* op, int64_t* n_owned, int64_t* ghost_lo, int64_t* ghost_hi, int64_t* interior_lo,
+                      int64_t* interior_hi);
+/* y_owned = A[owned rows] x, x given by its owned part on every rank (device pointers, n_owned entries each). */
+int femx_dist_spmv(femx_dist_op* op, const void* d_x_owned, void* d_y_owned, void* stream);
+/* `iters` steps of unpreconditioned CG from x0 = 0 (Chronopoulos-Gear form: one SpMV, one fused update kernel and
+ * ONE all-reduce of two doubles per iteration; the iteration is captured in a CUDA graph and replayed).
+ * h_residuals (host, iters+1 entries, may be NULL) receives ||r_k||_2; *h_ms (may be NULL) the device time of the solve.
+ * Synchronises the stream before returning. */
+int femx_dist_cg(femx_dist_op* op, const void* d_b_owned, void* d_x_owned, int iters, double* h_residuals, float* h_ms,
+                 void* stream);
+/* y = A x for node rows [row_lo, row_hi) of the pattern only (femx_spmv: all rows). */
+int femx_spmv_rows(const femx_pattern* pat, int dtype, const void* d_values, const void* d_x, int64_t x_base, void* d_y,
+                   int64_t row_lo, int64_t row_hi, void* stream);
+
 /* ------------------------------------------------ host-side I/O (no device needed) */
 
 /* Gmsh MSH 2.x ASCII: 3-node triangles, or 4-node tetrahedra when present (the boundary triangles of

@@ -34,10 +34,13 @@ CONFIGS = [
     dict(lt_tx=16, lt_ty=16, lt_minb=2, carveout=100),
     dict(lt_tx=12, lt_ty=16, lt_minb=2, carveout=100),
 ]
-DEFAULTS = dict(lattice=1, lt_tx=0, lt_ty=0, lt_minb=0, lt_kc=0, lt_pf=1, lt_regs=0, carveout=-1)
+DEFAULTS = dict(lattice=1, lt_tx=0, lt_ty=0, lt_minb=0, lt_kc=0, lt_pf=1, lt_regs=0, carveout=-1, rcp3=0)
 
 
 def main():
+    global CONFIGS
+    if os.environ.get("LATTICE_CFGS"):      # e.g. LATTICE_CFGS='[{"lt_tx":8,"lt_ty":16,"lt_minb":3}]' (ncu runs: one configuration)
+        CONFIGS = json.loads(os.environ["LATTICE_CFGS"])
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     ctx = femx.Context(0)
