@@ -1,18 +1,21 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the hot path: fp64 P1 assembly into CSR.
 
-Workload (BASELINE.json configs[1]): 2-D P1 Poisson stiffness on a structured
-4096 x 4096 triangle mesh (33,554,432 elements, 16,785,409 nodes, 117,465,089 nnz),
-fp64, deterministic numeric pass into a prebuilt CSR pattern.  One "step" = one
-numeric pass over the whole mesh.  With N GPUs each rank owns a slab of 4096 cell
-rows of a (4096*N) x 4096 mesh (weak scaling; owned CSR rows + ghost elements, no
-data-path collective).
+Workload (BASELINE.json configs[2], the north-star configuration): the symbolic integrand
+grad u . grad v + u v on 3-D P1 tetrahedra, 256^3 Kuhn cube (100,663,296 tets, 16,974,593 nodes,
+253,036,801 nnz), fp64, deterministic numeric pass into a prebuilt CSR pattern.  One "step" = one
+numeric pass over the whole mesh.  With N GPUs the FIXED cube is split into z-slabs of owned node
+planes with one ghost cell layer per side (strong scaling; assembly needs no collective); the
+assembled operator is then validated by SpMV + 100 CG iterations with NCCL halo exchange
+(BASELINE.json configs[4]) through the C++ multi-GPU layer (femx_dist_*).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg3|cfg1]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                  [--workload cfg3|cfg2|cfg4|cfg1] [--no-extras] [--no-cg]
 
-Prints ONE JSON line (see README / DESIGN.md §Measurement for the keys).
+Prints ONE JSON line (DESIGN.md §5 explains the keys).
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -25,11 +28,17 @@ for _p in (ROOT, os.path.join(ROOT, "cuda-fem_b200")):
         sys.path.insert(0, _p)
 
 WORKLOADS = {
-    # name: (dim, per-GPU cells along the sharded axis, other axes, builtin form name)
-    "cfg1": dict(dim=2, rows=64, cols=64, form="POISSON", desc="2-D P1 Poisson 64x64 unit square"),
-    "cfg2": dict(dim=2, rows=4096, cols=4096, form="POISSON", desc="2-D P1 Poisson 4096x4096 structured triangles"),
-    "cfg3": dict(dim=3, rows=256, cols=256, form="POISSON_MASS", desc="3-D P1 tets 256^3 Kuhn cube, grad.grad + u v"),
+    # n = cells along the sharded axis (node rows in 2-D, z in 3-D), m = cells along the other axes
+    "cfg1": dict(dim=2, n=64, m=64, form="POISSON", nd=1, params=(), desc="2-D P1 Poisson 64x64 unit square"),
+    "cfg2": dict(dim=2, n=4096, m=4096, form="POISSON", nd=1, params=(),
+                 desc="2-D P1 Poisson 4096x4096 structured triangles"),
+    "cfg3": dict(dim=3, n=256, m=256, form="POISSON_MASS", nd=1, params=(1.0,),
+                 desc="3-D P1 tets 256^3 Kuhn cube, grad.grad + u v (NVRTC integrand)"),
+    "cfg4": dict(dim=3, n=192, m=192, form="ELASTICITY", nd=3, params=(0.5769230769230769, 0.3846153846153846),
+                 desc="3-D linear elasticity P1 tets 192^3 Kuhn cube (12x12 element matrices, E=1, nu=0.3)"),
 }
+UNPINNED = ("3-D / mass / elasticity: the reference has no implementation (fea_symbolic_nvrtc_sparse.cpp:271-274 returns 3), "
+            "parity is against the oracle restatement, unpinned by the reference")
 
 
 def measured_peaks():
@@ -97,82 +106,195 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def ref_gpu_baseline(ctx, wl, mesh, pat):
-    """North-star reported baseline #1: the reference's own kernels (K4 COO, K5 ELL + global atomicAdd;
-    oracle/_ref, recompiled for sm_100 with the minimal fixes of oracle/build_ref.py) timed on the same
-    mesh.  fp32 as written and the mechanical fp64 retype.  Reported, not optimised."""
+def profiled_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of femx_csr from the committed
+    `ncu --set full` capture (profiles/traffic.json) + a hash tying the figure to the file, or (None, None)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    raw = open(p, "rb").read()
+    j = json.loads(raw)
+    ent = j.get(workload)
+    if ent is None:
+        return None, None
+    src = {"file": "profiles/traffic.json", "sha1": hashlib.sha1(raw).hexdigest()[:12]}
+    if isinstance(ent, dict):
+        src.update({k: v for k, v in ent.items() if k != "bytes"})
+        return ent.get("bytes"), src
+    return ent, src
+
+
+# ------------------------------------------------------------------ the workload on this rank ---
+def build_problem(ctx, femx, wl, rank, world):
+    """This rank's z-slab (node rows in 2-D) of the FIXED global mesh: owned planes [r0, r1), slab planes
+    [lo, hi] (one ghost layer per side).  Returns mesh, slab dict."""
+    dim, n, m = wl["dim"], wl["n"], wl["m"]
+    r0, r1, lo, hi = femx.dist_slab(n + 1, world, rank)
+    if dim == 2:
+        plane = m + 1
+        mesh = ctx.rectangle_mesh(0.0, 1.0, 0.0, 1.0, n, m, row_lo=lo, row_hi=hi)
+        ne_global = 2 * n * m
+    else:
+        plane = (m + 1) ** 2
+        mesh = ctx.box_mesh(m, m, n, k_lo=lo, k_hi=hi)
+        ne_global = 6 * n * m * m
+    slab = dict(r0=r0, r1=r1, lo=lo, hi=hi, plane=plane, row_begin=(r0 - lo) * plane, row_end=(r1 - lo) * plane,
+                col_base=lo * plane, ne_global=ne_global, nodes_global=(n + 1) * plane)
+    return mesh, slab
+
+
+def algorithmic_bytes(mesh, pat, dim):
+    """SURVEY §8d: connectivity int32 + node coordinates fp64 read once, CSR values written once;
+    no scatter map, no workspace."""
+    return mesh.n_elems * mesh.nn * 4 + mesh.n_nodes * dim * 8 + pat.nnz * 8
+
+
+def time_numeric_pass(torch, form, pat, mesh, vals, steps, warmup, barrier, sampler=None):
+    for _ in range(max(warmup, 3)):
+        form.assemble_csr(pat, mesh, vals)
+    barrier()
+    if sampler:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for k in range(steps):
+        form.assemble_csr(pat, mesh, vals)   # ONE kernel launch (femx_csr) per step
+        ev[k + 1].record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(steps))
+    return total_ms, per_launch, clocks
+
+
+def parity_vs_oracle(torch, wl, mesh, slab, pat, vals, rp, ci):
+    """Value-level parity AT THE BENCHMARKED SIZE, outside the timed region: up to three z-slabs of two owned node
+    planes (first / middle / last of this rank) are re-assembled by the CPU oracle from the device's own coordinates
+    and compared with the CUDA values: column indices bit-exact, values relF <= 1e-12."""
+    import numpy as np
+    from oracle import oracle as orc
+    dim, m, nd = wl["dim"], wl["m"], wl["nd"]
+    plane = slab["plane"]
+    owned_planes = slab["r1"] - slab["r0"]
+    n_local_planes = slab["hi"] - slab["lo"] + 1
+    firsts = sorted({0, max(0, owned_planes // 2 - 1), max(0, owned_planes - 2)})
+    worst, exact, rows_checked = 0.0, True, 0
+    for f in firsts:
+        p0 = slab["r0"] - slab["lo"] + f               # local plane of the first checked row plane
+        p1 = min(p0 + 2, slab["r1"] - slab["lo"])       # checked planes [p0, p1)
+        s0, s1 = max(p0 - 1, 0), min(p1, n_local_planes - 1)   # sub-mesh planes [s0, s1]
+        if dim == 3:
+            _, _, _, conn = orc.box_mesh(m, m, s1 - s0)
+        else:
+            _, _, _, conn = orc.rect_mesh(0, 1, 0, 1, s1 - s0, m)
+        sel = slice(s0 * plane, (s1 + 1) * plane)
+        coords = [c[sel].cpu().numpy() for c in mesh.node_xyz]
+        orp, oci = orc.pattern(conn, len(coords[0]))
+        if nd > 1:
+            drp, dci = orc.expand_pattern(nd, orp, oci)
+        else:
+            drp, dci = orp, oci
+        oc = coords if dim == 3 else (coords[0], coords[1], None)
+        ov = orc.assemble_csr(getattr(orc, wl["form"]), dim, nd, conn, *oc, drp, dci, params=wl["params"] or None)
+        a, b = (p0 - s0) * plane * nd, (p1 - s0) * plane * nd           # oracle dof rows
+        ga, gb = (p0 * plane - slab["row_begin"]) * nd, (p1 * plane - slab["row_begin"]) * nd   # pattern dof rows
+        va, vb = int(rp[ga].item()), int(rp[gb].item())
+        got = vals[va:vb].cpu().numpy()
+        want = ov[drp[a]:drp[b]]
+        cols = ci[va:vb].cpu().numpy().astype(np.int64)
+        wcols = dci[drp[a]:drp[b]].astype(np.int64) + (slab["lo"] + s0) * plane * nd
+        exact = exact and len(got) == len(want) and bool(np.array_equal(cols, wcols)) and \
+            bool(np.array_equal((rp[ga:gb + 1] - rp[ga]).cpu().numpy(), drp[a:b + 1] - drp[a]))
+        if len(got) == len(want):
+            worst = max(worst, float(np.linalg.norm(got - want) / np.linalg.norm(want)))
+        else:
+            worst = float("inf")
+        rows_checked += gb - ga
+    return {"against": "CPU oracle (oracle/femx_oracle.c) on the device's own coordinates", "rows_checked": rows_checked,
+            "z_slabs": len(firsts), "pattern_exact": exact, "relF": worst, "tolerance": 1e-12,
+            "ok": bool(exact and worst <= 1e-12)}
+
+
+def ref_gpu_baseline_and_parity(ctx, femx, torch, wl, mesh, pat, vals):
+    """cfg2 only (the reference is 2-D): the reference's own kernels (K4 COO, K5 ELL + global atomicAdd; oracle/_ref,
+    recompiled for sm_100 with the minimal fixes of oracle/build_ref.py) timed on the same mesh — and, with the fp64
+    retype, compared VALUE BY VALUE with femx at the full size: ELL pattern bit-exact, relF <= 1e-12."""
     try:
         from oracle import refimpl
         if not refimpl.available() or wl["dim"] != 2:
-            return None
-        import torch
+            return None, None
         out = {"what": "reference fea_kernel recompiled for sm_100 (fixes Q2,Q3,Q4,Q8,Q13), CUDA events, 3 launches"}
         ln, idx = pat.ell(7)
         gidx = mesh.conn.reshape(-1).contiguous()
+        parity = None
         for prec, tdt in (("f32", torch.float32), ("f64", torch.float64)):
             X = mesh.node_xyz[0][mesh.conn.reshape(-1).long()].to(tdt).contiguous()
             Y = mesh.node_xyz[1][mesh.conn.reshape(-1).long()].to(tdt).contiguous()
-            _, ms_ell = refimpl.assemble_ell(prec, wl["rows"], wl["cols"], X, Y, gidx, ln, idx, iters=3)
-            _, _, _, ms_coo = refimpl.assemble_coo(prec, wl["rows"], wl["cols"], X, Y, gidx, iters=3)
+            ell, ms_ell = refimpl.assemble_ell(prec, wl["n"], wl["m"], X, Y, gidx, ln, idx, iters=3)
+            coo = refimpl.assemble_coo(prec, wl["n"], wl["m"], X, Y, gidx, iters=3)
+            ms_coo = coo[-1]
             out[prec] = {"ell_atomic_ms": ms_ell, "ell_atomic_elements_per_s": mesh.n_elems / (ms_ell * 1e-3),
                          "coo_ms": ms_coo, "coo_elements_per_s": mesh.n_elems / (ms_coo * 1e-3)}
-            del X, Y
-        # the reference's symbolic pass: host Mesh::getNeighborNodesList (std::set per node), timed on
-        # its own configured mesh (1000 x 100, fea_test_sm_sym_sparse2.cu:16-17) next to femx's device pass
-        t0 = time.perf_counter()
-        refimpl.neighbor_list(1000, 100)
-        host_ms = 1e3 * (time.perf_counter() - t0)
-        small = ctx.rectangle_mesh(-3.0, 3.0, -3.0, 3.0, 1000, 100)
-        import femx as _femx
-        _femx.Pattern(ctx, small).close()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        sp_ = _femx.Pattern(ctx, small)
-        torch.cuda.synchronize()
-        dev_ms = 1e3 * (time.perf_counter() - t0)
-        sp_.close()
-        out["symbolic_pass_1000x100"] = {"reference_host_ms (incl. its mesh construction)": host_ms, "femx_device_ms": dev_ms}
-        return out
+            if prec == "f64":
+                del ell
+                ell, _ = refimpl.assemble_ell(prec, wl["n"], wl["m"], X, Y, gidx, ln, idx, iters=1)   # (K5 accumulates: one launch)
+                mine = pat.values_to_ell(vals, 7)
+                ref = ell.reshape(mine.shape).to(torch.float64)
+                relF = float(torch.linalg.norm(mine - ref) / torch.linalg.norm(ref))
+                # rows above node 2^24 explicitly (SURVEY Q3: the reference's float node ids break there)
+                hi_rows = slice(1 << 24, None)
+                relF_hi = float(torch.linalg.norm(mine[hi_rows] - ref[hi_rows]) / torch.linalg.norm(ref[hi_rows])) \
+                    if mine.shape[0] > (1 << 24) else None
+                A_ref = coo[0].to(torch.float64)
+                A_mine, _, _ = femx_coo_values(femx, ctx, wl, mesh)
+                relF_coo = float(torch.linalg.norm(A_mine - A_ref) / torch.linalg.norm(A_ref))
+                parity = {"against": "reference K5 (ELL+atomicAdd) and K4 (COO), fp64 retype, same mesh", "config": "cfg2",
+                          "pattern_exact": True, "pattern_note": "K5 consumes femx_pattern_export_ell (bit-equal to getNeighborNodesList, tests)",
+                          "relF": relF, "relF_rows_above_2^24": relF_hi, "relF_coo": relF_coo, "tolerance": 1e-12,
+                          "ok": bool(relF <= 1e-12 and relF_coo <= 1e-12 and (relF_hi is None or relF_hi <= 1e-12))}
+                del mine, ref, A_ref, A_mine
+            del X, Y, ell, coo
+        return out, parity
     except Exception as e:  # a reported extra must never take the headline down
-        return {"error": repr(e)}
+        return {"error": repr(e)}, None
 
 
-def profiled_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of femx_csr from the committed
-    `ncu --set full` capture (profiles/traffic.json), or None."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get(workload)
-    return None
+def femx_coo_values(femx, ctx, wl, mesh):
+    form = femx.Form(ctx, wl["dim"], getattr(femx, wl["form"]), nd=wl["nd"], params=wl["params"])
+    A, r, c = form.assemble_coo(mesh, indices=False)
+    form.close()
+    return A, r, c
 
 
-def slab_bounds(n_planes_total, world, rank):
-    """Owned node rows/planes [r0, r1) of rank, and the slab [lo, hi] incl. one ghost layer each side."""
-    r0 = round(rank * n_planes_total / world)
-    r1 = round((rank + 1) * n_planes_total / world)
-    return r0, r1
-
-
-def cpu_baseline_port(wl, sample_rows=None):
-    """The oracle's serial numeric pass on a bounded sample of the workload (1 core)."""
+def cpu_baseline_port(wl, seconds_target=12.0):
+    """The oracle's serial numeric pass on a bounded sub-mesh of the workload, 1 core, built with -O3 -march=native
+    on this host."""
     from oracle import oracle as orc
-    import numpy as np
-    if wl["dim"] == 2:
-        rows = sample_rows or min(wl["rows"], 2048)
-        X, Y, _, conn = orc.rect_mesh(0, 1, 0, 1, rows, wl["cols"])
+    dim, m, nd = wl["dim"], wl["m"], wl["nd"]
+    layers = {2: min(wl["n"], 2048), 3: min(wl["n"], 12 if nd == 1 else 3)}[dim]
+    if dim == 2:
+        X, Y, _, conn = orc.rect_mesh(0, 1, 0, 1, layers, m)
         Z = None
-        sample = f"{rows}x{wl['cols']} sub-mesh of the workload ({len(conn)} elements), numeric pass only, pattern prebuilt"
+        sample = f"{layers}x{m} sub-mesh of the workload"
     else:
-        rows = sample_rows or min(wl["rows"], 24)
-        X, Y, Z, conn = orc.box_mesh(wl["cols"], wl["cols"], rows)
-        sample = f"{wl['cols']}x{wl['cols']}x{rows} sub-mesh of the workload ({len(conn)} elements), numeric pass only, pattern prebuilt"
+        X, Y, Z, conn = orc.box_mesh(m, m, layers)
+        sample = f"{m}x{m}x{layers} sub-mesh of the workload"
     rp, ci = orc.pattern(conn, len(X))
+    if nd > 1:
+        rp, ci = orc.expand_pattern(nd, rp, ci)
     form = getattr(orc, wl["form"])
+    try:
+        orc.lib_native()
+        native, flags = True, orc.NATIVE_FLAGS
+    except Exception:
+        native, flags = False, "-O3 -march=x86-64-v2 -ffp-contract=off (native build failed)"
+    orc.assemble_csr(form, dim, nd, conn[:1000], X, Y, Z, rp, ci, params=wl["params"] or None, native=native)  # warm
     t0 = time.perf_counter()
-    orc.assemble_csr(form, wl["dim"], 1, conn, X, Y, Z, rp, ci, params=(1.0,))
+    orc.assemble_csr(form, dim, nd, conn, X, Y, Z, rp, ci, params=wl["params"] or None, native=native)
     dt = time.perf_counter() - t0
-    return {"value": len(conn) / dt, "unit": "elements/s", "cores": 1, "kind": "port", "sample": sample,
-            "seconds": dt}
+    return {"value": len(conn) / dt, "unit": "elements/s", "cores": 1, "kind": "port",
+            "sample": f"{sample} ({len(conn)} elements), numeric pass only, pattern prebuilt, {dt:.1f} s",
+            "flags": flags}
 
 
 _REF_STATE = {}
@@ -181,36 +303,43 @@ _REF_STATE = {}
 def _ref_worker(args):
     """One slab of the workload on one host core: mesh + pattern are built once per worker process
     (cached), every step re-runs the oracle's serial numeric pass on it."""
-    name, wl, rows = args
+    name, wl, layers = args
     from oracle import oracle as orc
     st = _REF_STATE.get(name)
     if st is None:
         if wl["dim"] == 2:
-            X, Y, _, conn = orc.rect_mesh(0, 1, 0, 1, rows, wl["cols"])
+            X, Y, _, conn = orc.rect_mesh(0, 1, 0, 1, layers, wl["m"])
             Z = None
         else:
-            X, Y, Z, conn = orc.box_mesh(wl["cols"], wl["cols"], rows)
+            X, Y, Z, conn = orc.box_mesh(wl["m"], wl["m"], layers)
         rp, ci = orc.pattern(conn, len(X))
-        st = _REF_STATE[name] = (X, Y, Z, conn, rp, ci)
-    X, Y, Z, conn, rp, ci = st
+        if wl["nd"] > 1:
+            rp, ci = orc.expand_pattern(wl["nd"], rp, ci)
+        try:
+            orc.lib_native()
+            native = True
+        except Exception:
+            native = False
+        st = _REF_STATE[name] = (X, Y, Z, conn, rp, ci, native)
+    X, Y, Z, conn, rp, ci, native = st
     t0 = time.perf_counter()
-    orc.assemble_csr(getattr(orc, wl["form"]), wl["dim"], 1, conn, X, Y, Z, rp, ci, params=(1.0,))
-    return len(conn), time.perf_counter() - t0
+    orc.assemble_csr(getattr(orc, wl["form"]), wl["dim"], wl["nd"], conn, X, Y, Z, rp, ci, params=wl["params"] or None,
+                     native=native)
+    return len(conn), time.perf_counter() - t0, native
 
 
 def run_reference(args, wl, rank, world):
-    """--impl reference: the reference ships no host implementation of the numeric pass (its
-    fea_kernel is CUDA only; its recompiled kernels are reported by the femx arm as
-    `ref_gpu_baseline`), so the CPU arm is the oracle port, run as independent row slabs on all
-    host cores (the same sharding as the multi-GPU layout).  Rank 0 only."""
+    """--impl reference: the reference ships no host implementation of the numeric pass (its fea_kernel is CUDA
+    only; its recompiled kernels are reported by the femx arm as `ref_gpu_baseline`), so the CPU arm is the oracle
+    port (-O3 -march=native), run as independent slabs on all host cores (the same sharding as the multi-GPU
+    layout).  Rank 0 only."""
     if rank != 0:
         return
     import multiprocessing as mp
     cores = max(1, (os.cpu_count() or 1))
-    per = 64 if wl["dim"] == 2 else 2   # cell rows per worker per step: a bounded sample (~0.1-0.2 s/step)
-    per = min(per, wl["rows"])
-    times = []
-    ne_step = None
+    per = {2: 64, 3: 2 if wl["nd"] == 1 else 1}[wl["dim"]]   # cell layers per worker per step: a bounded sample
+    per = min(per, wl["n"])
+    times, ne_step, native = [], None, False
     with mp.Pool(cores) as pool:
         job = [(args.workload, wl, per)] * cores
         for it in range(args.warmup + args.steps):
@@ -218,34 +347,78 @@ def run_reference(args, wl, rank, world):
             res = pool.map(_ref_worker, job, chunksize=1)
             dt = time.perf_counter() - t0
             ne_step = sum(r[0] for r in res)
+            native = all(r[2] for r in res)
             if it >= args.warmup:
-                times.append(dt)            # wall time of the step: all workers, slowest bounds it
+                times.append(dt)            # wall time of the step: all workers, the slowest bounds it
     tot = sum(times)
     value = ne_step * len(times) / tot
-    sample = (f"each step: {cores} workers x ({per} cell rows x {wl['cols']} cols"
-              + (f" x {wl['cols']}" if wl["dim"] == 3 else "") + f") slab of the workload = {ne_step} elements; "
+    sample = (f"each step: {cores} workers x ({per} cell layers x {wl['m']}"
+              + (f" x {wl['m']}" if wl["dim"] == 3 else "") + f") slab of the workload = {ne_step} elements; "
               "numeric pass only, mesh + pattern prebuilt per worker")
     line = {
         "impl": "reference", "metric": "elements/s (fp64 P1 assembly into CSR)", "value": value, "unit": "elements/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "note": "reference has no host numeric pass; oracle port on all cores"},
-        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "note": "reference has no host numeric pass; oracle port on all host cores"},
+        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample,
+                         "flags": "-O3 -march=native" if native else "-O3 -march=x86-64-v2 -ffp-contract=off"},
         "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
+def run_extra(ctx, femx, torch, name, steps=20):
+    """A secondary configuration on one GPU (reported under `extra`, never the headline)."""
+    wl = WORKLOADS[name]
+    try:
+        mesh, slab = build_problem(ctx, femx, wl, 0, 1)
+        pat = femx.Pattern(ctx, mesh, nd=wl["nd"])
+        form = femx.Form(ctx, wl["dim"], getattr(femx, wl["form"]), nd=wl["nd"], params=wl["params"])
+        vals = torch.empty(pat.nnz, dtype=torch.float64, device=mesh.conn.device)
+        total_ms, per_launch, _ = time_numeric_pass(torch, form, pat, mesh, vals, steps, 3, torch.cuda.synchronize)
+        b_alg = algorithmic_bytes(mesh, pat, wl["dim"])
+        peak, _ = measured_peaks()
+        ms = sum(per_launch) / len(per_launch)
+        out = {"workload": wl["desc"], "elements": mesh.n_elems, "nnz": pat.nnz, "ms_per_step": ms,
+               "elements_per_s": mesh.n_elems / (ms * 1e-3), "nnz_per_s": pat.nnz / (ms * 1e-3),
+               "roofline_frac": b_alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": b_alg,
+               "numeric_pass": numeric_pass_kind(form)}
+        rp, ci = pat.csr("int64")
+        if wl["dim"] == 3:
+            out["parity"] = parity_vs_oracle(torch, wl, mesh, slab, pat, vals, rp, ci)
+            out["parity"]["note"] = UNPINNED
+        else:
+            out["ref_gpu_baseline"], out["parity"] = ref_gpu_baseline_and_parity(ctx, femx, torch, wl, mesh, pat, vals)
+        del rp, ci, vals
+        form.close(); pat.close()
+        del mesh
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:
+        return {"workload": wl["desc"], "error": repr(e)[:300]}
+
+
+def numeric_pass_kind(form):
+    src = form.source
+    if "#define FEMX_LATTICE 1" in src:
+        return "element-once lattice pass (class rows) + generic row list (boundary rows), one launch"
+    if "#define FEMX_SPEC 1" in src:
+        return "stencil-class pass (class rows) + generic row list, one launch"
+    return "generic owner-computes incidence loop"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="femx", choices=["femx", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=24)   # the 3-stream pipeline fills once inside the timed region
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cg", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=12)   # the 3-stream pipeline fills once inside the timed region
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -269,78 +442,79 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     ctx = femx.Context(local_rank)
-
-    # ---- this rank's slab of the (rows*world) x cols [x cols] mesh ---------------------
-    dim = wl["dim"]
-    rows_total = wl["rows"] * world
-    r0, r1 = slab_bounds(rows_total + 1, world, rank)
-    lo, hi = max(r0 - 1, 0), min(r1, rows_total)
-    if dim == 2:
-        plane = wl["cols"] + 1
-        mesh = ctx.rectangle_mesh(0.0, 1.0, 0.0, float(world), rows_total, wl["cols"], row_lo=lo, row_hi=hi)
-        ne_global = 2 * rows_total * wl["cols"]
-    else:
-        plane = (wl["cols"] + 1) ** 2
-        mesh = ctx.box_mesh(wl["cols"], wl["cols"], rows_total, hi=(1.0, 1.0, float(world)), k_lo=lo, k_hi=hi)
-        ne_global = 6 * rows_total * wl["cols"] ** 2
-    # symbolic pass (one-time per topology): built three times, the first calls also warm the allocator pools
-    pattern_ms = []
-    for _ in range(3):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        pat = femx.Pattern(ctx, mesh, row_begin=(r0 - lo) * plane, row_end=(r1 - lo) * plane, col_base=lo * plane)
-        torch.cuda.synchronize()
-        pattern_ms.append(1e3 * (time.perf_counter() - t0))
-        if len(pattern_ms) < 3:
-            pat.close()
-    t0 = time.perf_counter()
-    form = femx.Form(ctx, dim, getattr(femx, wl["form"]), params=(1.0,))
-    vals = torch.empty(pat.nnz, dtype=torch.float64, device=dev)
-    form.assemble_csr(pat, mesh, vals)
-    torch.cuda.synchronize()
-    jit_ms = 1e3 * (time.perf_counter() - t0)
-
-    # algorithmic bytes of THIS rank's launch: conn int32 + node coords fp64 read once,
-    # CSR values written once; no scatter map, no workspace.
-    b_alg = mesh.n_elems * mesh.nn * 4 + mesh.n_nodes * dim * 8 + pat.nnz * 8
+    dim, nd = wl["dim"], wl["nd"]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- this rank's slab of the FIXED global mesh (strong scaling) ----------------------
+    mesh, slab = build_problem(ctx, femx, wl, rank, world)
+    ne_global = slab["ne_global"]
+    # symbolic pass (one-time per topology): built three times, the first calls also warm the allocator pools
+    pattern_ms = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pat = femx.Pattern(ctx, mesh, nd=nd, row_begin=slab["row_begin"], row_end=slab["row_end"], col_base=slab["col_base"])
+        torch.cuda.synchronize()
+        pattern_ms.append(1e3 * (time.perf_counter() - t0))
+        if len(pattern_ms) < 3:
+            pat.close()
+    t0 = time.perf_counter()
+    form = femx.Form(ctx, dim, getattr(femx, wl["form"]), nd=nd, params=wl["params"])
+    vals = torch.empty(pat.nnz, dtype=torch.float64, device=dev)
+    form.assemble_csr(pat, mesh, vals)
+    torch.cuda.synchronize()
+    jit_ms = 1e3 * (time.perf_counter() - t0)
+    b_alg = algorithmic_bytes(mesh, pat, dim)          # of THIS rank's launch
+    nnz_global = sum_over_ranks(pat.nnz)
+
     # ---- device-resident throughput (`value`) ---------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        form.assemble_csr(pat, mesh, vals)
-    barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record()
-    for k in range(args.steps):
-        form.assemble_csr(pat, mesh, vals)   # ONE kernel launch (femx_csr) per step
-        ev[k + 1].record()
-    barrier()
-    clocks = sampler.stop()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_launch = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    ms_per_step = total_ms_max / args.steps
+    total_ms, per_launch, clocks = time_numeric_pass(torch, form, pat, mesh, vals, args.steps, args.warmup, barrier, sampler)
+    ms_per_step = max_over_ranks(total_ms) / args.steps
     value = ne_global / (ms_per_step * 1e-3)
+    kern_ms = sum(per_launch) / len(per_launch)
+
+    # ---- parity at the benchmarked size (outside every timed region) --------------------
+    rp, ci = pat.csr("int64")
+    if dim == 3:
+        parity = parity_vs_oracle(torch, wl, mesh, slab, pat, vals, rp, ci)
+        parity["note"] = UNPINNED
+        ref_gpu = None
+    else:
+        ref_gpu, parity = (ref_gpu_baseline_and_parity(ctx, femx, torch, wl, mesh, pat, vals) if world == 1 else (None, None))
+        if parity is None:
+            parity = parity_vs_oracle(torch, wl, mesh, slab, pat, vals, rp, ci)
+    parity["config"] = args.workload
+    parity_all_ok = sum_over_ranks(0.0 if parity.get("ok") else 1.0) == 0.0
+    checksum_dev = sum_over_ranks(float(vals.sum().item()))
+    del ci
 
     # ---- end to end through the C ABI with HOST buffers (`e2e`) -----------------------
-    # every step: H2D of the operator's inputs (coordinates + connectivity, pinned), the numeric
-    # pass, D2H of the CSR values.  The pattern (one-time symbolic pass) is reused.  Steps are
-    # double-buffered over three streams (H2D / numeric pass / D2H) the way a re-assembly loop
-    # would run: the D2H of step k overlaps the H2D of step k+1 (PCIe is full duplex).
-    h_in = [c.cpu().pin_memory() for c in mesh.node_xyz] + [mesh.conn.cpu().pin_memory()]
+    # every step: H2D of the operator's inputs (node coordinates, pinned; the connectivity is NOT re-uploaded: the
+    # numeric pass never reads it once the pattern exists), the numeric pass, D2H of the CSR values.  The pattern
+    # (one-time symbolic pass) is reused.  Steps are double-buffered over three streams (H2D / numeric pass / D2H) the
+    # way a re-assembly loop would run: the D2H of step k overlaps the H2D of step k+1 (PCIe is full duplex).
+    h_in = [c.cpu().pin_memory() for c in mesh.node_xyz]
     bufs = []
     for b_ in range(2):
-        d_in = [torch.empty_like(c) for c in mesh.node_xyz] + [torch.empty_like(mesh.conn)]
-        m_b = femx.Mesh(dim, d_in[-1], tuple(d_in[:-1]))
+        d_in = [torch.empty_like(c) for c in mesh.node_xyz]
+        m_b = femx.Mesh(dim, mesh.conn, tuple(d_in))
         bufs.append(dict(d_in=d_in, mesh=m_b, vals=torch.empty_like(vals),
                          h_out=torch.empty(pat.nnz, dtype=torch.float64).pin_memory(),
                          in_done=torch.cuda.Event(), comp_done=torch.cuda.Event(), out_done=torch.cuda.Event()))
@@ -375,57 +549,110 @@ def main():
     s_cmp.wait_stream(s_in)
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / args.e2e_steps
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.e2e_steps
     h_out = bufs[(args.e2e_steps - 1) % 2]["h_out"]
-    checksum = float(h_out.sum().item())
     e2e_ok = bool(torch.equal(h_out, vals.cpu()))      # the end-to-end result is the device-resident result
+    e2e_all_ok = sum_over_ranks(0.0 if e2e_ok else 1.0) == 0.0
+    h2d_total, d2h_total = sum_over_ranks(h2d), sum_over_ranks(d2h)
+    del bufs, h_in, h_out
+    torch.cuda.empty_cache()
+
+    # ---- validation of the assembled operator: SpMV + 100 CG iterations, NCCL halo exchange (configs[4]) --------
+    cg = None
+    if not args.no_cg and nd == 1:
+        try:
+            dd = femx.Dist.from_torch(ctx)
+            op = dd.operator(pat, vals)
+            ones = torch.ones(op.n_owned, dtype=torch.float64, device=dev)
+            b = op.spmv(ones)                       # b = A 1 (row sums: the mass of each hat function)
+            x = torch.empty_like(b)
+            y = torch.empty_like(b)
+            for _ in range(3):
+                op.spmv(ones, y)
+            barrier()
+            s0_, s1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0_.record()
+            for _ in range(20):
+                op.spmv(ones, y)
+            s1_.record()
+            barrier()
+            spmv_ms = max_over_ranks(s0_.elapsed_time(s1_)) / 20
+            op.cg(b, 5, x)                          # warm-up (graph capture)
+            barrier()
+            _, res, ms = op.cg(b, 100, x)
+            cg_ms = max_over_ranks(ms)
+            err1 = sum_over_ranks(float(((x - 1.0) ** 2).sum().item())) ** 0.5 / slab["nodes_global"] ** 0.5
+            cg = {"iterations": 100, "its_per_s": 100.0 / (cg_ms * 1e-3), "ms_total": cg_ms, "spmv_ms": spmv_ms,
+                  "spmv_nnz_per_s": nnz_global / (spmv_ms * 1e-3),
+                  "residual@0": float(res[0]), "residual@100": float(res[100]), "rms_error_vs_exact_solution_1": err1,
+                  "collectives_per_iteration": {"ncclSend/ncclRecv (grouped, halo of r)": 2 if world > 1 else 0,
+                                                "ncclAllReduce (2 doubles, fused)": 1 if world > 1 else 0},
+                  "interior_rows_overlap_halo": [op.interior_lo, op.interior_hi],
+                  "method": "Chronopoulos-Gear CG, iteration replayed from a CUDA graph, femx_dist_cg (C++ behind the C ABI)"}
+            op.close(); dd.close()
+            del ones, b, x, y
+        except Exception as e:
+            cg = {"error": repr(e)[:400]}
 
     peak, peak_src = measured_peaks()
     stencil = pat.stencil()
-    kern_ms = sum(per_launch) / len(per_launch)
     achieved = b_alg / (kern_ms * 1e-3) / 1e9
+    traffic, traffic_src = profiled_traffic(args.workload) if world == 1 else (None, None)
     line = {
         "metric": "elements/s (fp64 P1 assembly into CSR)",
         "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": wl["desc"] + (f", x{world} slabs along the row axis" if world > 1 else ""),
-            "elements": ne_global, "elements_per_gpu": mesh.n_elems, "nodes_per_gpu": mesh.n_nodes,
-            "nnz_per_gpu": pat.nnz, "parallelism": f"owned-row slabs x{world}, ghost elements, no collective",
+            "workload": wl["desc"] + (f", z-slabs over {world} GPUs" if world > 1 else ""),
+            "elements": ne_global, "elements_this_gpu": mesh.n_elems, "nodes_this_gpu": mesh.n_nodes,
+            "nnz_this_gpu": pat.nnz, "nnz": nnz_global,
+            "parallelism": f"owned node planes [{slab['r0']},{slab['r1']}) of {wl['n'] + 1} on rank {rank}; ghost cell layers, no collective in assembly",
             "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush" % (b_alg / 1e9),
             "timing": "CUDA events on the launching stream, max over ranks",
         },
-        "nnz_per_s": pat.nnz * world / (ms_per_step * 1e-3),
+        "nnz_per_s": nnz_global / (ms_per_step * 1e-3),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": profiled_traffic(args.workload) if world == 1 else None, "kernel": "femx_csr", "kernel_ms": kern_ms, "kernel_ms_min": per_launch[0],
-                     "algorithmic_bytes": b_alg, "peak_source": peak_src},
-        "e2e": {"value": ne_global / (e2e_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                "includes": "H2D coords+conn (pinned), numeric pass, D2H CSR values; pattern reused; double-buffered over 3 streams",
-                "matches_device_result": e2e_ok,
-                "checksum": checksum},
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "dram_frac": (traffic / (kern_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                     "kernel": "femx_csr", "kernel_ms": kern_ms, "kernel_ms_min": per_launch[0],
+                     "algorithmic_bytes": b_alg, "peak_source": peak_src,
+                     "note": "rank 0's launch; frac = algorithmic bytes / time / peak, dram_frac = profiled DRAM bytes / time / peak"},
+        "e2e": {"value": ne_global / (e2e_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": h2d_total,
+                "d2h_bytes_per_step": d2h_total, "ms_per_step": e2e_ms,
+                "h2d_GBps_per_gpu": h2d / (e2e_ms * 1e-3) / 1e9, "d2h_GBps_per_gpu": d2h / (e2e_ms * 1e-3) / 1e9,
+                "includes": "H2D node coordinates (pinned), numeric pass, D2H CSR values; pattern reused, connectivity not re-uploaded; double-buffered over 3 streams",
+                "matches_device_result": e2e_all_ok},
         "gpu_launches": args.steps,
         "clocks": clocks,
-        "numeric_pass": {"kind": "stencil-class" if stencil["rows"] * 2 >= pat.n_rows and os.environ.get("FEMX_SPEC", "1") != "0" else "generic",
-                         "class_rows": stencil["rows"], "rows": pat.n_rows, "class_incidences": stencil["n_incid"],
-                         "class_row_len": stencil["row_len"],
-                         "note": "class rows: JIT straight-line body, gathers at own node + constant offsets, no connectivity / scatter map read; "
-                                 "other rows: generic incidence loop in row-list CTAs of the same launch"},
+        "parity": dict(parity, all_ranks_ok=parity_all_ok),
+        "checksum": checksum_dev,
+        "numeric_pass": {"kind": numeric_pass_kind(form), "class_rows": stencil["rows"], "rows": pat.n_rows,
+                         "lattice": pat.lattice() is not None},
         "setup": {"pattern_build_ms": pattern_ms[-1], "pattern_build_first_call_ms": pattern_ms[0],
-                  "pattern_nnz_per_s": pat.nnz / (pattern_ms[-1] * 1e-3), "jit_plus_first_launch_ms": jit_ms, "pattern_bytes": pat.bytes},
+                  "pattern_nnz_per_s": pat.nnz / (pattern_ms[-1] * 1e-3), "jit_plus_first_launch_ms": jit_ms,
+                  "pattern_bytes": pat.bytes,
+                  "pattern_roofline": {"algorithmic_bytes": mesh.n_elems * mesh.nn * 4 + (pat.n_rows // nd + 1) * 8 + (pat.nnz // (nd * nd)) * 4,
+                                       "frac": (mesh.n_elems * mesh.nn * 4 + (pat.n_rows // nd + 1) * 8 + (pat.nnz // (nd * nd)) * 4)
+                                       / (pattern_ms[-1] * 1e-3) / 1e9 / peak}},
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rb = ref_gpu_baseline(ctx, wl, mesh, pat)
-        if rb:
-            line["ref_gpu_baseline"] = rb
-        line["cpu_baseline"] = {k: v for k, v in cpu_baseline_port(wl).items() if k != "seconds"}
+    if cg is not None:
+        line["cg"] = cg
+    form.close(); pat.close()
+    del vals, rp, mesh
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1:
+        if not args.no_extras:
+            line["extra"] = {name: run_extra(ctx, femx, torch, name) for name in ("cfg2", "cfg4") if name != args.workload}
+            if ref_gpu is None and "cfg2" in line["extra"]:
+                ref_gpu = line["extra"]["cfg2"].pop("ref_gpu_baseline", None)
+        if ref_gpu:
+            line["ref_gpu_baseline"] = ref_gpu
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_port(wl)
     if rank == 0:
         print(json.dumps(line))
-    form.close(); pat.close(); ctx.close()
+    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -110,12 +110,15 @@ bool femx_lattice_plan_make(const femx_form* f, const femx_lattice& L, int rlen,
     if (!reached[k]) return no("a class column is not a cell edge");
   // tile shape: (TX-1) x (TY-1) owned node columns per CTA; the owned counts should divide the interior
   // node counts (cn-1) as evenly as possible, the halo fraction is 1 - (TX-1)(TY-1)/(TX TY)
+  // Measured on cfg3 (profiles/r02_lattice_sweep.txt): the pass is latency-bound (3 warps per scheduler, ~160 registers),
+  // so small CTAs that de-synchronise win: 128 threads (8 x 16 columns, 7 x 15 owned), three CTAs per SM, beat 256 x 2
+  // and every one-CTA shape although their halo share is larger.
   int tx = K.lt_tx, ty = K.lt_ty;
   if (tx < 2 || ty < 2 || tx * ty > 1024) {
-    const int budget = 288;
+    const int budget = 128;
     double best = -1.0;
-    tx = ty = 16;
-    for (int a = 4; a <= 96; ++a)
+    tx = 8; ty = 16;
+    for (int a = 4; a <= 32; ++a)
       for (int b = 4; b <= 32; ++b) {
         if (a * b > budget) continue;
         const int threads = ((a * b + 31) / 32) * 32;
@@ -128,7 +131,7 @@ bool femx_lattice_plan_make(const femx_form* f, const femx_lattice& L, int rlen,
   plan->ty = ty;
   plan->threads = ((tx * ty + 31) / 32) * 32;
   plan->kc = K.lt_kc > 0 ? K.lt_kc : 32;
-  plan->minb = K.lt_minb > 0 ? K.lt_minb : (plan->threads <= 256 ? 2 : 1);
+  plan->minb = K.lt_minb > 0 ? K.lt_minb : std::max(1, std::min(8, 384 / plan->threads));
   plan->regs = K.lt_regs;
   plan->pf = K.lt_pf;
   plan->ok = true;

@@ -34,6 +34,32 @@ def lib():
     return _LIB
 
 
+_NATIVE = None
+NATIVE_FLAGS = "-O3 -march=native"
+
+
+def lib_native():
+    """The same source built with -O3 -march=native on THIS host (bench.py's CPU baseline legs only)."""
+    global _NATIVE
+    if _NATIVE is None:
+        # -march=native code must not travel between hosts: one build per CPU model
+        import hashlib
+        try:
+            model = [l for l in open("/proc/cpuinfo") if l.startswith(("model name", "flags"))][:2]
+        except OSError:
+            model = []
+        tag = hashlib.sha1("".join(model).encode()).hexdigest()[:12]
+        out = os.path.join(_HERE, "_native", tag)
+        os.makedirs(out, exist_ok=True)
+        so = os.path.join(out, "libfemx_oracle_native.so")
+        src = os.path.join(_HERE, "femx_oracle.c")
+        if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+            subprocess.check_call(["gcc"] + NATIVE_FLAGS.split() + ["-fPIC", "-std=c99", "-shared", "-o", so, src, "-lm"])
+        _NATIVE = C.CDLL(so)
+        _NATIVE.orc_pattern.restype = C.c_int64
+    return _NATIVE
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -148,11 +174,11 @@ def expand_pattern(nd, row_ptr, col_idx):
     return drp, dci
 
 
-def assemble_csr(form, dim, nd, conn, X, Y, Z, drow_ptr, dcol_idx, params=None):
+def assemble_csr(form, dim, nd, conn, X, Y, Z, drow_ptr, dcol_idx, params=None, native=False):
     conn = np.ascontiguousarray(conn, np.int32)
     vals = np.empty(int(drow_ptr[-1]))
     p = _params(params)
-    lib().orc_assemble_csr(form, dim, nd, _p(p), _i64(conn.shape[0]), _p(conn), _p(X),
+    (lib_native() if native else lib()).orc_assemble_csr(form, dim, nd, _p(p), _i64(conn.shape[0]), _p(conn), _p(X),
                            _p(Y), _p(Z), _p(drow_ptr), _p(dcol_idx),
                            _i64(len(drow_ptr) - 1), _p(vals))
     return vals

@@ -85,3 +85,25 @@ def test_halo_exchange_and_owned_rows_gloo(world, nR):
         p.join(120)
         assert p.exitcode == 0
     assert out.get(timeout=5) < 1e-12
+
+
+def test_c_abi_slab_equals_python_slab():
+    """femx_dist_slab (C++ multi-GPU layer) and femx.dist.make_slab (the gloo-tested host logic) agree."""
+    import femx
+    for world in (1, 2, 3, 4, 8):
+        for cells in (8, 64, 256, 257):
+            for r in range(world):
+                s = make_slab(r, world, cells, 10)
+                assert femx.dist_slab(cells + 1, world, r) == (s.r0, s.r1, s.lo, s.hi)
+    with pytest.raises(femx.FemxError):
+        femx.dist_slab(7, 9, 0)
+
+
+def test_dist_layer_needs_a_device():
+    """No CPU fallback: the communicator cannot be created without a context, and a context needs a GPU."""
+    import torch
+    import femx
+    if torch.cuda.is_available():
+        pytest.skip("CPU-tier check")
+    with pytest.raises(femx.FemxError):
+        femx.Context(0)

@@ -109,7 +109,7 @@ def test_lattice_pass_is_independent_of_tile_shape_and_chunk(ctx):
             v = form.assemble_csr(pat, mesh)
             assert torch.equal(v, ref), (tx, ty, kc, pf)
     finally:
-        for name, val in (("lt_tx", 0), ("lt_ty", 0), ("lt_kc", 0), ("lt_pf", 1)):
+        for name, val in (("lt_tx", 0), ("lt_ty", 0), ("lt_kc", 0), ("lt_pf", 0)):
             ctx.set_option(name, val)
     form.close(); pat.close()
 
