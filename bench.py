@@ -271,7 +271,7 @@ def cpu_baseline_port(wl, seconds_target=12.0):
     on this host."""
     from oracle import oracle as orc
     dim, m, nd = wl["dim"], wl["m"], wl["nd"]
-    layers = {2: min(wl["n"], 2048), 3: min(wl["n"], 12 if nd == 1 else 3)}[dim]
+    layers = {2: min(wl["n"], 4096), 3: min(wl["n"], 96 if nd == 1 else 16)}[dim]   # about 10-20 s of CPU work
     if dim == 2:
         X, Y, _, conn = orc.rect_mesh(0, 1, 0, 1, layers, m)
         Z = None

@@ -68,8 +68,9 @@ struct femx_dist {
   femx_ctx* ctx = nullptr;
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
-  cudaStream_t s_comm = nullptr;   // the halo travels here while interior rows are multiplied on the caller's stream
-  cudaEvent_t e_ready = nullptr, e_halo = nullptr;
+  cudaStream_t s_comm = nullptr;   // the halo travels here while interior rows are multiplied on the compute stream
+  cudaStream_t s_main = nullptr;   // compute stream of femx_dist_cg (a capturable stream: the caller's may be the legacy stream)
+  cudaEvent_t e_ready = nullptr, e_halo = nullptr, e_in = nullptr;
 };
 
 struct femx_dist_op {
@@ -293,6 +294,8 @@ int femx_dist_create(femx_ctx* ctx, int rank, int world, const void* h_id, femx_
     }
   }
   cudaError_t e = cudaStreamCreateWithFlags(&d->s_comm, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->s_main, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->e_in, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->e_ready, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->e_halo, cudaEventDisableTiming);
   if (e != cudaSuccess) {
@@ -307,6 +310,8 @@ void femx_dist_destroy(femx_dist* d) {
   if (!d) return;
   if (d->comm) get_nccl()->CommDestroy(d->comm);
   if (d->s_comm) cudaStreamDestroy(d->s_comm);
+  if (d->s_main) cudaStreamDestroy(d->s_main);
+  if (d->e_in) cudaEventDestroy(d->e_in);
   if (d->e_ready) cudaEventDestroy(d->e_ready);
   if (d->e_halo) cudaEventDestroy(d->e_halo);
   delete d;
@@ -449,7 +454,11 @@ int femx_dist_cg(femx_dist_op* op, const void* d_b_owned, void* d_x_owned, int i
   femx_dist* d = op->d;
   femx_ctx* ctx = d->ctx;
   FEMX_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t st = (cudaStream_t)stream;
+  // the solve runs on the layer's own stream, ordered after the caller's: the iteration is stream-captured, and the
+  // caller's stream may be the legacy default stream, which cannot be captured
+  FEMX_CUDA_OK(ctx, cudaEventRecord(d->e_in, (cudaStream_t)stream));
+  FEMX_CUDA_OK(ctx, cudaStreamWaitEvent(d->s_main, d->e_in, 0));
+  cudaStream_t st = d->s_main;
   const size_t es = esize(op->dtype);
   const int64_t n = op->n_owned;
   if (op->hist_cap < iters + 1) {

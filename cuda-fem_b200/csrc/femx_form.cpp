@@ -761,6 +761,8 @@ int compile_variant(femx_form* f, const std::string& kernel, Variant** outv, boo
       return femx_fail(f->ctx, FEMX_ERR_CUDA, "cuModuleGetFunction(%s): %s", entry.c_str(),
                        es ? es : "?");
     }
+    if (lat && drv->ModuleGetFunction(&v.fn2, v.module, "femx_rowlist") != CUDA_SUCCESS)
+      return femx_fail(f->ctx, FEMX_ERR_CUDA, "cuModuleGetFunction(femx_rowlist) failed");
   }
   if (outv) *outv = &v;
   return FEMX_OK;
@@ -1188,18 +1190,29 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
     lat.kc = plan.kc;
     const long long ntz = khi >= klo ? (khi - klo + 1 + plan.kc - 1) / plan.kc : 0;
     int n_list = (int)pat->n_other;
-    const size_t smem = std::max(plan.smem, (size_t)plan.threads * seg * rs);
+    const size_t smem = plan.smem;
     if (smem > form->ctx->smem_optin)
       return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED, "femx_assemble_csr: the lattice pass needs %zu B of shared memory (> %zu)",
                        smem, form->ctx->smem_optin);
     st = prepare(v, smem, plan.threads);
     if (st != FEMX_OK) return st;
-    void* args[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &n_rows,
-                    &row_node0, &lat, &rowlist, &n_list, &seg_arg};
-    const long long blocks = (long long)lat.ntx * lat.nty * ntz + (n_list + plan.threads - 1) / plan.threads;
+    void* args[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &n_rows, &row_node0, &lat};
+    const long long blocks = (long long)lat.ntx * lat.nty * ntz;
     if (blocks > 2147483647LL) return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED, "femx_assemble_csr: %lld blocks exceed the grid limit", blocks);
-    if (blocks == 0) return FEMX_OK;
-    cr = drv->LaunchKernel(v->fn, (unsigned)blocks, 1, 1, (unsigned)plan.threads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
+    cr = CUDA_SUCCESS;
+    if (blocks > 0)
+      cr = drv->LaunchKernel(v->fn, (unsigned)blocks, 1, 1, (unsigned)plan.threads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
+    if (cr == CUDA_SUCCESS && n_list > 0) {
+      // the rows outside the class: their own (small-register) kernel behind the lattice pass; disjoint rows
+      const size_t smem2 = (size_t)128 * seg * rs;
+      if (smem2 > 48 * 1024 && (int)smem2 > v->smem2_set) {
+        if (drv->FuncSetAttribute(v->fn2, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem2) != CUDA_SUCCESS)
+          return femx_fail(form->ctx, FEMX_ERR_CUDA, "cuFuncSetAttribute(smem=%zu) failed", smem2);
+        v->smem2_set = (int)smem2;
+      }
+      void* args2[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &rowlist, &n_list, &seg_arg};
+      cr = drv->LaunchKernel(v->fn2, (unsigned)((n_list + 127) / 128), 1, 1, 128, 1, 1, (unsigned)smem2, (CUstream)stream, args2, nullptr);
+    }
   } else {
     if (spec) {
       sc.np = pat->spec_np; sc.rlen = pat->spec_rlen; sc.self = pat->spec_self;

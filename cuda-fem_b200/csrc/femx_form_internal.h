@@ -13,7 +13,8 @@ struct femx_variant {
   std::vector<char> cubin;
   CUmodule module = nullptr;
   CUfunction fn = nullptr;
-  int smem_set = 0;
+  CUfunction fn2 = nullptr;  // lattice variants: femx_rowlist (the rows outside the class)
+  int smem_set = 0, smem2_set = 0;
   int carveout_set = 0;
   size_t lt_smem = 0;  // lattice variants: dynamic shared memory the generated kernel needs
   int lt_nslot = 0;

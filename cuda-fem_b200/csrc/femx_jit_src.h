@@ -621,12 +621,16 @@ static const char* const kFemxJitLattice = R"FEMX(
 // [k0, k1).  Thread (ix, iy) holds the column with lower-corner node (i, j): per plane it evaluates the cell
 // (i, j, kc) — its P elements, each ONCE — reduces them to one value per cell edge and one Jacobian sum per
 // corner, adds what the cell below left for the shared plane (register carry), and publishes the sums other
-// columns need ("fields") to shared memory.  After the barrier the thread gathers the values of row (i, j, kc):
-// each off-diagonal entry is the sum of the fields of the cells around its edge, the diagonal follows from the
-// zero row sum of the stiffness part.  Rows go to a shared-memory image and leave through one bulk store per
-// run of consecutive class rows.  Column ix = 0 / iy = 0 is the halo (cells only, no rows).  Rows outside the
-// stencil class (the mesh boundary) are taken by row-list CTAs with the generic incidence loop, as in the
-// stencil-class kernel.
+// columns need ("fields") to shared memory.  The values of row (i, j, kc) are then gathered: each off-diagonal
+// entry is the sum of the fields of the cells around its edge, the diagonal follows from the zero row sum of
+// the stiffness part.  Rows go to a shared-memory image and leave through one bulk store per run of consecutive
+// class rows.  Column ix = 0 / iy = 0 is the halo (cells only, no rows).
+// The columns of a CTA are not kept in lock step: publishing plane kc ARRIVES on an mbarrier, the gather of that
+// plane WAITS on it one cell later (after the arithmetic of cell kc+1) — by then the phase has normally completed,
+// so warps drift up to one plane apart and one warp's gather overlaps another's arithmetic.  Field buffers are 2 /
+// 3 planes deep accordingly (femx_lattice.cpp).  A line of the tile lies inside one warp (FEMX_LT_TX divides 32),
+// so a run of rows is completed, fenced and stored warp-locally (__syncwarp, no CTA barrier).
+// Rows outside the stencil class (the mesh boundary) are taken by femx_rowlist (generic incidence loop).
 struct femx_lat {
   int cnx, cny, cnz;  // cells per axis
   int sy, sz;         // node strides (x stride 1)
@@ -636,11 +640,9 @@ struct femx_lat {
   int kc;             // node planes per CTA
 };
 #define LT_NT FEMX_TILE_NODES
-#define LT_F(SLOT) (lt_F + (SLOT) * LT_NT)
 #ifndef FEMX_HOST_EMU
 #define FEMX_TID ((int)threadIdx.x)
 #define FEMX_BID ((int)blockIdx.x)
-#define FEMX_LT_SYNC() __syncthreads()
 #define FEMX_LT_KERNEL extern "C" __global__ void __launch_bounds__(LT_NT, FEMX_LT_MINB)
 __device__ __forceinline__ void femx_lt_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void femx_lt_bulk_store(real* dst, const real* src, unsigned bytes) {
@@ -650,6 +652,26 @@ __device__ __forceinline__ void femx_lt_bulk_store(real* dst, const real* src, u
 }
 __device__ __forceinline__ void femx_lt_bulk_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void femx_lt_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void femx_lt_bar_init(void* bar, int count) {
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void femx_lt_bar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void femx_lt_bar_wait(void* bar, int parity) {
+  unsigned done;
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void femx_lt_syncwarp() { __syncwarp(); }
+__device__ __forceinline__ unsigned femx_lt_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
 #endif
 
 #define LT_LOAD_PLANE(K, A, B, C, D)                                                          \
@@ -662,7 +684,6 @@ __device__ __forceinline__ void femx_lt_prefetch(const void* p) { asm volatile("
     cz##A = __ldg(Z + p_); cz##B = __ldg(Z + p_ + FEMX_CS);                                   \
     cz##C = __ldg(Z + q_); cz##D = __ldg(Z + q_ + FEMX_CS);                                   \
   }
-
 #define LT_PREFETCH_PLANE(K)                                                                   \
   {                                                                                           \
     const i64 p_ = (i64)(nb + (K) * lat.sz) * FEMX_CS, q_ = p_ + (i64)lat.sy * FEMX_CS;       \
@@ -671,38 +692,71 @@ __device__ __forceinline__ void femx_lt_prefetch(const void* p) { asm volatile("
     femx_lt_prefetch(Z + p_); femx_lt_prefetch(Z + p_ + FEMX_CS); femx_lt_prefetch(Z + q_); femx_lt_prefetch(Z + q_ + FEMX_CS); \
   }
 
+// Gather + store of one node plane: `mine` rows take their values from the field buffers (GS / GD of the plane, GP of
+// the plane below), place them in the image with the 16-byte phase of their global address, and the first row of
+// every run of consecutive class rows (found by ballot inside the line's warp) issues one bulk store for the run.
+#define LT_GATHER_PLANE(MINE, R0, GS, GD, GP)                                                                     \
+  {                                                                                                               \
+    femx_lt_bulk_wait(); /* this warp's bulk stores of the previous plane have read the image */                  \
+    femx_lt_syncwarp();                                                                                           \
+    real* lt_row = lt_img + t * FEMX_LT_RLEN + (((R0).x - t * FEMX_LT_RLEN) & (FEMX_EPV - 1));                     \
+    if (MINE) { FEMX_LT_GATHER(GS, GD, GP) }                                                                      \
+    femx_lt_fence();                                                                                              \
+    const unsigned lt_m = femx_lt_ballot(MINE);                                                                   \
+    const unsigned lt_line = (lt_m >> ((t & 31) - ix)) & ((FEMX_LT_TX == 32) ? 0xffffffffu : ((1u << FEMX_LT_TX) - 1u)); \
+    if ((MINE) && (ix == 0 || !((lt_line >> (ix - 1)) & 1u))) {                                                   \
+      const unsigned z_ = ~(lt_line >> ix);                                                                       \
+      const int len = z_ ? __ffs(z_) - 1 : 32 - ix;                                                               \
+      const int n_ = len * FEMX_LT_RLEN;                                                                          \
+      real* dst = vals + (i64)(R0).x;                                                                             \
+      const real* src = lt_row;                                                                                   \
+      const int head = min(n_, (FEMX_EPV - (int)((R0).x & (FEMX_EPV - 1))) & (FEMX_EPV - 1));                     \
+      const int mid = (n_ - head) & ~(FEMX_EPV - 1);                                                              \
+      if (mid > 0) femx_lt_bulk_store(dst + head, src + head, (unsigned)(mid * sizeof(real)));                    \
+      for (int q = 0; q < head; ++q) dst[q] = src[q]; /* ragged ends: < 16 bytes each */                          \
+      for (int q = head + mid; q < n_; ++q) dst[q] = src[q];                                                      \
+    }                                                                                                             \
+  }
+
+#ifndef FEMX_HOST_EMU
+// ---- the rows OUTSIDE the class (the mesh boundary): compacted list, one thread each, generic incidence loop.
+// A kernel of its own (launched behind the lattice pass on the same stream): it needs 40 registers, not the 168 of the
+// lattice pass — as CTAs of that kernel these rows held a sixth of its SM slots while stalling on dependent gathers.
+extern "C" __global__ void __launch_bounds__(128)
+femx_rowlist(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
+             const int* __restrict__ col_loc, const unsigned* __restrict__ sell_code,
+             const int* __restrict__ sell_elem, const real* __restrict__ X,
+             const real* __restrict__ Y, const real* __restrict__ Z, const i64 cs,
+             real* __restrict__ vals, const int* __restrict__ rowlist, const int n_list, const int seg) {
+  extern __shared__ __align__(128) unsigned char femx_smem[];
+  const int k_ = blockIdx.x * 128 + threadIdx.x;
+  if (k_ >= n_list) return;
+  const int row = __ldg(rowlist + k_);
+  const int2 r0 = __ldg(&rowinfo[row]);
+  const int rlen = __ldg(&rowinfo[row + 1].x) - r0.x;
+  const int np = r0.y & FEMX_NP_MASK;
+  real* srow = reinterpret_cast<real*>(femx_smem) + (size_t)threadIdx.x * seg;
+  if (np > 0) {
+    const int sp = __ldg(slice_ptr + (row >> 5)) + (row & 31);
+    femx_generic_row(r0, np, rlen * ND, srow, sell_code + sp, col_loc + r0.x, sell_elem + sp, X, Y, Z, cs);
+    real* dst = vals + (i64)r0.x * (ND * ND);
+    for (int j = 0; j < rlen * (ND * ND); ++j) dst[j] = srow[j];
+  }
+}
+#endif
+
 FEMX_LT_KERNEL
 femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
          const int* __restrict__ col_loc, const unsigned* __restrict__ sell_code,
          const int* __restrict__ sell_elem, const real* __restrict__ X,
          const real* __restrict__ Y, const real* __restrict__ Z, const i64 cs,
-         real* __restrict__ vals, const int n_rows, const int row_node0, const femx_lat lat,
-         const int* __restrict__ rowlist, const int n_list, const int seg) {
+         real* __restrict__ vals, const int n_rows, const int row_node0, const femx_lat lat) {
 #ifndef FEMX_HOST_EMU
   extern __shared__ __align__(128) unsigned char femx_smem[];
-  // ---- the first CTAs take the rows OUTSIDE the class: compacted list, one thread each, generic loop
-  const int n_lb = (n_list + LT_NT - 1) / LT_NT;
-  if (FEMX_BID < n_lb) {
-    const int k_ = FEMX_BID * LT_NT + FEMX_TID;
-    if (k_ >= n_list) return;
-    const int row = __ldg(rowlist + k_);
-    const int2 r0 = __ldg(&rowinfo[row]);
-    const int rlen = __ldg(&rowinfo[row + 1].x) - r0.x;
-    const int np = r0.y & FEMX_NP_MASK;
-    real* srow = reinterpret_cast<real*>(femx_smem) + (size_t)FEMX_TID * seg;
-    if (np > 0) {
-      const int sp = __ldg(slice_ptr + (row >> 5)) + (row & 31);
-      femx_generic_row(r0, np, rlen * ND, srow, sell_code + sp, col_loc + r0.x, sell_elem + sp, X, Y, Z, cs);
-      real* dst = vals + (i64)r0.x * (ND * ND);
-      for (int j = 0; j < rlen * (ND * ND); ++j) dst[j] = srow[j];
-    }
-    return;
-  }
-  const int b = FEMX_BID - n_lb;
 #else
   unsigned char* femx_smem = femx_emu_smem();
-  const int b = FEMX_BID;
 #endif
+  const int b = FEMX_BID;
   const int t = FEMX_TID;
   const int tx = b % lat.ntx, ty = (b / lat.ntx) % lat.nty, tz = b / (lat.ntx * lat.nty);
   const int ix = t % FEMX_LT_TX, iy = t / FEMX_LT_TX;
@@ -711,9 +765,11 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   const int i = min(iu, lat.cnx - 1), j = min(ju, lat.cny - 1);
   const bool own_col = ix >= 1 && iy >= 1 && iy < FEMX_LT_TY && iu < lat.cnx && ju < lat.cny;
   const int k0 = lat.klo + tz * lat.kc, k1 = min(k0 + lat.kc, lat.khi + 1);
-  real* lt_F = reinterpret_cast<real*>(femx_smem);                                          // fields [FEMX_LT_NSLOT][LT_NT]
-  real* lt_img = lt_F + FEMX_LT_NSLOT * LT_NT;                                              // value image [LT_NT][RLEN] (+ phase slack)
-  unsigned char* lt_cls = reinterpret_cast<unsigned char*>(lt_img + LT_NT * FEMX_LT_RLEN + 4);  // class flag per thread
+  void* lt_bar = femx_smem;                                                                   // mbarrier (128-byte header)
+  real* lt_FS = reinterpret_cast<real*>(femx_smem + 128) + t;                                 // 2-deep fields [f][2][LT_NT]
+  real* lt_FD = lt_FS + 2 * FEMX_LT_NS * LT_NT;                                               // 3-deep fields [f][3][LT_NT]
+  real* lt_img = reinterpret_cast<real*>(femx_smem + 128) + FEMX_LT_NSLOT * LT_NT;            // value image [LT_NT][RLEN] (+ phase slack)
+  femx_lt_bar_init(lt_bar, LT_NT);
   const int nb = lat.node0 + i + j * lat.sy;  // node id of the column at plane 0
   // corner c = dx | dy << 1 | dz << 2 of the current cell: c0..c3 on node plane kc, c4..c7 on plane kc + 1
   real cx0, cx1, cx2, cx3, cx4, cx5, cx6, cx7, cy0, cy1, cy2, cy3, cy4, cy5, cy6, cy7, cz0, cz1, cz2, cz3, cz4, cz5, cz6, cz7;
@@ -724,14 +780,16 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   LT_LOAD_PLANE(k0, 4, 5, 6, 7)
 #endif
   FEMX_LT_CARRY_DECL
+  int2 r0p = make_int2(0, 0);   // metadata of the row one plane below (gathered one cell late)
+  bool minep = false;
+  int b2 = 0, b3 = 0;           // buffer of plane kc: (kc - k0 + 1) & 1 and % 3
   for (int kc = k0 - 1; kc < k1; ++kc) {
-    const int par = kc & 1;
 #if FEMX_LT_PF
     // the top plane was prefetched into L1 one cell ago; the plane after it is requested now
     LT_LOAD_PLANE(kc + 1, 4, 5, 6, 7)
     if (kc + 1 < k1) LT_PREFETCH_PLANE(kc + 2)
 #endif
-    // metadata of row (i, j, kc): needed after the cell, issued before it
+    // metadata of row (i, j, kc): needed when the plane is gathered, issued before the cell
     const int row = nb + kc * lat.sz - row_node0;
     const bool rowok = own_col && kc >= k0 && row >= 0 && row < n_rows;
     int2 r0 = make_int2(0, 0);
@@ -745,31 +803,27 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
 #endif
     FEMX_LT_CELL
     FEMX_LT_FIELDS
-    femx_lt_bulk_wait();  // the bulk stores of the previous plane have read the image
-    if (kc >= k0) { FEMX_LT_PUBLISH(par) } else { FEMX_LT_PUBLISH_UP(par) }
-    FEMX_LT_SYNC();
     if (kc >= k0) {
-      const bool mine = rowok && (r0.y & FEMX_ROW_SPEC);
-      // the row's place in the image carries the 16-byte phase of its global address (aligned bulk stores);
-      // the phase is the same for all rows of a run of consecutive class rows
-      real* lt_row = lt_img + t * FEMX_LT_RLEN + ((r0.x - t * FEMX_LT_RLEN) & (FEMX_EPV - 1));
-      if (mine) { FEMX_LT_GATHER(par) }
-      lt_cls[t] = mine ? 1 : 0;
-      femx_lt_fence();
-      FEMX_LT_SYNC();
-      if (mine && (ix == 1 || !lt_cls[t - 1])) {  // first row of a run: one bulk store for the whole run
-        int len = 1;
-        while (ix + len < FEMX_LT_TX && lt_cls[t + len]) ++len;
-        const int n = len * FEMX_LT_RLEN;
-        real* dst = vals + (i64)r0.x;
-        const real* src = lt_row;
-        const int head = min(n, (FEMX_EPV - (int)(r0.x & (FEMX_EPV - 1))) & (FEMX_EPV - 1));
-        const int mid = (n - head) & ~(FEMX_EPV - 1);
-        if (mid > 0) femx_lt_bulk_store(dst + head, src + head, (unsigned)(mid * sizeof(real)));
-        for (int q = 0; q < head; ++q) dst[q] = src[q];  // ragged ends: < 16 bytes each
-        for (int q = head + mid; q < n; ++q) dst[q] = src[q];
+      // every column has published plane kc - 1 (arrived one cell ago): gather it while slower warps still compute
+      femx_lt_bar_wait(lt_bar, (kc - k0) & 1);
+      if (kc > k0) {
+        const int p3 = b3 == 0 ? 2 : b3 - 1, q3 = p3 == 0 ? 2 : p3 - 1;   // 3-deep buffers of planes kc-1, kc-2
+        LT_GATHER_PLANE(minep, r0p, lt_FS + (b2 ^ 1) * LT_NT, lt_FD + p3 * LT_NT, lt_FD + q3 * LT_NT)
       }
+      FEMX_LT_PUBLISH(lt_FS + b2 * LT_NT, lt_FD + b3 * LT_NT)
+    } else {
+      FEMX_LT_PUBLISH_UP(lt_FD + b3 * LT_NT)
     }
+    femx_lt_bar_arrive(lt_bar);
+    r0p = r0;
+    minep = rowok && (r0.y & FEMX_ROW_SPEC);
+    b2 ^= 1;
+    b3 = b3 == 2 ? 0 : b3 + 1;
+  }
+  {  // the last plane
+    femx_lt_bar_wait(lt_bar, (k1 - k0) & 1);
+    const int p3 = b3 == 0 ? 2 : b3 - 1, q3 = p3 == 0 ? 2 : p3 - 1;
+    LT_GATHER_PLANE(minep, r0p, lt_FS + (b2 ^ 1) * LT_NT, lt_FD + p3 * LT_NT, lt_FD + q3 * LT_NT)
   }
   femx_lt_bulk_wait();
 }

@@ -114,12 +114,12 @@ bool femx_lattice_plan_make(const femx_form* f, const femx_lattice& L, int rlen,
   // so small CTAs that de-synchronise win: 128 threads (8 x 16 columns, 7 x 15 owned), three CTAs per SM, beat 256 x 2
   // and every one-CTA shape although their halo share is larger.
   int tx = K.lt_tx, ty = K.lt_ty;
-  if (tx < 2 || ty < 2 || tx * ty > 1024) {
+  if (tx < 2 || ty < 2 || tx * ty > 1024 || 32 % tx) {
     const int budget = 128;
     double best = -1.0;
     tx = 8; ty = 16;
-    for (int a = 4; a <= 32; ++a)
-      for (int b = 4; b <= 32; ++b) {
+    for (int a = 4; a <= 32; a *= 2)   // a line of the tile lies inside one warp (runs of rows are stored warp-locally)
+      for (int b = 3; b <= 32; ++b) {
         if (a * b > budget) continue;
         const int threads = ((a * b + 31) / 32) * 32;
         const long long tiles_x = (std::max(L.cn[0] - 1, 1) + a - 2) / (a - 1), tiles_y = (std::max(L.cn[1] - 1, 1) + b - 2) / (b - 1);
@@ -314,9 +314,13 @@ std::string femx_lattice_defines(const femx_form* f, const femx_lattice& L, femx
   }
   for (auto& e : entry) std::sort(e.begin(), e.end(), [](const Ref& a, const Ref& b) { return a.f != b.f ? a.f < b.f : a.prev < b.prev; });
   std::sort(jref.begin(), jref.end(), [](const Ref& a, const Ref& b) { return a.f < b.f; });
-  int nslot = 0;
-  for (auto& fl : fields) { fl.slot = nslot; nslot += fl.dbl ? 2 : 1; }
-  plan->nslot = nslot;
+  // shared-memory slots.  The columns of a CTA are NOT in lock step (split-phase barrier: a thread gathers plane
+  // kc-1 one cell after it published it), so a field published for plane kc must survive until the slowest thread
+  // has gathered plane kc: fields read only by their own plane's gather are kept 2 deep (index kc & 1), fields also
+  // read by the downward entries of the next plane 3 deep (index kc % 3).  Slot = index within the kind * depth + buffer.
+  int ns = 0, ndb = 0;
+  for (auto& fl : fields) fl.slot = fl.dbl ? ndb++ : ns++;
+  plan->nslot = 2 * ns + 3 * ndb;
 
   auto tname = [&](const Field& fl, const Term& tm) {
     if (fl.jac) return std::string(tm.sz ? "Cj" : "Jc") + std::to_string(tm.id);
@@ -342,24 +346,26 @@ std::string femx_lattice_defines(const femx_form* f, const femx_lattice& L, femx
   }
   o << " \\\n   ";
   for (auto& c : carry) o << " " << c.first << " = " << c.second << ";";
-  o << "\n#define FEMX_LT_PUBLISH(PAR)";
+  // PS / PD: this thread's element of the 2-deep / 3-deep buffer of the plane being published
+  auto slot_off = [&](const Field& fl) {
+    return std::to_string(fl.slot * (fl.dbl ? 3 : 2)) + " * LT_NT";
+  };
+  o << "\n#define FEMX_LT_PUBLISH(PS, PD)";
   for (size_t k = 0; k < fields.size(); ++k)
-    o << " \\\n    LT_F(" << fields[k].slot << (fields[k].dbl ? " + (PAR)" : "") << ")[t] = Fv" << k << ";";
-  o << "\n#define FEMX_LT_PUBLISH_UP(PAR)";
+    o << " \\\n    (" << (fields[k].dbl ? "PD" : "PS") << ")[" << slot_off(fields[k]) << "] = Fv" << k << ";";
+  o << "\n#define FEMX_LT_PUBLISH_UP(PD)";
   for (size_t k = 0; k < fields.size(); ++k)
-    if (fields[k].dbl) o << " \\\n    LT_F(" << fields[k].slot << " + (PAR))[t] = Fv" << k << ";";
+    if (fields[k].dbl) o << " \\\n    (PD)[" << slot_off(fields[k]) << "] = Fv" << k << ";";
+  // GS / GD: the gathered plane's buffers, GP: the 3-deep buffer of the plane below it
   auto refstr = [&](const Ref& r) {
     std::ostringstream s;
-    if (!r.prev && r.sx == 0 && r.sy == 0) { s << "Fv" << r.f; return s.str(); }
-    s << "LT_F(" << fields[r.f].slot;
-    if (fields[r.f].dbl) s << (r.prev ? " + ((PAR) ^ 1)" : " + (PAR)");
-    s << ")[t";
+    s << "(" << (r.prev ? "GP" : (fields[r.f].dbl ? "GD" : "GS")) << ")[" << slot_off(fields[r.f]);
     if (r.sx) s << " - 1";
     if (r.sy) s << " - FEMX_LT_TX";
     s << "]";
     return s.str();
   };
-  o << "\n#define FEMX_LT_GATHER(PAR)";
+  o << "\n#define FEMX_LT_GATHER(GS, GD, GP)";
   for (int p = 0; p < plan->rlen; ++p) {
     if (p == plan->self) continue;
     o << " \\\n    const real v" << p << " = ";
@@ -372,10 +378,11 @@ std::string femx_lattice_defines(const femx_form* f, const femx_lattice& L, femx
   for (int p = 0; p < plan->rlen; ++p)
     if (p != plan->self) o << " S_ += v" << p << ";";
   o << " lt_row[" << plan->self << "] = fma(" << lnum(f->lt_cj) << ", SJ, -S_); }\n";
+  o << "#define FEMX_LT_NS " << ns << "\n";
   o << "#define FEMX_LT_TX " << plan->tx << "\n#define FEMX_LT_TY " << plan->ty << "\n#define FEMX_LT_NSLOT " << plan->nslot
     << "\n#define FEMX_LT_RLEN " << plan->rlen << "\n#define FEMX_LT_MINB " << plan->minb << "\n#define FEMX_LT_PF " << plan->pf << "\n#define FEMX_LATTICE 1\n";
-  // bytes of dynamic shared memory: fields | value image (+ alignment slack) | class flags
+  // bytes of dynamic shared memory: mbarrier (128 B) | fields | value image (+ alignment slack)
   const size_t rs = f->dtype == FEMX_F32 ? 4 : 8;
-  plan->smem = ((size_t)plan->nslot * plan->threads + (size_t)plan->threads * plan->rlen + 4) * rs + plan->threads + 16;
+  plan->smem = 128 + ((size_t)plan->nslot * plan->threads + (size_t)plan->threads * plan->rlen + 4) * rs + 16;
   return o.str();
 }

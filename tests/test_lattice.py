@@ -103,7 +103,7 @@ def test_lattice_pass_is_independent_of_tile_shape_and_chunk(ctx):
     form = femx.Form(ctx, 3, femx.POISSON_MASS)
     ref = form.assemble_csr(pat, mesh).clone()
     try:
-        for tx, ty, kc, pf in ((4, 4, 1, 1), (32, 8, 5, 0), (6, 30, 100, 1), (16, 16, 3, 0)):
+        for tx, ty, kc, pf in ((4, 4, 1, 1), (32, 8, 5, 0), (8, 30, 100, 1), (16, 16, 3, 0), (2, 9, 4, 0)):
             for name, val in (("lt_tx", tx), ("lt_ty", ty), ("lt_kc", kc), ("lt_pf", pf)):
                 ctx.set_option(name, val)
             v = form.assemble_csr(pat, mesh)

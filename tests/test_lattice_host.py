@@ -25,6 +25,7 @@ HARNESS_PRE = r'''
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <optional>
 #include <thread>
 #include <vector>
 using std::max;
@@ -42,15 +43,30 @@ static inline float femx_rcp(float a) { return 1.0f / a; }
 static thread_local int emu_tid = 0;
 static int emu_bid = 0;
 static unsigned char* emu_smem = nullptr;
-static std::barrier<>* emu_bar = nullptr;
+static std::barrier<>* emu_bar = nullptr;              // the CTA's mbarrier: split arrive / wait
+static std::vector<std::barrier<>*> emu_warp_bar;       // __syncwarp
+static std::vector<int> emu_flags;                      // ballot scratch
+static thread_local std::optional<std::barrier<>::arrival_token> emu_tok;
 #define FEMX_TID emu_tid
 #define FEMX_BID emu_bid
-#define FEMX_LT_SYNC() emu_bar->arrive_and_wait()
 #define FEMX_LT_KERNEL static void
 static inline unsigned char* femx_emu_smem() { return emu_smem; }
 static inline void femx_lt_fence() {}
 static inline void femx_lt_bulk_wait() {}
 static inline void femx_lt_prefetch(const void*) {}
+static inline void femx_lt_bar_init(void*, int) {}
+static inline void femx_lt_bar_arrive(void*) { emu_tok.emplace(emu_bar->arrive()); }
+static inline void femx_lt_bar_wait(void*, int) { emu_bar->wait(std::move(*emu_tok)); emu_tok.reset(); }
+static inline void femx_lt_syncwarp() { emu_warp_bar[emu_tid >> 5]->arrive_and_wait(); }
+static inline unsigned femx_lt_ballot(int pred) {
+  emu_flags[emu_tid] = pred ? 1 : 0;
+  femx_lt_syncwarp();
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) m |= (unsigned)emu_flags[(emu_tid & ~31) + l] << l;
+  femx_lt_syncwarp();
+  return m;
+}
+static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 '''
 
 HARNESS_POST = r'''
@@ -95,12 +111,16 @@ int main(int argc, char** argv) {
     emu_bid = b;
     std::barrier<> bar(LT_NT);
     emu_bar = &bar;
+    emu_flags.assign(LT_NT, 0);
+    for (auto* w : emu_warp_bar) delete w;
+    emu_warp_bar.clear();
+    for (int w = 0; w < LT_NT / 32; ++w) emu_warp_bar.push_back(new std::barrier<>(32));
     std::vector<std::thread> th;
     for (int t = 0; t < LT_NT; ++t)
       th.emplace_back([&, t] {
         emu_tid = t;
         femx_csr(rowinfo.data(), nullptr, nullptr, nullptr, nullptr, C[0].data(), C[1].data(), C[2].data(), 1, vals,
-                 n_rows, row0, lat, nullptr, 0, 0);
+                 n_rows, row0, lat);
       });
     for (auto& x : th) x.join();
   }
@@ -171,7 +191,7 @@ def run_emu(tmp_path, builtin, dims, tile, kc, dtype=femx.F64, row_range=None):
 
 
 @pytest.mark.parametrize("builtin", ["POISSON_MASS", "POISSON", "MASS"])
-@pytest.mark.parametrize("dims,tile,kc", [((6, 5, 4), (4, 3), 2), ((9, 7, 5), (6, 5), 8), ((5, 5, 6), (16, 16), 3)])
+@pytest.mark.parametrize("dims,tile,kc", [((6, 5, 4), (4, 3), 2), ((9, 7, 5), (8, 5), 8), ((5, 5, 6), (16, 16), 3), ((40, 3, 3), (32, 3), 1)])
 def test_lattice_pass_on_host_equals_oracle(tmp_path, builtin, dims, tile, kc):
     got, ref, rp, ci, inner, _ = run_emu(tmp_path, builtin, dims, tile, kc)
     rows = np.flatnonzero(inner)
@@ -204,7 +224,7 @@ def test_lattice_pass_on_host_slab_rows(tmp_path):
 
 
 def test_lattice_pass_on_host_fp32(tmp_path):
-    got, ref, rp, ci, inner, _ = run_emu(tmp_path, "POISSON_MASS", (6, 6, 4), (5, 4), 4, dtype=femx.F32)
+    got, ref, rp, ci, inner, _ = run_emu(tmp_path, "POISSON_MASS", (6, 6, 4), (8, 4), 4, dtype=femx.F32)
     rows = np.flatnonzero(inner)
     mask = np.zeros(len(ref), bool)
     for r in rows:

@@ -14,24 +14,23 @@ import femx  # noqa: E402
 CONFIGS = [
     dict(lattice=0),
     dict(),
-    dict(lt_tx=8, lt_ty=16, lt_minb=3),
-    dict(lt_tx=8, lt_ty=16, lt_minb=3, rcp3=1),
-    dict(lt_tx=8, lt_ty=16, lt_minb=4),
-    dict(lt_tx=16, lt_ty=8, lt_minb=3),
+    dict(lt_pf=1),
+    dict(lt_minb=2),
+    dict(lt_minb=4),
+    dict(lt_tx=16, lt_ty=8),
+    dict(lt_tx=8, lt_ty=12),
     dict(lt_tx=8, lt_ty=8, lt_minb=6),
     dict(lt_tx=8, lt_ty=8, lt_minb=5),
-    dict(lt_tx=6, lt_ty=16, lt_minb=4),
-    dict(lt_tx=12, lt_ty=8, lt_minb=4),
-    dict(lt_tx=8, lt_ty=12, lt_minb=4),
-    dict(lt_tx=8, lt_ty=12, lt_minb=3),
     dict(lt_tx=4, lt_ty=16, lt_minb=6),
-    dict(lt_tx=8, lt_ty=16, lt_minb=3, lt_pf=0),
-    dict(lt_tx=8, lt_ty=16, lt_minb=3, lt_kc=64),
-    dict(lt_tx=8, lt_ty=16, lt_minb=3, lt_kc=16),
-    dict(lt_tx=8, lt_ty=16, lt_minb=3, carveout=100),
-    dict(lt_tx=8, lt_ty=16, lt_minb=3, carveout=75),
+    dict(lt_tx=8, lt_ty=24, lt_minb=2),
+    dict(lt_tx=16, lt_ty=16, lt_minb=1),
     dict(lt_tx=16, lt_ty=16, lt_minb=2),
-    dict(lt_tx=12, lt_ty=16, lt_minb=2)]
+    dict(lt_tx=8, lt_ty=32, lt_minb=1),
+    dict(lt_tx=32, lt_ty=8, lt_minb=1),
+    dict(lt_kc=64),
+    dict(lt_kc=16),
+    dict(carveout=100),
+    dict(rcp3=1)]
 DEFAULTS = dict(lattice=1, lt_tx=0, lt_ty=0, lt_minb=0, lt_kc=0, lt_pf=0, lt_regs=0, carveout=-1, rcp3=0)
 
 
