@@ -31,7 +31,7 @@ const knob_entry kKnobs[] = {
     {"FEMX_RCP3", "rcp3", &femx_knobs::rcp3}, {"FEMX_SPEC_PREFETCH", "spec_prefetch", &femx_knobs::spec_prefetch},
     {"FEMX_SPEC_PIN", "spec_pin", &femx_knobs::spec_pin}, {"FEMX_LISTLAST", "listlast", &femx_knobs::listlast},
     {"FEMX_ROWSUM", "rowsum", &femx_knobs::rowsum}, {"FEMX_CHAINORDER", "chainorder", &femx_knobs::chainorder},
-    {"FEMX_LATTICE", "lattice", &femx_knobs::lattice}, {"FEMX_LT_TX", "lt_tx", &femx_knobs::lt_tx},
+    {"FEMX_LATTICE", "lattice", &femx_knobs::lattice}, {"FEMX_LATTICE_PATTERN", "lattice_pattern", &femx_knobs::lattice_pattern}, {"FEMX_LT_TX", "lt_tx", &femx_knobs::lt_tx},
     {"FEMX_LT_TY", "lt_ty", &femx_knobs::lt_ty}, {"FEMX_LT_KC", "lt_kc", &femx_knobs::lt_kc},
     {"FEMX_LT_MINB", "lt_minb", &femx_knobs::lt_minb}, {"FEMX_LT_REGS", "lt_regs", &femx_knobs::lt_regs}, {"FEMX_LT_PF", "lt_pf", &femx_knobs::lt_pf},
     {"FEMX_DIST_GRAPH", "dist_graph", &femx_knobs::dist_graph},

@@ -1117,7 +1117,7 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   femx_lattice_plan plan;
   bool lattice = false;
   std::string lat_key;
-  if (cls && pat->lat.ok && form->lt_ok && live.lattice != 0) {
+  if (cls && pat->lat.ok && pat->lat_rows > 0 && pat->lat_rows == pat->spec_rows && form->lt_ok && live.lattice != 0) {
     std::string why;
     femx_knobs kk = form->knobs;
     kk.lt_tx = live.lt_tx; kk.lt_ty = live.lt_ty; kk.lt_kc = live.lt_kc; kk.lt_minb = live.lt_minb;

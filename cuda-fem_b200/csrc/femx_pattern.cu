@@ -11,7 +11,9 @@
 //   6. column fill + per-incidence position codes (the element-slot → CSR-offset map)
 // The output is bit-identical to the reference's sorted std::set rows.
 #include <algorithm>
+#include <array>
 #include <climits>
+#include <cstring>
 #include <cstdio>
 #include <vector>
 
@@ -278,6 +280,24 @@ __global__ void slice_sizes(const int* __restrict__ pair_ptr, int n_rows, int n_
   if ((threadIdx.x & 31) == 0) size[s] = np * 32;
 }
 
+__global__ void row_len_max(const int* __restrict__ rowlen, int n_rows, int* __restrict__ out) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  int v = r < n_rows ? rowlen[r] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+}
+
+__global__ void slice_sizes_cnt(const int* __restrict__ cnt, int n_rows, int n_slices, int* __restrict__ size) {
+  int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= n_slices) return;
+  int r = s * 32 + (threadIdx.x & 31);
+  int np = r < n_rows ? cnt[r] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) np = max(np, __shfl_xor_sync(0xffffffffu, np, o));
+  if ((threadIdx.x & 31) == 0) size[s] = np * 32;
+}
+
 __global__ void to_sell(const int* __restrict__ pair_ptr, const int* __restrict__ slice_ptr, int n_rows,
                         const int* __restrict__ pair_elem, const unsigned* __restrict__ pair_code,
                         int* __restrict__ sell_elem, unsigned* __restrict__ sell_code) {
@@ -448,6 +468,39 @@ int tmp_alloc(femx_ctx* ctx, T** p, int64_t n, cudaStream_t st) {
 
 inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
+// the rows outside the class, compacted (ascending): the numeric pass runs them in a launch of their own
+int build_other_rows(femx_ctx* ctx, femx_pattern* p, long long class_rows, cudaStream_t st) {
+  const int64_t nr = p->n_rows;
+  int *d_flag = nullptr, *d_pos = nullptr, *d_count = nullptr;
+  int rc = tmp_alloc(ctx, &d_flag, nr + 1, st);
+  if (rc == FEMX_OK) rc = tmp_alloc(ctx, &d_pos, nr + 1, st);
+  if (rc == FEMX_OK) rc = tmp_alloc(ctx, &d_count, 1, st);
+  long long n_other = 0;
+  if (rc == FEMX_OK) {
+    other_flags<<<nblocks(nr, 256), 256, 0, st>>>(p->d_rowinfo, (int)nr, d_flag);
+    rc = exclusive_scan(ctx, d_flag, nr, d_pos, &n_other, st);
+  }
+  if (rc == FEMX_OK && n_other != nr - class_rows)
+    rc = femx_fail(ctx, FEMX_ERR_CUDA, "stencil class: %lld rows outside the class, expected %lld", n_other,
+                   (long long)(nr - class_rows));
+  if (rc == FEMX_OK) rc = dev_alloc(ctx, &p->d_other_rows, n_other, &p->bytes);
+  if (rc == FEMX_OK) {
+    cudaMemsetAsync(d_count, 0, sizeof(int), st);
+    other_fill<<<nblocks(nr, 256), 256, 0, st>>>(p->d_rowinfo, (int)nr, d_pos, p->d_other_rows, d_count);
+    int mx = 0;
+    cudaError_t e = cudaMemcpyAsync(&mx, d_count, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) rc = femx_fail(ctx, FEMX_ERR_CUDA, "stencil class: row list failed: %s", cudaGetErrorString(e));
+    p->n_other = n_other;
+    p->max_row_other = mx;
+  }
+  cudaFreeAsync(d_flag, st);
+  cudaFreeAsync(d_pos, st);
+  cudaFreeAsync(d_count, st);
+  return rc;
+}
+
 // Finds the dominant stencil class among evenly spaced sample rows, flags its rows / whole tiles in
 // rowinfo and keeps a host copy of the class's scatter codes for the JIT (femx_form.cpp).
 int detect_stencil_class(femx_ctx* ctx, femx_pattern* p, const int* d_pair_ptr, const unsigned* d_pair_code,
@@ -515,35 +568,8 @@ int detect_stencil_class(femx_ctx* ctx, femx_pattern* p, const int* d_pair_ptr, 
   SC_CUDA(cudaMemcpyAsync(&cnt, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
   SC_CUDA(cudaStreamSynchronize(st));
   SC_CUDA(cudaGetLastError());
-  // the rows outside the class, compacted (ascending): the numeric pass runs them in a launch of their own
-  {
-    int *d_flag = nullptr, *d_pos = nullptr;
-    rc = tmp_alloc(ctx, &d_flag, nr + 1, st);
-    if (rc == FEMX_OK) rc = tmp_alloc(ctx, &d_pos, nr + 1, st);
-    long long n_other = 0;
-    if (rc == FEMX_OK) {
-      other_flags<<<nblocks(nr, 256), 256, 0, st>>>(p->d_rowinfo, (int)nr, d_flag);
-      rc = exclusive_scan(ctx, d_flag, nr, d_pos, &n_other, st);
-    }
-    if (rc == FEMX_OK && n_other != nr - cnt)
-      rc = femx_fail(ctx, FEMX_ERR_CUDA, "stencil class: %lld rows outside the class, expected %lld", n_other,
-                     (long long)(nr - cnt));
-    if (rc == FEMX_OK) rc = dev_alloc(ctx, &p->d_other_rows, n_other, &p->bytes);
-    if (rc == FEMX_OK) {
-      cudaMemsetAsync(d_count, 0, sizeof(int), st);
-      other_fill<<<nblocks(nr, 256), 256, 0, st>>>(p->d_rowinfo, (int)nr, d_pos, p->d_other_rows, d_count);
-      int mx = 0;
-      cudaError_t e = cudaMemcpyAsync(&mx, d_count, sizeof(int), cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      if (e == cudaSuccess) e = cudaGetLastError();
-      if (e != cudaSuccess) rc = femx_fail(ctx, FEMX_ERR_CUDA, "stencil class: row list failed: %s", cudaGetErrorString(e));
-      p->n_other = n_other;
-      p->max_row_other = mx;
-    }
-    cudaFreeAsync(d_flag, st);
-    cudaFreeAsync(d_pos, st);
-    if (rc != FEMX_OK) return done(rc);
-  }
+  rc = build_other_rows(ctx, p, cnt, st);
+  if (rc != FEMX_OK) return done(rc);
 #undef SC_CUDA
   p->spec_np = np; p->spec_rlen = rlen; p->spec_self = self; p->spec_rows = cnt;
   p->spec_codes = codes;
@@ -590,7 +616,9 @@ __global__ void lattice_verify(const int* __restrict__ conn, long long n_elems, 
   if (!ok) atomicAdd(bad, 1);
 }
 
-int detect_lattice(femx_ctx* ctx, femx_pattern* p, const int* d_conn, cudaStream_t st) {
+// check_class: the lattice is only recorded when the pattern's class rows are exactly its interior nodes
+// (general symbolic pass); the lattice-templated pass defines the class itself and passes false
+int detect_lattice(femx_ctx* ctx, femx_pattern* p, const int* d_conn, cudaStream_t st, bool check_class) {
   p->lat = femx_lattice();
   const int nn = p->nn, dim = nn - 1;
   const int64_t ne = p->n_elems;
@@ -681,12 +709,298 @@ int detect_lattice(femx_ctx* ctx, femx_pattern* p, const int* d_conn, cudaStream
       const long long lo = std::max<long long>(n0, p->row_begin), hi = std::min<long long>(n1, p->row_end);
       if (hi > lo) interior += hi - lo;
     }
-  if (interior != p->spec_rows) return done(FEMX_OK);
+  if (check_class && interior != p->spec_rows) return done(FEMX_OK);
+  for (int t = 0; t < P; ++t)  // (degenerate template elements are left to the general pass, which reports them)
+    for (int a = 0; a < nn; ++a)
+      for (int b = a + 1; b < nn; ++b)
+        if (L.corner[t][a] == L.corner[t][b]) return done(FEMX_OK);
   L.ok = true;
   p->lat = L;
   p->lat_rows = interior;
   return done(FEMX_OK);
 #undef LT_CUDA
+}
+
+
+// --------------------------------------------- lattice-templated symbolic pass ---
+// On a lattice mesh (every element verified against the cell template: detect_lattice) the rows of the pattern are
+// translates of at most 3^dim templates — one per (low face / interior / high face) position along each axis.  The
+// templates are produced on the host by running the SAME row rules (ascending incidences, sorted duplicate-free
+// columns, position codes with first-touch flags) on a replica of at most 2 cells per axis; the device then writes
+// rowinfo, columns and the SELL scatter map of every row from its template at memory speed, instead of the
+// histogram / bucket / per-row sort-merge pipeline.  Output identical to the general pass, bit for bit (tests).
+#define LT_MAX_NP 32
+#define LT_MAX_RLEN 27
+struct lat_row_tmpl {
+  int np, rlen, self;
+  signed char col[LT_MAX_RLEN][3];   // column displacement (dx, dy, dz), ascending node id
+  signed char cell[LT_MAX_NP][3];    // cell of incidence k relative to the node: (sx, sy, sz) in {-1, 0}
+  unsigned char t[LT_MAX_NP], li[LT_MAX_NP];
+  unsigned code[LT_MAX_NP];
+};
+struct lat_geom {
+  int dim, P, nn;
+  int cn[3];
+  long long s[3];
+  long long node0;
+  int row_begin, n_rows;
+  int dom;  // dominant class (flagged FEMX_ROW_SPEC), -1 = none
+};
+
+__device__ __forceinline__ int lat_class_of(const lat_geom& g, long long node, int* ijk) {
+  long long q = node - g.node0;
+  if (q < 0) return -1;
+  long long k = 0, j, i;
+  if (g.dim == 3) { k = q / g.s[2]; q -= k * g.s[2]; }
+  j = q / g.s[1];
+  i = q - j * g.s[1];
+  if (i > g.cn[0] || j > g.cn[1] || k > g.cn[2]) return -1;
+  ijk[0] = (int)i; ijk[1] = (int)j; ijk[2] = (int)k;
+  const int ci = i == 0 ? 0 : (i == g.cn[0] ? 2 : 1), cj = j == 0 ? 0 : (j == g.cn[1] ? 2 : 1);
+  const int ck = g.dim == 3 ? (k == 0 ? 0 : (k == g.cn[2] ? 2 : 1)) : 0;
+  return ci + 3 * cj + 9 * ck;
+}
+
+__global__ void lat_row_len_k(lat_geom g, const lat_row_tmpl* __restrict__ T, int* __restrict__ rowlen, int* __restrict__ npair,
+                              unsigned long long* __restrict__ tot_pairs, int* __restrict__ n_dom) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  int np = 0, dom = 0;
+  if (r < g.n_rows) {
+    int ijk[3];
+    const int c = lat_class_of(g, (long long)g.row_begin + r, ijk);
+    rowlen[r] = c < 0 ? 0 : T[c].rlen;
+    np = c < 0 ? 0 : T[c].np;
+    npair[r] = np;
+    dom = c >= 0 && c == g.dom;
+  }
+  // block totals
+  __shared__ int sh[256], sd[256];
+  sh[threadIdx.x] = np; sd[threadIdx.x] = dom;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh[threadIdx.x] += sh[threadIdx.x + o]; sd[threadIdx.x] += sd[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { atomicAdd(tot_pairs, (unsigned long long)sh[0]); atomicAdd(n_dom, sd[0]); }
+}
+
+__global__ void lat_row_fill_k(lat_geom g, const lat_row_tmpl* __restrict__ T, const int* __restrict__ row_ptr,
+                               const int* __restrict__ slice_ptr, int2* __restrict__ rowinfo, int* __restrict__ col_idx,
+                               unsigned* __restrict__ sell_code, int* __restrict__ sell_elem) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > g.n_rows) return;
+  if (r == g.n_rows) { rowinfo[r] = make_int2(row_ptr[r], 0); return; }
+  const int rp = row_ptr[r];
+  int ijk[3];
+  const long long node = (long long)g.row_begin + r;
+  const int c = lat_class_of(g, node, ijk);
+  if (c < 0) { rowinfo[r] = make_int2(rp, 0); return; }
+  const lat_row_tmpl& t = T[c];
+  rowinfo[r] = make_int2(rp, t.np | (c == g.dom ? FEMX_ROW_SPEC : 0) | (t.self << 24));
+  for (int k = 0; k < t.rlen; ++k)
+    col_idx[rp + k] = (int)(node + t.col[k][0] + t.col[k][1] * g.s[1] + t.col[k][2] * g.s[2]);
+  const int sp = slice_ptr[r >> 5] + (r & 31);
+  for (int k = 0; k < t.np; ++k) {
+    const long long cell = (ijk[0] + t.cell[k][0]) + (long long)g.cn[0] * ((ijk[1] + t.cell[k][1]) + (long long)g.cn[1] * (ijk[2] + t.cell[k][2]));
+    sell_elem[sp + k * 32] = (int)((cell * g.P + t.t[k]) * g.nn + t.li[k]);
+    sell_code[sp + k * 32] = t.code[k];
+  }
+}
+
+// the row rules of row_fill / build_row on a replica mesh, on the host
+void lattice_templates(const femx_lattice& L, int nn, std::vector<lat_row_tmpl>* out) {
+  const int dim = L.dim;
+  int m[3] = {std::min(L.cn[0], 2), std::min(L.cn[1], 2), dim == 3 ? std::min(L.cn[2], 2) : 1};
+  const int rs[3] = {1, m[0] + 1, (m[0] + 1) * (m[1] + 1)};
+  auto node_of = [&](int i, int j, int k) { return i + j * rs[1] + (dim == 3 ? k * rs[2] : 0); };
+  std::vector<std::vector<int>> conn;  // replica elements, cell-major like the lattice
+  std::vector<std::array<int, 4>> ecell;
+  for (int ck = 0; ck < (dim == 3 ? m[2] : 1); ++ck)
+    for (int cj = 0; cj < m[1]; ++cj)
+      for (int ci = 0; ci < m[0]; ++ci)
+        for (int t = 0; t < L.P; ++t) {
+          std::vector<int> e(nn);
+          for (int a = 0; a < nn; ++a) {
+            const int c = L.corner[t][a];
+            e[a] = node_of(ci + (c & 1), cj + ((c >> 1) & 1), ck + ((c >> 2) & 1));
+          }
+          conn.push_back(e);
+          ecell.push_back({ci, cj, ck, t});
+        }
+  out->assign(27, lat_row_tmpl());
+  for (int az = 0; az < (dim == 3 ? 3 : 1); ++az)
+    for (int ay = 0; ay < 3; ++ay)
+      for (int ax = 0; ax < 3; ++ax) {
+        lat_row_tmpl& T = (*out)[ax + 3 * ay + 9 * az];
+        memset(&T, 0, sizeof T);
+        // representative position of the class along each axis; classes that do not occur stay empty
+        int pos[3];
+        const int a3[3] = {ax, ay, az};
+        bool exists = true;
+        for (int d = 0; d < 3; ++d) {
+          const int md = d < dim ? m[d] : 0;
+          if (a3[d] == 0) pos[d] = 0;
+          else if (a3[d] == 2) pos[d] = md;
+          else { pos[d] = 1; if (md < 2) exists = false; }
+          if (d >= dim && a3[d] != 0) exists = false;
+        }
+        if (!exists) continue;
+        const int n = node_of(pos[0], pos[1], pos[2]);
+        std::vector<int> inc, list;  // incidences e*nn + li ascending; sorted duplicate-free columns
+        for (size_t e = 0; e < conn.size(); ++e)
+          for (int a = 0; a < nn; ++a)
+            if (conn[e][a] == n) inc.push_back((int)e * nn + a);
+        for (int pe : inc)
+          for (int a = 0; a < nn; ++a) list.push_back(conn[pe / nn][a]);
+        std::sort(list.begin(), list.end());
+        list.erase(std::unique(list.begin(), list.end()), list.end());
+        T.np = (int)inc.size();
+        T.rlen = (int)list.size();
+        T.self = (int)(std::lower_bound(list.begin(), list.end(), n) - list.begin());
+        for (int k = 0; k < T.rlen; ++k) {
+          const int q = list[k];
+          const int qi = q % rs[1], qj = (q / rs[1]) % (m[1] + 1), qk = dim == 3 ? q / rs[2] : 0;
+          T.col[k][0] = (signed char)(qi - pos[0]); T.col[k][1] = (signed char)(qj - pos[1]); T.col[k][2] = (signed char)(qk - pos[2]);
+        }
+        std::vector<char> seen(list.size(), 0);
+        for (int k = 0; k < T.np; ++k) {
+          const int e = inc[k] / nn, li = inc[k] % nn;
+          unsigned code = (unsigned)li << 28;
+          for (int a = 0; a < nn; ++a) {
+            if (a == li) continue;
+            const int p0 = (int)(std::lower_bound(list.begin(), list.end(), conn[e][a]) - list.begin());
+            const int j = nn == 4 ? (a ^ li) - 1 : (a - li - 1 + 3) % 3;
+            code |= (unsigned)p0 << (7 * j);
+            if (!seen[p0]) { code |= 1u << (21 + j); seen[p0] = 1; }
+          }
+          T.code[k] = code;
+          T.t[k] = (unsigned char)ecell[e][3];
+          T.li[k] = (unsigned char)li;
+          T.cell[k][0] = (signed char)(ecell[e][0] - pos[0]); T.cell[k][1] = (signed char)(ecell[e][1] - pos[1]);
+          T.cell[k][2] = (signed char)(ecell[e][2] - pos[2]);
+        }
+      }
+}
+
+
+int build_from_lattice(femx_ctx* ctx, femx_pattern* p, cudaStream_t st) {
+  const femx_lattice& L = p->lat;
+  const int nn = p->nn, dim = L.dim;
+  const int64_t nr = p->n_rows;
+  std::vector<lat_row_tmpl> T;
+  lattice_templates(L, nn, &T);
+  // dominant class: the one with the most nodes in the lattice (the interior, unless an axis has a single cell)
+  int dom = -1;
+  long long best = 0;
+  for (int c = 0; c < 27; ++c) {
+    if (T[c].np == 0) continue;
+    const int a3[3] = {c % 3, (c / 3) % 3, c / 9};
+    long long cnt = 1;
+    for (int d = 0; d < dim; ++d) cnt *= a3[d] == 1 ? std::max(L.cn[d] - 1, 0) : 1;
+    if (cnt > best) { best = cnt; dom = c; }
+  }
+  const bool want_class = p->nd == 1 && ctx->knobs.spec != 0 && dom >= 0 && T[dom].np <= FEMX_SPEC_MAX_NP &&
+                          T[dom].rlen <= (nn == 4 ? 16 : FEMX_SPEC_MAX_RLEN);
+  lat_geom g = {};
+  g.dim = dim; g.P = L.P; g.nn = nn;
+  for (int d = 0; d < 3; ++d) { g.cn[d] = L.cn[d]; g.s[d] = L.s[d]; }
+  g.node0 = L.node0; g.row_begin = (int)p->row_begin; g.n_rows = (int)nr;
+  g.dom = want_class ? dom : -1;
+  lat_row_tmpl* d_T = nullptr;
+  int *d_rowlen = nullptr, *d_np = nullptr, *d_row_ptr = nullptr, *d_ssize = nullptr, *d_flags = nullptr;
+  unsigned long long* d_tot = nullptr;
+  int rc = FEMX_OK;
+  auto cleanup = [&]() {
+    cudaFreeAsync(d_T, st); cudaFreeAsync(d_rowlen, st); cudaFreeAsync(d_np, st); cudaFreeAsync(d_row_ptr, st);
+    cudaFreeAsync(d_ssize, st); cudaFreeAsync(d_flags, st); cudaFreeAsync(d_tot, st);
+  };
+#define LB_TRY(x) do { rc = (x); if (rc != FEMX_OK) { cleanup(); return rc; } } while (0)
+#define LB_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess) { cleanup(); return femx_fail(ctx, FEMX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); } \
+  } while (0)
+  LB_TRY(tmp_alloc(ctx, &d_T, 27, st));
+  LB_TRY(tmp_alloc(ctx, &d_rowlen, nr + 1, st));
+  LB_TRY(tmp_alloc(ctx, &d_np, nr + 1, st));
+  LB_TRY(tmp_alloc(ctx, &d_row_ptr, nr + 1, st));
+  LB_TRY(tmp_alloc(ctx, &d_flags, 4, st));
+  LB_TRY(tmp_alloc(ctx, &d_tot, 1, st));
+  LB_CUDA(cudaMemcpyAsync(d_T, T.data(), sizeof(lat_row_tmpl) * 27, cudaMemcpyHostToDevice, st));
+  LB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, st));
+  LB_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long), st));
+  if (nr > 0) lat_row_len_k<<<nblocks(nr, 256), 256, 0, st>>>(g, d_T, d_rowlen, d_np, d_tot, d_flags);
+  long long nnz = 0;
+  LB_TRY(exclusive_scan(ctx, d_rowlen, nr, d_row_ptr, &nnz, st));
+  unsigned long long tot_pairs = 0;
+  int h_flags[4];
+  LB_CUDA(cudaMemcpyAsync(&tot_pairs, d_tot, sizeof tot_pairs, cudaMemcpyDeviceToHost, st));
+  LB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+  LB_CUDA(cudaStreamSynchronize(st));
+  if (nnz >= (1LL << 31) - 1 || tot_pairs >= (1ULL << 31) - 1) {
+    cleanup();
+    return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: %lld node-level nonzeros / %llu incidences exceed 32-bit offsets", nnz, tot_pairs);
+  }
+  long long n_dom = h_flags[0];
+  if (want_class && n_dom * 4 < nr) { g.dom = -1; n_dom = 0; }  // (the general pass wants a quarter of its sample rows)
+  p->n_pairs = (int64_t)tot_pairs;
+  p->nnz_node = nnz;
+  LB_TRY(dev_alloc(ctx, &p->d_rowinfo, nr + 1, &p->bytes));
+  LB_TRY(dev_alloc(ctx, &p->d_col_idx, nnz + 8, &p->bytes));
+  LB_CUDA(cudaMemsetAsync(p->d_col_idx + nnz, 0, sizeof(int) * 8, st));
+  const int64_t n_slices = (nr + 31) / 32;
+  LB_TRY(tmp_alloc(ctx, &d_ssize, n_slices + 1, st));
+  LB_TRY(dev_alloc(ctx, &p->d_slice_ptr, n_slices + 1, &p->bytes));
+  long long n_sell = 0;
+  if (n_slices > 0) slice_sizes_cnt<<<nblocks(n_slices, 8), 256, 0, st>>>(d_np, (int)nr, (int)n_slices, d_ssize);
+  LB_TRY(exclusive_scan(ctx, d_ssize, n_slices, p->d_slice_ptr, &n_sell, st));
+  if (n_sell >= (1LL << 31) - 1) {
+    cleanup();
+    return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: padded scatter map (%lld) exceeds 32-bit offsets", n_sell);
+  }
+  p->n_sell = n_sell;
+  LB_TRY(dev_alloc(ctx, &p->d_sell_code, n_sell, &p->bytes));
+  LB_TRY(dev_alloc(ctx, &p->d_sell_elem, n_sell, &p->bytes));
+  if (n_sell > 0) {
+    LB_CUDA(cudaMemsetAsync(p->d_sell_code, 0, sizeof(unsigned) * n_sell, st));
+    LB_CUDA(cudaMemsetAsync(p->d_sell_elem, 0, sizeof(int) * n_sell, st));
+  }
+  lat_row_fill_k<<<nblocks(nr + 1, 128), 128, 0, st>>>(g, d_T, d_row_ptr, p->d_slice_ptr, p->d_rowinfo, p->d_col_idx,
+                                                       p->d_sell_code, p->d_sell_elem);
+  LB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, st));
+  if (nr > 0) {
+    int64_t ntiles = (nr + p->tile_nodes - 1) / p->tile_nodes;
+    tile_max<<<nblocks(ntiles, 128), 128, 0, st>>>(p->d_rowinfo, p->d_slice_ptr, (int)nr, p->tile_nodes, d_flags + 2);
+    row_len_max<<<nblocks(nr, 256), 256, 0, st>>>(d_rowlen, (int)nr, d_flags + 1);
+  }
+  LB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+  LB_CUDA(cudaStreamSynchronize(st));
+  LB_CUDA(cudaGetLastError());
+  p->max_row = h_flags[1];
+  p->max_tile_nnz = h_flags[2];
+  p->max_tile_codes = h_flags[3];
+  if (g.dom >= 0 && n_dom > 0) {
+    const lat_row_tmpl& D = T[g.dom];
+    p->spec_np = D.np; p->spec_rlen = D.rlen; p->spec_self = D.self; p->spec_rows = n_dom;
+    p->spec_codes.assign(D.code, D.code + D.np);
+    p->spec_off.resize(D.rlen);
+    for (int k = 0; k < D.rlen; ++k) p->spec_off[k] = (int32_t)(D.col[k][0] + D.col[k][1] * L.s[1] + D.col[k][2] * L.s[2]);
+    unsigned long long kh = 1469598103934665603ull;
+    for (int k = 0; k < D.np; ++k) kh = (kh ^ D.code[k]) * 1099511628211ull;
+    char key[96];
+    snprintf(key, sizeof key, "%016llx_%d_%d_%d", kh, D.np, D.rlen, D.self);
+    p->spec_key = key;
+    LB_TRY(build_other_rows(ctx, p, n_dom, st));
+    // the element-once numeric pass takes the class rows only when they are the lattice-interior nodes
+    const int interior = dim == 3 ? 13 : 4;
+    p->lat_rows = g.dom == interior ? n_dom : 0;
+  } else {
+    p->lat_rows = 0;
+  }
+  cleanup();
+  return FEMX_OK;
+#undef LB_TRY
+#undef LB_CUDA
 }
 
 }  // namespace
@@ -719,6 +1033,18 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
   p->n_rows = row_end - row_begin;
   p->tile_nodes = femx_tile_nodes_for(nd, ctx->knobs);
   const int64_t nr = p->n_rows, total = n_elems * nn;
+  // Lattice meshes (every element a translate of the cell template — verified): rows from templates, at memory speed
+  if (ctx->knobs.lattice_pattern != 0 && nr > 0 && n_elems > 0) {
+    int rc0 = detect_lattice(ctx, p, d_conn, st, false);
+    if (rc0 != FEMX_OK) { femx_pattern_destroy(p); return rc0; }
+    if (p->lat.ok) {
+      rc0 = build_from_lattice(ctx, p, st);
+      if (rc0 != FEMX_OK) { femx_pattern_destroy(p); return rc0; }
+      if (ctx->knobs.lattice == 0) p->lat_rows = 0;
+      *out = p;
+      return FEMX_OK;
+    }
+  }
   int *d_cnt = nullptr, *d_pair_ptr = nullptr, *d_row_ptr = nullptr, *d_flags = nullptr;
   int* d_pair_elem = nullptr;       // CSR-style incidence lists (temporary)
   unsigned* d_pair_code = nullptr;
@@ -844,7 +1170,7 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
   // dominant stencil class (scalar problems; FEMX_SPEC=0 switches the detection off)
   if (nd == 1 && nr > 0 && n_pairs > 0 && ctx->knobs.spec != 0) {
     PB_TRY(detect_stencil_class(ctx, p, d_pair_ptr, d_pair_code, st));
-    if (p->spec_np > 0 && ctx->knobs.lattice != 0) PB_TRY(detect_lattice(ctx, p, d_conn, st));
+    if (p->spec_np > 0 && ctx->knobs.lattice != 0) PB_TRY(detect_lattice(ctx, p, d_conn, st, true));
   }
   PB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
   PB_CUDA(cudaStreamSynchronize(st));

@@ -162,3 +162,51 @@ def test_unaligned_value_buffer_is_rejected(ctx):
         form.assemble_csr(pat, mesh, buf[1:])
     assert e.value.status == 1 and "16-byte" in str(e.value)
     form.close(); pat.close()
+
+
+@pytest.mark.parametrize("case", ["rect 9x11", "rect 1x40", "box 7x6x5", "box 37x5x1", "box 1x1x1", "box 2x2x9 slab", "box 6x5x4 nd3"])
+def test_lattice_templated_symbolic_pass_equals_general_pass(ctx, case):
+    """On lattice meshes the symbolic pass writes the rows from (at most 3^dim) templates; everything it produces —
+    CSR, class, scatter map (exercised through the generic numeric pass and the load vector) — must equal the general
+    histogram / sort / merge pipeline bit for bit."""
+    import torch
+    kind, dims = case.split()[0], [int(v) for v in case.split()[1].split("x")]
+    nd = 3 if "nd3" in case else 1
+    if kind == "rect":
+        mesh = ctx.rectangle_mesh(0, 1, 0, 2, dims[0], dims[1])
+        rows = dict()
+    else:
+        mesh = ctx.box_mesh(*dims)
+        rows = dict()
+        if "slab" in case:
+            plane = (dims[0] + 1) * (dims[1] + 1)
+            rows = dict(row_begin=2 * plane, row_end=7 * plane + 3, col_base=11)
+    out = []
+    for flag in (1, 0):
+        ctx.set_option("lattice_pattern", flag)
+        try:
+            pat = femx.Pattern(ctx, mesh, nd=nd, **rows)
+        finally:
+            ctx.set_option("lattice_pattern", 1)
+        rp, ci = pat.csr("int64")
+        st = pat.stencil()
+        info = (pat.n_rows, pat.nnz, pat.max_row, pat.bytes)
+        dim = mesh.dim
+        form = femx.Form(ctx, dim, femx.ELASTICITY if nd == 3 else femx.POISSON_MASS, nd=nd, params=(0.6, 0.4) if nd == 3 else (1.0,))
+        ctx.set_option("spec", 0)
+        try:
+            v = form.assemble_csr(pat, mesh)      # generic pass: reads the whole scatter map
+        finally:
+            ctx.set_option("spec", 1)
+        b = form.assemble_rhs(pat, mesh)
+        v2 = form.assemble_csr(pat, mesh)         # default path (class / lattice pass where available)
+        lat = pat.lattice()
+        out.append((rp.cpu(), ci.cpu(), st, info, v.cpu(), b.cpu(), v2.cpu(), lat))
+        form.close(); pat.close()
+    a, g = out
+    assert a[7] is not None                                           # the templated pass ran (a lattice was found)
+    assert torch.equal(a[0], g[0]) and torch.equal(a[1], g[1])
+    assert a[3] == g[3], (a[3], g[3])
+    for k in ("n_incid", "row_len", "self_pos", "rows", "codes", "offsets"):
+        assert a[2][k] == g[2][k], (k, a[2], g[2])
+    assert torch.equal(a[4], g[4]) and torch.equal(a[5], g[5]) and torch.equal(a[6], g[6])
