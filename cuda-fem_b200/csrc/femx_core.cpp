@@ -33,7 +33,8 @@ const knob_entry kKnobs[] = {
     {"FEMX_ROWSUM", "rowsum", &femx_knobs::rowsum}, {"FEMX_CHAINORDER", "chainorder", &femx_knobs::chainorder},
     {"FEMX_LATTICE", "lattice", &femx_knobs::lattice}, {"FEMX_LATTICE_PATTERN", "lattice_pattern", &femx_knobs::lattice_pattern}, {"FEMX_LT_TX", "lt_tx", &femx_knobs::lt_tx},
     {"FEMX_LT_TY", "lt_ty", &femx_knobs::lt_ty}, {"FEMX_LT_KC", "lt_kc", &femx_knobs::lt_kc},
-    {"FEMX_LT_MINB", "lt_minb", &femx_knobs::lt_minb}, {"FEMX_LT_REGS", "lt_regs", &femx_knobs::lt_regs}, {"FEMX_LT_PF", "lt_pf", &femx_knobs::lt_pf},
+    {"FEMX_LT_MINB", "lt_minb", &femx_knobs::lt_minb}, {"FEMX_LT_REGS", "lt_regs", &femx_knobs::lt_regs}, {"FEMX_LT_PF", "lt_pf", &femx_knobs::lt_pf}, {"FEMX_LT_UNROLL", "lt_unroll", &femx_knobs::lt_unroll},
+    {"FEMX_LT_SIDE", "lt_side", &femx_knobs::lt_side},
     {"FEMX_DIST_GRAPH", "dist_graph", &femx_knobs::dist_graph},
 };
 }  // namespace
@@ -161,6 +162,9 @@ int femx_ctx_set_option(femx_ctx* ctx, const char* name, int value) {
 void femx_ctx_destroy(femx_ctx* ctx) {
   if (!ctx) return;
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->s_side) cudaStreamDestroy(ctx->s_side);
+  if (ctx->e_fork) cudaEventDestroy(ctx->e_fork);
+  if (ctx->e_join) cudaEventDestroy(ctx->e_join);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   delete ctx;
 }

@@ -1121,7 +1121,7 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
     std::string why;
     femx_knobs kk = form->knobs;
     kk.lt_tx = live.lt_tx; kk.lt_ty = live.lt_ty; kk.lt_kc = live.lt_kc; kk.lt_minb = live.lt_minb;
-    kk.lt_regs = live.lt_regs; kk.lt_pf = live.lt_pf;
+    kk.lt_regs = live.lt_regs; kk.lt_pf = live.lt_pf; kk.lt_unroll = live.lt_unroll;
     if (femx_lattice_plan_make(form, pat->lat, pat->spec_rlen, pat->spec_self, pat->spec_off, kk, &plan, &why)) {
       lat_key = femx_lattice_key(pat->lat, plan);
       if (!form->lt_failed.count(lat_key)) {
@@ -1187,8 +1187,20 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
     lat.klo = (int)klo; lat.khi = (int)khi;
     lat.ntx = (L.cn[0] - 1 + plan.tx - 2) / (plan.tx - 1);
     lat.nty = (L.cn[1] - 1 + plan.ty - 2) / (plan.ty - 1);
+    // node planes per CTA: every CTA pays one extra cell layer to prime its carry, and the grid should fill whole
+    // waves of (CTAs per SM) x SMs — the chunk count that minimises waves x (planes + 1) (a knob overrides)
+    const long long nk = khi >= klo ? khi - klo + 1 : 0;
+    if (live.lt_kc <= 0 && nk > 0) {
+      const long long tiles = (long long)lat.ntx * lat.nty, slots = std::max(1, form->ctx->sm_count * plan.minb);
+      long long best_cost = -1;
+      for (long long nz = 1; nz <= std::max<long long>(1, nk / 4); ++nz) {
+        const long long kc = (nk + nz - 1) / nz, waves = (tiles * ((nk + kc - 1) / kc) + slots - 1) / slots;
+        const long long cost = waves * (kc + 1);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; plan.kc = (int)kc; }
+      }
+    }
     lat.kc = plan.kc;
-    const long long ntz = khi >= klo ? (khi - klo + 1 + plan.kc - 1) / plan.kc : 0;
+    const long long ntz = nk > 0 ? (nk + plan.kc - 1) / plan.kc : 0;
     int n_list = (int)pat->n_other;
     const size_t smem = plan.smem;
     if (smem > form->ctx->smem_optin)
@@ -1199,20 +1211,38 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
     void* args[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &n_rows, &row_node0, &lat};
     const long long blocks = (long long)lat.ntx * lat.nty * ntz;
     if (blocks > 2147483647LL) return femx_fail(form->ctx, FEMX_ERR_UNSUPPORTED, "femx_assemble_csr: %lld blocks exceed the grid limit", blocks);
+    // The rows outside the class have a (small-register) kernel of their own.  It runs on the context's side stream,
+    // forked from and joined to the caller's stream by events: beside the lattice pass, not behind it.
+    femx_ctx* cx = form->ctx;
+    bool side = n_list > 0 && blocks > 0 && live.lt_side != 0;
+    if (side && !cx->s_side) {
+      if (cudaStreamCreateWithFlags(&cx->s_side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&cx->e_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&cx->e_join, cudaEventDisableTiming) != cudaSuccess) {
+        (void)cudaGetLastError();
+        side = false;
+      }
+    }
     cr = CUDA_SUCCESS;
-    if (blocks > 0)
-      cr = drv->LaunchKernel(v->fn, (unsigned)blocks, 1, 1, (unsigned)plan.threads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
-    if (cr == CUDA_SUCCESS && n_list > 0) {
-      // the rows outside the class: their own (small-register) kernel behind the lattice pass; disjoint rows
+    auto launch_rows = [&](CUstream s) -> CUresult {
       const size_t smem2 = (size_t)128 * seg * rs;
       if (smem2 > 48 * 1024 && (int)smem2 > v->smem2_set) {
-        if (drv->FuncSetAttribute(v->fn2, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem2) != CUDA_SUCCESS)
-          return femx_fail(form->ctx, FEMX_ERR_CUDA, "cuFuncSetAttribute(smem=%zu) failed", smem2);
+        if (drv->FuncSetAttribute(v->fn2, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem2) != CUDA_SUCCESS) return CUDA_ERROR_INVALID_VALUE;
         v->smem2_set = (int)smem2;
       }
       void* args2[] = {&rowinfo, &slice_ptr, &col, &code, &pelem, &X, &Y, &Z, &cs, &d_values, &rowlist, &n_list, &seg_arg};
-      cr = drv->LaunchKernel(v->fn2, (unsigned)((n_list + 127) / 128), 1, 1, 128, 1, 1, (unsigned)smem2, (CUstream)stream, args2, nullptr);
+      return drv->LaunchKernel(v->fn2, (unsigned)((n_list + 127) / 128), 1, 1, 128, 1, 1, (unsigned)smem2, s, args2, nullptr);
+    };
+    if (side) {
+      FEMX_CUDA_OK(cx, cudaEventRecord(cx->e_fork, (cudaStream_t)stream));
+      FEMX_CUDA_OK(cx, cudaStreamWaitEvent(cx->s_side, cx->e_fork, 0));
+      cr = launch_rows((CUstream)cx->s_side);
+      FEMX_CUDA_OK(cx, cudaEventRecord(cx->e_join, cx->s_side));
     }
+    if (cr == CUDA_SUCCESS && blocks > 0)
+      cr = drv->LaunchKernel(v->fn, (unsigned)blocks, 1, 1, (unsigned)plan.threads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
+    if (side) FEMX_CUDA_OK(cx, cudaStreamWaitEvent((cudaStream_t)stream, cx->e_join, 0));
+    else if (cr == CUDA_SUCCESS && n_list > 0) cr = launch_rows((CUstream)stream);
   } else {
     if (spec) {
       sc.np = pat->spec_np; sc.rlen = pat->spec_rlen; sc.self = pat->spec_self;

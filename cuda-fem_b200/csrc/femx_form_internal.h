@@ -35,6 +35,7 @@ struct femx_lattice_plan {
   int kc = 32;               // node planes per CTA
   int minb = 1;              // __launch_bounds__ min blocks
   int regs = 0;              // --maxrregcount (0: none)
+  int unroll = 1;            // unroll factor of the plane loop (2: the plane roll needs no register moves)
   int pf = 1;                // 1: the next plane is prefetched into L1 and loaded when needed; 0: loaded one cell ahead
   int nslot = 0;             // shared-memory field slots
   int rlen = 0, self = 0;    // the stencil class

@@ -783,6 +783,7 @@ femx_csr(const int2* __restrict__ rowinfo, const int* __restrict__ slice_ptr,
   int2 r0p = make_int2(0, 0);   // metadata of the row one plane below (gathered one cell late)
   bool minep = false;
   int b2 = 0, b3 = 0;           // buffer of plane kc: (kc - k0 + 1) & 1 and % 3
+  FEMX_LT_LOOP_PRAGMA
   for (int kc = k0 - 1; kc < k1; ++kc) {
 #if FEMX_LT_PF
     // the top plane was prefetched into L1 one cell ago; the plane after it is requested now

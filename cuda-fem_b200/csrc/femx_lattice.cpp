@@ -134,6 +134,7 @@ bool femx_lattice_plan_make(const femx_form* f, const femx_lattice& L, int rlen,
   plan->minb = K.lt_minb > 0 ? K.lt_minb : std::max(1, std::min(8, 384 / plan->threads));
   plan->regs = K.lt_regs;
   plan->pf = K.lt_pf;
+  plan->unroll = K.lt_unroll > 0 ? K.lt_unroll : 1;
   plan->ok = true;
   return true;
 }
@@ -145,7 +146,7 @@ std::string femx_lattice_key(const femx_lattice& L, const femx_lattice_plan& pla
     for (int a = 0; a <= L.dim; ++a) k << (int)L.corner[t][a];
   k << ".";
   for (int v : plan.pos) k << (v < 0 ? std::string("x") : std::to_string(v)) << ",";
-  k << plan.rlen << "." << plan.self << "." << plan.tx << "x" << plan.ty << "m" << plan.minb << "r" << plan.regs << "p" << plan.pf;
+  k << plan.rlen << "." << plan.self << "." << plan.tx << "x" << plan.ty << "m" << plan.minb << "r" << plan.regs << "p" << plan.pf << "u" << plan.unroll;
   return k.str();
 }
 
@@ -380,7 +381,7 @@ std::string femx_lattice_defines(const femx_form* f, const femx_lattice& L, femx
   o << " lt_row[" << plan->self << "] = fma(" << lnum(f->lt_cj) << ", SJ, -S_); }\n";
   o << "#define FEMX_LT_NS " << ns << "\n";
   o << "#define FEMX_LT_TX " << plan->tx << "\n#define FEMX_LT_TY " << plan->ty << "\n#define FEMX_LT_NSLOT " << plan->nslot
-    << "\n#define FEMX_LT_RLEN " << plan->rlen << "\n#define FEMX_LT_MINB " << plan->minb << "\n#define FEMX_LT_PF " << plan->pf << "\n#define FEMX_LATTICE 1\n";
+    << "\n#define FEMX_LT_RLEN " << plan->rlen << "\n#define FEMX_LT_MINB " << plan->minb << "\n#define FEMX_LT_PF " << plan->pf << "\n#define FEMX_LT_LOOP_PRAGMA _Pragma(\"unroll " << plan->unroll << "\")" << "\n#define FEMX_LATTICE 1\n";
   // bytes of dynamic shared memory: mbarrier (128 B) | fields | value image (+ alignment slack)
   const size_t rs = f->dtype == FEMX_F32 ? 4 : 8;
   plan->smem = 128 + ((size_t)plan->nslot * plan->threads + (size_t)plan->threads * plan->rlen + 4) * rs + 16;

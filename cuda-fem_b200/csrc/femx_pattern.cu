@@ -676,20 +676,25 @@ int detect_lattice(femx_ctx* ctx, femx_pattern* p, const int* d_conn, cudaStream
   const long long n_cells = ne / P;
   int h_tmp[2] = {(int)std::min<long long>(n_cells, INT_MAX), 0};
   LT_CUDA(cudaMemcpyAsync(d_tmp, h_tmp, sizeof h_tmp, cudaMemcpyHostToDevice, st));
-  lattice_first_break<<<nblocks(n_cells, 256), 256, 0, st>>>(d_conn, n_cells, (long long)P * nn, 1, d_tmp);
+  // (a line has fewer cells than the y stride has nodes: the search never needs to look further)
+  const long long nsx = std::min<long long>(n_cells, sy);
+  h_tmp[0] = (int)nsx;
+  LT_CUDA(cudaMemcpyAsync(d_tmp, h_tmp, sizeof(int), cudaMemcpyHostToDevice, st));
+  lattice_first_break<<<nblocks(nsx, 256), 256, 0, st>>>(d_conn, nsx, (long long)P * nn, 1, d_tmp);
   LT_CUDA(cudaMemcpyAsync(h_tmp, d_tmp, sizeof(int), cudaMemcpyDeviceToHost, st));
   LT_CUDA(cudaStreamSynchronize(st));
-  const long long cnx = h_tmp[0];
+  const long long cnx = h_tmp[0];   // (== nsx when no break was found below the bound: then the mesh is one line)
   if (cnx < 2 || n_cells % cnx || cnx + 1 > sy) return done(FEMX_OK);
   const long long n_lines = n_cells / cnx;
   long long cny = n_lines, cnz = 1;
   if (dim == 3) {
-    h_tmp[0] = (int)n_lines;
+    const long long nsy = std::min<long long>(n_lines, sz / sy + 1);
+    h_tmp[0] = (int)nsy;
     LT_CUDA(cudaMemcpyAsync(d_tmp, h_tmp, sizeof(int), cudaMemcpyHostToDevice, st));
-    lattice_first_break<<<nblocks(n_lines, 256), 256, 0, st>>>(d_conn, n_lines, cnx * P * nn, sy, d_tmp);
+    lattice_first_break<<<nblocks(nsy, 256), 256, 0, st>>>(d_conn, nsy, cnx * P * nn, sy, d_tmp);
     LT_CUDA(cudaMemcpyAsync(h_tmp, d_tmp, sizeof(int), cudaMemcpyDeviceToHost, st));
     LT_CUDA(cudaStreamSynchronize(st));
-    cny = h_tmp[0];
+    cny = h_tmp[0] == nsy && nsy < n_lines ? 0 : h_tmp[0];   // no break below the bound although lines remain: not a lattice
     if (cny < 1 || n_lines % cny || cny * sy + cnx + 1 > sz) return done(FEMX_OK);
     cnz = n_lines / cny;
   }
@@ -764,26 +769,30 @@ __device__ __forceinline__ int lat_class_of(const lat_geom& g, long long node, i
 }
 
 __global__ void lat_row_len_k(lat_geom g, const lat_row_tmpl* __restrict__ T, int* __restrict__ rowlen, int* __restrict__ npair,
-                              unsigned long long* __restrict__ tot_pairs, int* __restrict__ n_dom) {
+                              unsigned long long* __restrict__ tot_pairs, int* __restrict__ n_dom) {   // n_dom[1]: longest row
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  int np = 0, dom = 0;
+  int np = 0, dom = 0, rl = 0;
   if (r < g.n_rows) {
     int ijk[3];
     const int c = lat_class_of(g, (long long)g.row_begin + r, ijk);
-    rowlen[r] = c < 0 ? 0 : T[c].rlen;
+    rl = c < 0 ? 0 : T[c].rlen;
+    rowlen[r] = rl;
     np = c < 0 ? 0 : T[c].np;
     npair[r] = np;
     dom = c >= 0 && c == g.dom;
   }
   // block totals
-  __shared__ int sh[256], sd[256];
-  sh[threadIdx.x] = np; sd[threadIdx.x] = dom;
+  __shared__ int sh[256], sd[256], sm[256];
+  sh[threadIdx.x] = np; sd[threadIdx.x] = dom; sm[threadIdx.x] = rl;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { sh[threadIdx.x] += sh[threadIdx.x + o]; sd[threadIdx.x] += sd[threadIdx.x + o]; }
+    if (threadIdx.x < o) {
+      sh[threadIdx.x] += sh[threadIdx.x + o]; sd[threadIdx.x] += sd[threadIdx.x + o];
+      sm[threadIdx.x] = max(sm[threadIdx.x], sm[threadIdx.x + o]);
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { atomicAdd(tot_pairs, (unsigned long long)sh[0]); atomicAdd(n_dom, sd[0]); }
+  if (threadIdx.x == 0) { atomicAdd(tot_pairs, (unsigned long long)sh[0]); atomicAdd(n_dom, sd[0]); atomicMax(n_dom + 1, sm[0]); }
 }
 
 __global__ void lat_row_fill_k(lat_geom g, const lat_row_tmpl* __restrict__ T, const int* __restrict__ row_ptr,
@@ -944,6 +953,7 @@ int build_from_lattice(femx_ctx* ctx, femx_pattern* p, cudaStream_t st) {
     return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: %lld node-level nonzeros / %llu incidences exceed 32-bit offsets", nnz, tot_pairs);
   }
   long long n_dom = h_flags[0];
+  p->max_row = h_flags[1];
   if (want_class && n_dom * 4 < nr) { g.dom = -1; n_dom = 0; }  // (the general pass wants a quarter of its sample rows)
   p->n_pairs = (int64_t)tot_pairs;
   p->nnz_node = nnz;
@@ -973,12 +983,10 @@ int build_from_lattice(femx_ctx* ctx, femx_pattern* p, cudaStream_t st) {
   if (nr > 0) {
     int64_t ntiles = (nr + p->tile_nodes - 1) / p->tile_nodes;
     tile_max<<<nblocks(ntiles, 128), 128, 0, st>>>(p->d_rowinfo, p->d_slice_ptr, (int)nr, p->tile_nodes, d_flags + 2);
-    row_len_max<<<nblocks(nr, 256), 256, 0, st>>>(d_rowlen, (int)nr, d_flags + 1);
   }
   LB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
   LB_CUDA(cudaStreamSynchronize(st));
   LB_CUDA(cudaGetLastError());
-  p->max_row = h_flags[1];
   p->max_tile_nnz = h_flags[2];
   p->max_tile_codes = h_flags[3];
   if (g.dom >= 0 && n_dom > 0) {

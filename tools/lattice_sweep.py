@@ -14,24 +14,21 @@ import femx  # noqa: E402
 CONFIGS = [
     dict(lattice=0),
     dict(),
-    dict(lt_pf=1),
-    dict(lt_minb=2),
-    dict(lt_minb=4),
-    dict(lt_tx=16, lt_ty=8),
-    dict(lt_tx=8, lt_ty=12),
-    dict(lt_tx=8, lt_ty=8, lt_minb=6),
-    dict(lt_tx=8, lt_ty=8, lt_minb=5),
-    dict(lt_tx=4, lt_ty=16, lt_minb=6),
-    dict(lt_tx=8, lt_ty=24, lt_minb=2),
-    dict(lt_tx=16, lt_ty=16, lt_minb=1),
-    dict(lt_tx=16, lt_ty=16, lt_minb=2),
-    dict(lt_tx=8, lt_ty=32, lt_minb=1),
-    dict(lt_tx=32, lt_ty=8, lt_minb=1),
+    dict(lt_side=0),
+    dict(lt_unroll=2),
+    dict(lt_unroll=2, lt_side=0),
     dict(lt_kc=64),
-    dict(lt_kc=16),
-    dict(carveout=100),
-    dict(rcp3=1)]
-DEFAULTS = dict(lattice=1, lt_tx=0, lt_ty=0, lt_minb=0, lt_kc=0, lt_pf=0, lt_regs=0, carveout=-1, rcp3=0)
+    dict(lt_kc=32),
+    dict(lt_kc=128),
+    dict(lt_unroll=2, rcp3=1),
+    dict(lt_tx=8, lt_ty=16),
+    dict(lt_tx=8, lt_ty=16, lt_unroll=2),
+    dict(lt_tx=32, lt_ty=4),
+    dict(lt_tx=16, lt_ty=8, lt_regs=152),
+    dict(lt_tx=16, lt_ty=8, lt_minb=4, lt_unroll=2),
+    dict(lt_tx=16, lt_ty=6, lt_minb=4),
+    dict(lt_tx=16, lt_ty=12, lt_minb=2)]
+DEFAULTS = dict(lattice=1, lt_tx=0, lt_ty=0, lt_minb=0, lt_kc=0, lt_pf=0, lt_regs=0, carveout=-1, rcp3=0, lt_unroll=1, lt_side=1)
 
 
 def main():
