@@ -28,7 +28,7 @@ CONFIGS = [
     dict(lt_tx=16, lt_ty=8, lt_minb=4, lt_unroll=2),
     dict(lt_tx=16, lt_ty=6, lt_minb=4),
     dict(lt_tx=16, lt_ty=12, lt_minb=2)]
-DEFAULTS = dict(lattice=1, lt_tx=0, lt_ty=0, lt_minb=0, lt_kc=0, lt_pf=0, lt_regs=0, carveout=-1, rcp3=0, lt_unroll=1, lt_side=1)
+DEFAULTS = dict(lattice=1, lt_tx=0, lt_ty=0, lt_minb=0, lt_kc=0, lt_pf=0, lt_regs=0, carveout=-1, rcp3=0, lt_unroll=2, lt_side=1)
 
 
 def main():
