@@ -38,8 +38,15 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     ctx = femx.Context(0)
-    mesh = ctx.box_mesh(n, n, n)
-    pat = femx.Pattern(ctx, mesh)
+    if os.environ.get("LATTICE_SLAB"):     # "rank/world": time one rank's z-slab of the n^3 cube (strong-scaling tuning)
+        rank, world = (int(v) for v in os.environ["LATTICE_SLAB"].split("/"))
+        r0, r1, lo, hi = femx.dist_slab(n + 1, world, rank)
+        plane = (n + 1) ** 2
+        mesh = ctx.box_mesh(n, n, n, k_lo=lo, k_hi=hi)
+        pat = femx.Pattern(ctx, mesh, row_begin=(r0 - lo) * plane, row_end=(r1 - lo) * plane, col_base=lo * plane)
+    else:
+        mesh = ctx.box_mesh(n, n, n)
+        pat = femx.Pattern(ctx, mesh)
     b_alg = mesh.n_elems * 16 + mesh.n_nodes * 24 + pat.nnz * 8
     print(json.dumps(dict(n=n, elems=mesh.n_elems, nnz=pat.nnz, lattice=pat.lattice() is not None)), flush=True)
     ref = None
