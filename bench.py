@@ -586,7 +586,10 @@ def main():
                   "spmv_nnz_per_s": nnz_global / (spmv_ms * 1e-3),
                   "residual@0": float(res[0]), "residual@100": float(res[100]), "rms_error_vs_exact_solution_1": err1,
                   "collectives_per_iteration": {"ncclSend/ncclRecv (grouped, halo of r)": 2 if world > 1 else 0,
-                                                "ncclAllReduce (2 doubles, fused)": 1 if world > 1 else 0},
+                                                "reduction of 2 doubles": (0 if world == 1 else 1),
+                                                "reduction_path": ("none (1 rank)" if world == 1 else
+                                                                   ("NVLink peer memory, fused into the kernel that finishes the dot products and advances alpha/beta"
+                                                                    if dd.p2p_reduction else "ncclAllReduce"))},
                   "interior_rows_overlap_halo": [op.interior_lo, op.interior_hi],
                   "method": "Chronopoulos-Gear CG, iteration replayed from a CUDA graph, femx_dist_cg (C++ behind the C ABI)"}
             op.close(); dd.close()

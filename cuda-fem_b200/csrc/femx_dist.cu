@@ -34,6 +34,7 @@ struct nccl_api {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
   std::string err;
@@ -51,6 +52,7 @@ const nccl_api* get_nccl() {
         {"ncclCommDestroy", (void**)&api.CommDestroy}, {"ncclGroupStart", (void**)&api.GroupStart},
         {"ncclGroupEnd", (void**)&api.GroupEnd},       {"ncclSend", (void**)&api.Send},
         {"ncclRecv", (void**)&api.Recv},               {"ncclAllReduce", (void**)&api.AllReduce},
+        {"ncclAllGather", (void**)&api.AllGather},
         {"ncclGetErrorString", (void**)&api.GetErrorString},
     };
     for (auto& s : syms) {
@@ -71,7 +73,16 @@ struct femx_dist {
   cudaStream_t s_comm = nullptr;   // the halo travels here while interior rows are multiplied on the compute stream
   cudaStream_t s_main = nullptr;   // compute stream of femx_dist_cg (a capturable stream: the caller's may be the legacy stream)
   cudaEvent_t e_ready = nullptr, e_halo = nullptr, e_in = nullptr;
+  // NVLink peer memory for the fused reduction of the CG (dot products -> all-reduce -> CG scalars in ONE kernel):
+  // every rank owns 2 x world slots, peers[r] is rank r's buffer mapped through CUDA IPC (peers[rank] = own buffer)
+  struct p2p_slot* p2p_mine = nullptr;
+  struct p2p_slot** d_peers = nullptr;   // device array [world]
+  std::vector<void*> p2p_opened;         // IPC mappings to close
+  unsigned long long* d_seq = nullptr;   // reductions done so far (the same number on every rank)
+  bool p2p = false;
 };
+
+struct p2p_slot { double v[2]; unsigned long long seq; unsigned long long pad; };
 
 struct femx_dist_op {
   femx_dist* d = nullptr;
@@ -151,8 +162,8 @@ __global__ void __launch_bounds__(256) dot2_fin_k(const double* __restrict__ par
   if (threadIdx.x == 0) { out[0] = sh0[0]; out[1] = sh1[0]; }
 }
 
-// Chronopoulos-Gear recurrences from the reduced gamma = (r,r), delta = (w,r); records gamma
-__global__ void cg_scalars_k(double* __restrict__ sc, double* __restrict__ hist, int* __restrict__ it) {
+// Chronopoulos-Gear recurrences (device function): from the reduced gamma = (r,r), delta = (w,r); records gamma
+__device__ __forceinline__ void cg_scalars(double* __restrict__ sc, double* __restrict__ hist, int* __restrict__ it) {
   const int k = *it;
   const double gamma = sc[0], delta = sc[1];
   double beta = 0.0, alpha;
@@ -166,6 +177,58 @@ __global__ void cg_scalars_k(double* __restrict__ sc, double* __restrict__ hist,
   sc[2] = gamma; sc[3] = alpha; sc[4] = alpha; sc[5] = beta;
   *it = k + 1;
 }
+
+// ONE kernel (one CTA) for "finish the two dot products, sum them over the ranks, advance the CG scalars":
+// the block reduces this rank's partial sums, thread r < world stores them (then a sequence number, behind a system-scope
+// fence) into slot [parity][rank] of rank r's buffer over NVLink, polls slot [parity][r] of the own buffer, and thread 0 adds
+// the world contributions in rank order — the same order on every rank, so every rank holds the same bits — and runs the
+// recurrences.  Replaces dot2_fin_k + ncclAllReduce (2 doubles) + cg_scalars_k; slots alternate by parity so that a rank one
+// reduction ahead never overwrites what a slower rank still reads.
+__global__ void __launch_bounds__(256) cg_reduce_p2p_k(const double* __restrict__ part, int nblocks, double* __restrict__ sc,
+                                                       double* __restrict__ hist, int* __restrict__ it,
+                                                       p2p_slot* const* __restrict__ peers, int rank, int world,
+                                                       unsigned long long* __restrict__ seq_counter) {
+  __shared__ double sh0[256], sh1[256];
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) { s0 += part[i]; s1 += part[FEMX_DOT_BLOCKS + i]; }
+  sh0[threadIdx.x] = s0; sh1[threadIdx.x] = s1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh0[threadIdx.x] += sh0[threadIdx.x + o]; sh1[threadIdx.x] += sh1[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  const double m0 = sh0[0], m1 = sh1[0];
+  __syncthreads();
+  if (world > 1) {
+    const unsigned long long seq = *seq_counter + 1;
+    const int par = (int)(seq & 1);
+    if ((int)threadIdx.x < world) {
+      const int r = threadIdx.x;
+      volatile p2p_slot* dst = peers[r] + par * world + rank;      // my contribution, in rank r's buffer
+      dst->v[0] = m0;
+      dst->v[1] = m1;
+      __threadfence_system();
+      dst->seq = seq;
+      volatile p2p_slot* src = peers[rank] + par * world + r;      // rank r's contribution, in my buffer
+      while (src->seq != seq) { }
+      __threadfence_system();
+      sh0[r] = src->v[0];
+      sh1[r] = src->v[1];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double g = 0.0, d = 0.0;
+      for (int r = 0; r < world; ++r) { g += sh0[r]; d += sh1[r]; }
+      sc[0] = g; sc[1] = d;
+      *seq_counter = seq;
+    }
+  } else if (threadIdx.x == 0) {
+    sc[0] = m0; sc[1] = m1;
+  }
+  if (threadIdx.x == 0) cg_scalars(sc, hist, it);
+}
+
+__global__ void cg_scalars_k(double* __restrict__ sc, double* __restrict__ hist, int* __restrict__ it) { cg_scalars(sc, hist, it); }
 
 __global__ void cg_final_k(const double* __restrict__ sc, double* __restrict__ hist, const int* __restrict__ it) { hist[*it] = sc[0]; }
 
@@ -228,6 +291,7 @@ int spmv_overlapped(femx_dist_op* op, void* ext, void* y, cudaStream_t st) {
   return rc;
 }
 
+// (gamma, delta) = ((r,r), (w,r)) summed over the ranks, then the CG scalars for the next update — ONE reduction per iteration
 int reduce2(femx_dist_op* op, const void* r, const void* w, cudaStream_t st) {
   femx_dist* d = op->d;
   const int64_t n = op->n_owned;
@@ -236,9 +300,16 @@ int reduce2(femx_dist_op* op, const void* r, const void* w, cudaStream_t st) {
     dot2_part_k<double><<<blocks, 256, 0, st>>>(n, (const double*)r, (const double*)w, (const double*)r, op->d_part);
   else
     dot2_part_k<float><<<blocks, 256, 0, st>>>(n, (const float*)r, (const float*)w, (const float*)r, op->d_part);
+  if (d->world == 1 || d->p2p) {
+    cg_reduce_p2p_k<<<1, 256, 0, st>>>(op->d_part, blocks, op->d_sc, op->d_hist, op->d_it, d->d_peers, d->rank, d->world, d->d_seq);
+    FEMX_CUDA_OK(d->ctx, cudaGetLastError());
+    return FEMX_OK;
+  }
   dot2_fin_k<<<1, 256, 0, st>>>(op->d_part, blocks, op->d_sc);
   FEMX_CUDA_OK(d->ctx, cudaGetLastError());
-  if (d->world > 1) ND_OK(d, get_nccl()->AllReduce(op->d_sc, op->d_sc, 2, ncclDouble, ncclSum, d->comm, st));  // ONE per iteration
+  ND_OK(d, get_nccl()->AllReduce(op->d_sc, op->d_sc, 2, ncclDouble, ncclSum, d->comm, st));
+  cg_scalars_k<<<1, 1, 0, st>>>(op->d_sc, op->d_hist, op->d_it);
+  FEMX_CUDA_OK(d->ctx, cudaGetLastError());
   return FEMX_OK;
 }
 
@@ -247,7 +318,6 @@ int cg_iteration(femx_dist_op* op, void* x, cudaStream_t st) {
   const int64_t n = op->n_owned;
   const size_t es = esize(op->dtype);
   void* r = (char*)op->r_ext + op->ghost_lo * es;
-  cg_scalars_k<<<1, 1, 0, st>>>(op->d_sc, op->d_hist, op->d_it);
   if (op->dtype == FEMX_F64)
     cg_update_k<double><<<nb256(n), 256, 0, st>>>(n, op->d_sc, (double*)r, (const double*)op->w, (double*)op->p, (double*)op->s, (double*)x);
   else
@@ -256,6 +326,49 @@ int cg_iteration(femx_dist_op* op, void* x, cudaStream_t st) {
   int rc = spmv_overlapped(op, op->r_ext, op->w, st);
   if (rc != FEMX_OK) return rc;
   return reduce2(op, r, op->w, st);
+}
+
+
+// Peer buffers of the fused reduction: every rank allocates 2 x world slots, the IPC handles travel over one ncclAllGather,
+// every rank maps the others' buffers (NVLink peer access).  All ranks agree on success through an all-reduce (MIN), so either
+// every rank uses the peer path or none does.
+void dist_setup_p2p(femx_dist* d) {
+  const nccl_api* nc = get_nccl();
+  const int world = d->world;
+  bool ok = true;
+  unsigned char* d_h = nullptr;
+  std::vector<unsigned char> h((size_t)world * sizeof(cudaIpcMemHandle_t));
+  if (cudaMalloc((void**)&d->p2p_mine, sizeof(p2p_slot) * 2 * world) != cudaSuccess) ok = false;
+  if (ok && cudaMemset(d->p2p_mine, 0, sizeof(p2p_slot) * 2 * world) != cudaSuccess) ok = false;
+  cudaIpcMemHandle_t mine;
+  if (ok && cudaIpcGetMemHandle(&mine, d->p2p_mine) != cudaSuccess) ok = false;
+  if (cudaMalloc((void**)&d_h, h.size()) != cudaSuccess) { (void)cudaGetLastError(); return; }
+  if (ok) cudaMemcpy(d_h + (size_t)d->rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice);
+  // (collective calls are made by every rank whatever `ok` is, so that nobody hangs)
+  ncclResult_t r = nc->AllGather(d_h + (size_t)d->rank * sizeof mine, d_h, sizeof mine, ncclUint8, d->comm, d->s_comm);
+  if (r != ncclSuccess || cudaStreamSynchronize(d->s_comm) != cudaSuccess) ok = false;
+  cudaMemcpy(h.data(), d_h, h.size(), cudaMemcpyDeviceToHost);
+  std::vector<p2p_slot*> peers(world, nullptr);
+  for (int q = 0; q < world && ok; ++q) {
+    if (q == d->rank) { peers[q] = d->p2p_mine; continue; }
+    cudaIpcMemHandle_t hq;
+    memcpy(&hq, h.data() + (size_t)q * sizeof hq, sizeof hq);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+    d->p2p_opened.push_back(p);
+    peers[q] = (p2p_slot*)p;
+  }
+  if (ok && cudaMalloc((void**)&d->d_peers, sizeof(p2p_slot*) * world) != cudaSuccess) ok = false;
+  if (ok) cudaMemcpy(d->d_peers, peers.data(), sizeof(p2p_slot*) * world, cudaMemcpyHostToDevice);
+  (void)cudaGetLastError();
+  // agreement (and a barrier: every buffer is zeroed and mapped before anyone's first reduction)
+  double flag = ok ? 1.0 : 0.0, *d_flag = (double*)d_h;
+  cudaMemcpy(d_flag, &flag, sizeof flag, cudaMemcpyHostToDevice);
+  r = nc->AllReduce(d_flag, d_flag, 1, ncclDouble, ncclMin, d->comm, d->s_comm);
+  if (r == ncclSuccess && cudaStreamSynchronize(d->s_comm) == cudaSuccess) cudaMemcpy(&flag, d_flag, sizeof flag, cudaMemcpyDeviceToHost);
+  else flag = 0.0;
+  cudaFree(d_h);
+  d->p2p = flag == 1.0;
 }
 
 }  // namespace
@@ -302,12 +415,24 @@ int femx_dist_create(femx_ctx* ctx, int rank, int world, const void* h_id, femx_
     femx_dist_destroy(d);
     return femx_fail(ctx, FEMX_ERR_CUDA, "femx_dist_create: %s", cudaGetErrorString(e));
   }
+  // sequence counter of the fused reduction (also used at world == 1) and, for world > 1, the peer buffers
+  e = cudaMalloc((void**)&d->d_seq, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(d->d_seq, 0, sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    femx_dist_destroy(d);
+    return femx_fail(ctx, FEMX_ERR_NOMEM, "femx_dist_create: %s", cudaGetErrorString(e));
+  }
+  if (world > 1 && ctx->knobs.dist_p2p != 0) dist_setup_p2p(d);   // failure is not an error: the NCCL all-reduce stays
   *out = d;
   return FEMX_OK;
 }
 
 void femx_dist_destroy(femx_dist* d) {
   if (!d) return;
+  for (void* p : d->p2p_opened) cudaIpcCloseMemHandle(p);
+  cudaFree(d->p2p_mine);
+  cudaFree(d->d_peers);
+  cudaFree(d->d_seq);
   if (d->comm) get_nccl()->CommDestroy(d->comm);
   if (d->s_comm) cudaStreamDestroy(d->s_comm);
   if (d->s_main) cudaStreamDestroy(d->s_main);
@@ -427,6 +552,14 @@ void femx_dist_op_destroy(femx_dist_op* op) {
   delete op;
 }
 
+int femx_dist_info(const femx_dist* d, int* rank, int* world, int* p2p_reduction) {
+  if (!d) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_dist_info: NULL argument");
+  if (rank) *rank = d->rank;
+  if (world) *world = d->world;
+  if (p2p_reduction) *p2p_reduction = d->p2p ? 1 : 0;
+  return FEMX_OK;
+}
+
 int femx_dist_op_info(const femx_dist_op* op, int64_t* n_owned, int64_t* ghost_lo, int64_t* ghost_hi, int64_t* interior_lo,
                       int64_t* interior_hi) {
   if (!op) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_dist_op_info: NULL argument");
@@ -513,7 +646,6 @@ int femx_dist_cg(femx_dist_op* op, const void* d_b_owned, void* d_x_owned, int i
       if (rc != FEMX_OK) return fail(rc);
     }
   }
-  cg_final_k<<<1, 1, 0, st>>>(op->d_sc, op->d_hist, op->d_it);
   CG_CUDA(cudaEventRecord(t1, st));
   std::vector<double> hist(iters + 1);
   CG_CUDA(cudaMemcpyAsync(hist.data(), op->d_hist, sizeof(double) * (iters + 1), cudaMemcpyDeviceToHost, st));

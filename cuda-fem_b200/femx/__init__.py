@@ -49,7 +49,7 @@ class _MeshView(C.Structure):
 SYMBOLS = [
     "femx_ctx_create", "femx_ctx_destroy", "femx_last_error", "femx_version", "femx_ctx_set_option",
     "femx_pattern_lattice", "femx_form_cubin_lattice",
-    "femx_dist_unique_id", "femx_dist_create", "femx_dist_destroy", "femx_dist_slab", "femx_dist_allreduce",
+    "femx_dist_unique_id", "femx_dist_create", "femx_dist_info", "femx_dist_destroy", "femx_dist_slab", "femx_dist_allreduce",
     "femx_dist_op_create", "femx_dist_op_destroy", "femx_dist_op_info", "femx_dist_spmv", "femx_dist_cg", "femx_spmv_rows",
     "femx_form_compile", "femx_form_compile_offline", "femx_form_destroy", "femx_form_source",
     "femx_form_log", "femx_form_entry", "femx_form_prologue", "femx_form_cubin",
@@ -500,6 +500,13 @@ class Dist:
             t.copy_(torch.frombuffer(bytearray(dist_unique_id()), dtype=torch.uint8))
         dist.broadcast(t, 0)
         return Dist(ctx, rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    @property
+    def p2p_reduction(self):
+        """True when the CG reduction runs over NVLink peer memory (femx_dist_info)."""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self.ctx.check(lib().femx_dist_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return bool(c.value)
 
     def allreduce(self, t, op="sum", stream=None):
         """in-place on a float64 device tensor"""

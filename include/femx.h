@@ -342,6 +342,10 @@ typedef struct femx_dist_op femx_dist_op;  /* this rank's rows of the operator +
 int femx_dist_unique_id(void* h_id);
 int femx_dist_create(femx_ctx* ctx, int rank, int world, const void* h_id, femx_dist** out);  /* world == 1: h_id may be NULL */
 void femx_dist_destroy(femx_dist* d);
+/* *p2p_reduction = 1 when the CG's reduction runs over NVLink peer memory (CUDA IPC buffers of all ranks mapped into every
+ * rank): one kernel finishes the two dot products, exchanges the partial sums with every peer and advances the CG scalars;
+ * 0 = ncclAllReduce (peer mapping unavailable, or option dist_p2p = 0). */
+int femx_dist_info(const femx_dist* d, int* rank, int* world, int* p2p_reduction);
 /* Even split of n_planes node planes over `world` ranks: owned planes [r0, r1), slab planes [lo, hi]. */
 int femx_dist_slab(int64_t n_planes, int world, int rank, int64_t* r0, int64_t* r1, int64_t* lo, int64_t* hi);
 /* In-place sum (op_max = 0) or max (1) of n doubles across ranks (timing / checksums of the harness). */
@@ -357,7 +361,8 @@ int femx_dist_op_info(const femx_dist_op* op, int64_t* n_owned, int64_t* ghost_l
 /* y_owned = A[owned rows] x, x given by its owned part on every rank (device pointers, n_owned entries each). */
 int femx_dist_spmv(femx_dist_op* op, const void* d_x_owned, void* d_y_owned, void* stream);
 /* `iters` steps of unpreconditioned CG from x0 = 0 (Chronopoulos-Gear form: one SpMV, one fused update kernel and
- * ONE all-reduce of two doubles per iteration; the iteration is captured in a CUDA graph and replayed).
+ * ONE reduction of two doubles per iteration — over NVLink peer memory, fused into the kernel that finishes the dot products
+ * and advances alpha / beta (femx_dist_info), else ncclAllReduce; the iteration is captured in a CUDA graph and replayed).
  * h_residuals (host, iters+1 entries, may be NULL) receives ||r_k||_2; *h_ms (may be NULL) the device time of the solve.
  * Synchronises the stream before returning. */
 int femx_dist_cg(femx_dist_op* op, const void* d_b_owned, void* d_x_owned, int iters, double* h_residuals, float* h_ms,
