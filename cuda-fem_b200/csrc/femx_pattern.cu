@@ -400,8 +400,8 @@ __global__ void other_fill(const int2* __restrict__ rowinfo, int n_rows, const i
 
 // ---------------------------------------------------------------- exports ---
 __global__ void export_csr_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx, int n_rows,
-                             int nd, int col_base, long long* __restrict__ rp64, int* __restrict__ rp32,
-                             int* __restrict__ dcol) {
+                             int nd, int col_base, const int* __restrict__ l2g, long long* __restrict__ rp64,
+                             int* __restrict__ rp32, int* __restrict__ dcol) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // dof row
   int64_t nrows_d = (int64_t)n_rows * nd;
   if (t > nrows_d) return;
@@ -418,7 +418,7 @@ __global__ void export_csr_k(const int2* __restrict__ rowinfo, const int* __rest
   if (rp32) rp32[t] = (int)start;
   if (dcol)
     for (int p = 0; p < len; ++p) {
-      int col = col_idx[lo + p] + col_base;
+      int col = l2g ? l2g[col_idx[lo + p]] : col_idx[lo + p] + col_base;
       for (int d = 0; d < nd; ++d) dcol[start + (long long)p * nd + d] = col * nd + d;
     }
 }
@@ -1254,7 +1254,20 @@ int femx_pattern_export_csr(const femx_pattern* p, int64_t* d_rp64, int32_t* d_r
   FEMX_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
   int64_t n = p->n_rows * p->nd + 1;
   export_csr_k<<<nblocks(n, 128), 128, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd,
-                                                                  (int)p->col_base, (long long*)d_rp64, d_rp32, d_col);
+                                                                  (int)p->col_base, nullptr, (long long*)d_rp64, d_rp32, d_col);
+  FEMX_CUDA_OK(p->ctx, cudaGetLastError());
+  return FEMX_OK;
+}
+
+int femx_pattern_export_csr_mapped(const femx_pattern* p, const int32_t* d_local_to_global, int64_t* d_rp64, int32_t* d_rp32,
+                                   int32_t* d_col, void* stream) {
+  if (!p || !d_local_to_global) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_pattern_export_csr_mapped: NULL argument");
+  if (d_rp32 && p->nnz_node * p->nd * p->nd >= (1LL << 31) - 1)
+    return femx_fail(p->ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_export_csr_mapped: nnz does not fit a 32-bit row_ptr");
+  FEMX_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
+  int64_t n = p->n_rows * p->nd + 1;
+  export_csr_k<<<nblocks(n, 128), 128, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)p->n_rows, p->nd, 0,
+                                                                  d_local_to_global, (long long*)d_rp64, d_rp32, d_col);
   FEMX_CUDA_OK(p->ctx, cudaGetLastError());
   return FEMX_OK;
 }

@@ -49,7 +49,9 @@ class _MeshView(C.Structure):
 SYMBOLS = [
     "femx_ctx_create", "femx_ctx_destroy", "femx_last_error", "femx_version", "femx_ctx_set_option",
     "femx_pattern_lattice", "femx_form_cubin_lattice",
-    "femx_dist_unique_id", "femx_dist_create", "femx_dist_info", "femx_dist_destroy", "femx_dist_slab", "femx_dist_allreduce",
+    "femx_dist_unique_id", "femx_dist_create", "femx_dist_info",
+    "femx_partition_extract", "femx_part_destroy", "femx_part_info", "femx_part_arrays", "femx_part_copy", "femx_part_gather",
+    "femx_pattern_export_csr_mapped", "femx_dist_destroy", "femx_dist_slab", "femx_dist_allreduce",
     "femx_dist_op_create", "femx_dist_op_destroy", "femx_dist_op_info", "femx_dist_spmv", "femx_dist_cg", "femx_spmv_rows",
     "femx_form_compile", "femx_form_compile_offline", "femx_form_destroy", "femx_form_source",
     "femx_form_log", "femx_form_entry", "femx_form_prologue", "femx_form_cubin",
@@ -451,6 +453,52 @@ class Pattern:
     def close(self):
         if self.h:
             lib().femx_pattern_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Partition:
+    """Ghost-element sub-mesh of the rank that owns global nodes [node_lo, node_hi) of an unstructured mesh
+    (femx_partition_extract): local connectivity, local -> global node map, owned local rows [row_begin, row_end)."""
+
+    def __init__(self, ctx, mesh, node_lo, node_hi, stream=None):
+        import torch
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        ctx.check(lib().femx_partition_extract(ctx.h, mesh.nn, _i64(mesh.n_nodes), _i64(mesh.n_elems), _vp(mesh.conn),
+                                               _i64(node_lo), _i64(node_hi), _stream(stream), C.byref(self.h)))
+        v = [C.c_int64() for _ in range(4)]
+        ctx.check(lib().femx_part_info(self.h, *[C.byref(x) for x in v]))
+        self.n_nodes, self.n_elems, self.row_begin, self.row_end = (x.value for x in v)
+        dev = mesh.conn.device
+        self.l2g = torch.empty(self.n_nodes, dtype=torch.int32, device=dev)
+        self.conn = torch.empty((self.n_elems, mesh.nn), dtype=torch.int32, device=dev)
+        self.elem_ids = torch.empty(self.n_elems, dtype=torch.int32, device=dev)
+        ctx.check(lib().femx_part_copy(self.h, _vp(self.conn), _vp(self.l2g), _vp(self.elem_ids), _stream(stream)))
+        # node coordinates of the sub-mesh
+        xyz = []
+        for c in mesh.node_xyz:
+            o = torch.empty(self.n_nodes, dtype=c.dtype, device=dev)
+            dt = F64 if c.dtype == torch.float64 else F32
+            ctx.check(lib().femx_part_gather(self.h, dt, _vp(c), _vp(o), _stream(stream)))
+            xyz.append(o)
+        self.mesh = Mesh(mesh.dim, self.conn, tuple(xyz))
+
+    def pattern(self, nd=1, stream=None):
+        return Pattern(self.ctx, self.mesh, nd=nd, row_begin=self.row_begin, row_end=self.row_end, stream=stream)
+
+    def global_csr(self, pattern, stream=None):
+        """row_ptr (int64, relative to the rank's first row) and GLOBAL column ids of the rank's rows."""
+        import torch
+        dev = self.conn.device
+        rp = torch.empty(pattern.n_rows + 1, dtype=torch.int64, device=dev)
+        col = torch.empty(pattern.nnz, dtype=torch.int32, device=dev)
+        self.ctx.check(lib().femx_pattern_export_csr_mapped(pattern.h, _vp(self.l2g), _vp(rp), _vp(None), _vp(col), _stream(stream)))
+        return rp, col
+
+    def close(self):
+        if self.h:
+            lib().femx_part_destroy.argtypes = [C.c_void_p]
+            lib().femx_part_destroy(self.h)
             self.h = C.c_void_p()
 
 

@@ -371,6 +371,30 @@ int femx_dist_cg(femx_dist_op* op, const void* d_b_owned, void* d_x_owned, int i
 int femx_spmv_rows(const femx_pattern* pat, int dtype, const void* d_values, const void* d_x, int64_t x_base, void* d_y,
                    int64_t row_lo, int64_t row_hi, void* stream);
 
+/* Unstructured meshes: partition by owned CSR rows with duplicated ghost elements.  The rank owns the contiguous node range
+ * [node_lo, node_hi) of the caller's numbering (e.g. equal ranges after an RCM / space-filling-curve ordering).  The extraction
+ * keeps every element that touches an owned node (ascending element id), renumbers the touched nodes by their rank among the
+ * sorted global ids (owned nodes stay contiguous: local rows [row_begin, row_end)) and keeps the local -> global map.
+ * femx_pattern_build(nn, nd, n_local_nodes, n_local_elems, d_conn_local, row_begin, row_end, 0, ...) + femx_assemble_csr on
+ * the gathered coordinates then give the rank's rows of the GLOBAL matrix, bit-identical to the single-GPU rows and with no
+ * communication; femx_pattern_export_csr_mapped writes global column ids.  (The SpMV / CG validator handles slab partitions only.) */
+typedef struct femx_part femx_part;
+int femx_partition_extract(femx_ctx* ctx, int nn, int64_t n_nodes, int64_t n_elems, const int32_t* d_conn, int64_t node_lo,
+                           int64_t node_hi, void* stream, femx_part** out);
+void femx_part_destroy(femx_part* part);
+int femx_part_info(const femx_part* part, int64_t* n_local_nodes, int64_t* n_local_elems, int64_t* row_begin, int64_t* row_end);
+/* Device arrays owned by the object: local connectivity [n_local_elems * nn], local -> global node ids [n_local_nodes]
+ * (ascending), global ids of the kept elements [n_local_elems] (ascending). */
+int femx_part_arrays(const femx_part* part, const int32_t** d_conn_local, const int32_t** d_local_to_global,
+                     const int32_t** d_elem_ids);
+/* The same arrays copied into caller-owned device buffers (any pointer may be NULL). */
+int femx_part_copy(const femx_part* part, int32_t* d_conn_local, int32_t* d_local_to_global, int32_t* d_elem_ids, void* stream);
+/* d_local[i] = d_global[local_to_global[i]] (node coordinates of the sub-mesh). */
+int femx_part_gather(const femx_part* part, int dtype, const void* d_global, void* d_local, void* stream);
+/* femx_pattern_export_csr with the columns mapped through d_local_to_global instead of shifted by col_base. */
+int femx_pattern_export_csr_mapped(const femx_pattern* pat, const int32_t* d_local_to_global, int64_t* d_row_ptr64,
+                                   int32_t* d_row_ptr32, int32_t* d_col_idx, void* stream);
+
 /* ------------------------------------------------ host-side I/O (no device needed) */
 
 /* Gmsh MSH 2.x ASCII: 3-node triangles, or 4-node tetrahedra when present (the boundary triangles of
