@@ -1052,6 +1052,8 @@ int femx_assemble_rhs(femx_form* form, const femx_pattern* pat, const femx_mesh_
   if (pat->n_rows == 0) return FEMX_OK;
   if (!d_rhs) return femx_fail(form->ctx, FEMX_ERR_INVALID, "femx_assemble_rhs: d_rhs is NULL");
   FEMX_CUDA_OK(form->ctx, cudaSetDevice(form->ctx->device));
+  st = femx_pattern_complete_map(pat, stream);   // the load vector walks every row's scatter map
+  if (st != FEMX_OK) return st;
   Variant* v = nullptr;
   st = compile_variant(form, "rhs", &v, true);
   if (st != FEMX_OK) return st;
@@ -1258,6 +1260,8 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
       }
     }
     if (!spec) {
+      st = femx_pattern_complete_map(pat, stream);   // the generic pass reads every row's scatter map
+      if (st != FEMX_OK) return st;
       st = compile_variant(form, kname, &v, true, nullptr, pat->tile_nodes);
       if (st != FEMX_OK) return st;
     }

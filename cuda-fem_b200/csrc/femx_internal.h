@@ -123,9 +123,14 @@ struct femx_pattern {
   int32_t* d_other_rows = nullptr;   // [n_other] rows outside the class, ascending (device)
   int64_t n_other = 0;
   int max_row_other = 0;             // longest of those rows
+  bool map_complete = true;          // false: the scatter map of the class rows is not written yet (femx_pattern_complete_map)
+  void* d_lat_tmpl = nullptr;        // row templates of the lattice-templated pass (device), kept for that completion
+  int lat_dom = -1;
   femx_lattice lat;                  // lattice structure of the mesh, if it has one (and a class was found)
   int64_t lat_rows = 0;              // class rows = lattice-interior nodes among the owned rows (checked)
 };
+
+int femx_pattern_complete_map(const femx_pattern* p, void* stream);
 
 // rowinfo[i].y = #incidences (bits 0-21) | (bit 22 reserved) | FEMX_ROW_SPEC | own position << 24
 #define FEMX_NP_MASK 0x3fffff

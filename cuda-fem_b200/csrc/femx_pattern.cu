@@ -797,19 +797,28 @@ __global__ void lat_row_len_k(lat_geom g, const lat_row_tmpl* __restrict__ T, in
 
 __global__ void lat_row_fill_k(lat_geom g, const lat_row_tmpl* __restrict__ T, const int* __restrict__ row_ptr,
                                const int* __restrict__ slice_ptr, int2* __restrict__ rowinfo, int* __restrict__ col_idx,
-                               unsigned* __restrict__ sell_code, int* __restrict__ sell_elem) {
+                               unsigned* __restrict__ sell_code, int* __restrict__ sell_elem, int map_only) {
+  // map_only = 0: rowinfo + columns of every row, scatter map of the rows OUTSIDE the dominant class (the class rows'
+  // map is read by no kernel of the default path and is written on demand: femx_pattern_complete_map);
+  // map_only = 1: the scatter map of the class rows
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r > g.n_rows) return;
-  if (r == g.n_rows) { rowinfo[r] = make_int2(row_ptr[r], 0); return; }
-  const int rp = row_ptr[r];
+  if (r == g.n_rows) { if (!map_only) rowinfo[r] = make_int2(row_ptr ? row_ptr[r] : 0, 0); return; }
   int ijk[3];
   const long long node = (long long)g.row_begin + r;
   const int c = lat_class_of(g, node, ijk);
-  if (c < 0) { rowinfo[r] = make_int2(rp, 0); return; }
+  if (!map_only) {
+    const int rp = row_ptr[r];
+    if (c < 0) { rowinfo[r] = make_int2(rp, 0); return; }
+    const lat_row_tmpl& t0 = T[c];
+    rowinfo[r] = make_int2(rp, t0.np | (c == g.dom ? FEMX_ROW_SPEC : 0) | (t0.self << 24));
+    for (int k = 0; k < t0.rlen; ++k)
+      col_idx[rp + k] = (int)(node + t0.col[k][0] + t0.col[k][1] * g.s[1] + t0.col[k][2] * g.s[2]);
+    if (c == g.dom) return;
+  } else if (c < 0 || c != g.dom) {
+    return;
+  }
   const lat_row_tmpl& t = T[c];
-  rowinfo[r] = make_int2(rp, t.np | (c == g.dom ? FEMX_ROW_SPEC : 0) | (t.self << 24));
-  for (int k = 0; k < t.rlen; ++k)
-    col_idx[rp + k] = (int)(node + t.col[k][0] + t.col[k][1] * g.s[1] + t.col[k][2] * g.s[2]);
   const int sp = slice_ptr[r >> 5] + (r & 31);
   for (int k = 0; k < t.np; ++k) {
     const long long cell = (ijk[0] + t.cell[k][0]) + (long long)g.cn[0] * ((ijk[1] + t.cell[k][1]) + (long long)g.cn[1] * (ijk[2] + t.cell[k][2]));
@@ -973,12 +982,9 @@ int build_from_lattice(femx_ctx* ctx, femx_pattern* p, cudaStream_t st) {
   p->n_sell = n_sell;
   LB_TRY(dev_alloc(ctx, &p->d_sell_code, n_sell, &p->bytes, st));
   LB_TRY(dev_alloc(ctx, &p->d_sell_elem, n_sell, &p->bytes, st));
-  if (n_sell > 0) {
-    LB_CUDA(cudaMemsetAsync(p->d_sell_code, 0, sizeof(unsigned) * n_sell, st));
-    LB_CUDA(cudaMemsetAsync(p->d_sell_elem, 0, sizeof(int) * n_sell, st));
-  }
+  // (no zero fill: the padding of a slice is copied by the generic pass's bulk loads but never used)
   lat_row_fill_k<<<nblocks(nr + 1, 128), 128, 0, st>>>(g, d_T, d_row_ptr, p->d_slice_ptr, p->d_rowinfo, p->d_col_idx,
-                                                       p->d_sell_code, p->d_sell_elem);
+                                                       p->d_sell_code, p->d_sell_elem, 0);
   LB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, st));
   if (nr > 0) {
     int64_t ntiles = (nr + p->tile_nodes - 1) / p->tile_nodes;
@@ -1007,11 +1013,45 @@ int build_from_lattice(femx_ctx* ctx, femx_pattern* p, cudaStream_t st) {
   } else {
     p->lat_rows = 0;
   }
+  // the scatter map of the class rows is completed on demand (femx_pattern_complete_map); keep what that needs
+  p->map_complete = !(g.dom >= 0 && n_dom > 0);
+  if (!p->map_complete) {
+    rc = dev_alloc(ctx, (lat_row_tmpl**)&p->d_lat_tmpl, 27, &p->bytes, st);
+    if (rc != FEMX_OK) { cleanup(); return rc; }
+    LB_CUDA(cudaMemcpyAsync(p->d_lat_tmpl, d_T, sizeof(lat_row_tmpl) * 27, cudaMemcpyDeviceToDevice, st));
+    p->lat_dom = g.dom;
+    LB_CUDA(cudaStreamSynchronize(st));
+  }
   cleanup();
   return FEMX_OK;
 #undef LB_TRY
 #undef LB_CUDA
 }
+
+}  // namespace
+
+// Patterns built by the lattice-templated pass leave out the scatter map of the class rows (3.1 of the 4.4 GB on cfg3):
+// the stencil-class and lattice numeric passes never read it.  The passes that do — the generic incidence loop over
+// all rows (unstructured fallback switched on by option, element-expanded coordinates, custom strings with contraction)
+// and the load vector — call this first; it runs once per pattern.
+int femx_pattern_complete_map(const femx_pattern* cp, void* stream) {
+  femx_pattern* p = const_cast<femx_pattern*>(cp);
+  if (!p || p->map_complete) return FEMX_OK;
+  FEMX_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
+  const femx_lattice& L = p->lat;
+  lat_geom g = {};
+  g.dim = L.dim; g.P = L.P; g.nn = p->nn;
+  for (int d = 0; d < 3; ++d) { g.cn[d] = L.cn[d]; g.s[d] = L.s[d]; }
+  g.node0 = L.node0; g.row_begin = (int)p->row_begin; g.n_rows = (int)p->n_rows;
+  g.dom = p->lat_dom;
+  lat_row_fill_k<<<nblocks(p->n_rows + 1, 128), 128, 0, (cudaStream_t)stream>>>(g, (const lat_row_tmpl*)p->d_lat_tmpl, nullptr, p->d_slice_ptr,
+                                                                                  p->d_rowinfo, p->d_col_idx, p->d_sell_code, p->d_sell_elem, 1);
+  FEMX_CUDA_OK(p->ctx, cudaGetLastError());
+  p->map_complete = true;
+  return FEMX_OK;
+}
+
+namespace {
 
 }  // namespace
 
@@ -1202,6 +1242,7 @@ void femx_pattern_destroy(femx_pattern* p) {
   cudaFree(p->d_sell_code);
   cudaFree(p->d_sell_elem);
   cudaFree(p->d_other_rows);
+  cudaFree(p->d_lat_tmpl);
   delete p;
 }
 

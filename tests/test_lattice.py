@@ -190,7 +190,7 @@ def test_lattice_templated_symbolic_pass_equals_general_pass(ctx, case):
             ctx.set_option("lattice_pattern", 1)
         rp, ci = pat.csr("int64")
         st = pat.stencil()
-        info = (pat.n_rows, pat.nnz, pat.max_row, pat.bytes)
+        info = (pat.n_rows, pat.nnz, pat.max_row)
         dim = mesh.dim
         form = femx.Form(ctx, dim, femx.ELASTICITY if nd == 3 else femx.POISSON_MASS, nd=nd, params=(0.6, 0.4) if nd == 3 else (1.0,))
         ctx.set_option("spec", 0)
