@@ -254,6 +254,12 @@ def ref_gpu_baseline_and_parity(ctx, femx, torch, wl, mesh, pat, vals):
                           "ok": bool(relF <= 1e-12 and relF_coo <= 1e-12 and (relF_hi is None or relF_hi <= 1e-12))}
                 del mine, ref, A_ref, A_mine
             del X, Y, ell, coo
+        try:   # the reference's accumulation micro-benchmark (atomicadd.cu:73-129), the contention K5 suffers
+            av = refimpl.atomic_variants()
+            if av:
+                out["atomicadd_variants"] = av
+        except Exception as e:
+            out["atomicadd_variants"] = {"error": repr(e)[:200]}
         return out, parity
     except Exception as e:  # a reported extra must never take the headline down
         return {"error": repr(e)}, None

@@ -153,6 +153,60 @@ def build_one(src_name, out_stem, shim, mesh_w_line, mesh_h_line):
         print("built", os.path.relpath(so, HERE))
 
 
+SHIM_ATOMIC = r'''
+// ---- shim (not reference code): times the reference's three accumulation variants on n values ----------
+// (atomicadd.cu:73-129: naive global atomicAdd, shared-memory staged block sum + one atomicAdd per block, CAS-loop double add;
+//  its main() launches only the first on SIZE = 50)
+extern "C" int ref_atomic_variants(long n, int iters, float* ms3, double* results3) {
+  float* dIn = 0; double* dInD = 0; float* dRes = 0; double* dResD = 0;
+  cudaMalloc(&dIn, n * sizeof(float)); cudaMalloc(&dInD, n * sizeof(double));
+  cudaMalloc(&dRes, sizeof(float)); cudaMalloc(&dResD, sizeof(double));
+  float* h = (float*)malloc(n * sizeof(float)); double* hd = (double*)malloc(n * sizeof(double));
+  for (long i = 0; i < n; i++) { h[i] = 1.0f; hd[i] = 1.0; }
+  cudaMemcpy(dIn, h, n * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemcpy(dInD, hd, n * sizeof(double), cudaMemcpyHostToDevice);
+  dim3 blk(BLOCK_X_NAIVE, BLOCK_Y_NAIVE, 1);
+  dim3 grd(BLOCK_COUNT_X, (unsigned)((n + (long)BLOCK_X_NAIVE * BLOCK_Y_NAIVE * BLOCK_COUNT_X - 1) / ((long)BLOCK_X_NAIVE * BLOCK_Y_NAIVE * BLOCK_COUNT_X)), 1);
+  ref_size = n;
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  for (int v = 0; v < 3; v++) {
+    float best = 1e30f;
+    for (int it = 0; it < iters; it++) {
+      cudaMemset(dRes, 0, sizeof(float)); cudaMemset(dResD, 0, sizeof(double));
+      cudaEventRecord(a);
+      if (v == 0) reductionKernel<<<grd, blk>>>(dRes, dIn);
+      if (v == 1) reductionKernel2<<<grd, blk>>>(dRes, dIn);
+      if (v == 2) reductionKernel3<<<grd, blk>>>(dResD, dInD);
+      cudaEventRecord(b); cudaEventSynchronize(b);
+      float ms; cudaEventElapsedTime(&ms, a, b);
+      if (ms < best) best = ms;
+    }
+    ms3[v] = best;
+    if (v < 2) { float r; cudaMemcpy(&r, dRes, sizeof r, cudaMemcpyDeviceToHost); results3[v] = r; }
+    else cudaMemcpy(&results3[v], dResD, sizeof(double), cudaMemcpyDeviceToHost);
+  }
+  int err = (int)cudaGetLastError();
+  cudaFree(dIn); cudaFree(dInD); cudaFree(dRes); cudaFree(dResD); free(h); free(hd);
+  return err;
+}
+'''
+
+
+def build_atomicadd():
+    """atomicadd.cu (SURVEY a10): the three accumulation variants as a timed side baseline.  In-memory edits: SIZE becomes a
+    run-time value, main is renamed, the per-thread debug printf of reductionKernel2 is removed."""
+    t = open(os.path.join(REF, "atomicadd.cu")).read()
+    t = sub_once(t, "#define SIZE 50\n", "__device__ __managed__ long ref_size = 50;\n#define SIZE ref_size\n", "SIZE")
+    t = sub_once(t, "int main()", "int ref_main_unused()", "main")
+    t = sub_once(t, '    printf("(%d %d) (%d %d) (%d %d)\\n",blockDim.x, blockDim.y, blockIdx.x, blockIdx.y, threadIdx.x, threadIdx.y);\n', "", "debug printf")
+    gen = os.path.join(GEN, "ref_atomicadd.cu")
+    open(gen, "w").write(t + SHIM_ATOMIC)
+    so = os.path.join(OUT, "libref_atomicadd.so")
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100,code=sm_100", "-O2", "-std=c++14", "-w", "-shared",
+                           "-Xcompiler", "-fPIC", "-cudart", "static", "-o", so, gen])
+    print("built", os.path.relpath(so, HERE))
+
+
 def main():
     if not os.path.isdir(REF):
         print("oracle/build_ref.py: /root/reference not present; keeping prebuilt oracle/_ref as is")
@@ -166,6 +220,7 @@ def main():
     subprocess.check_call([NVCC, "-gencode", "arch=compute_100,code=sm_100", "-O2", "-std=c++14", "-w", "-cudart", "static",
                            "-o", exe, os.path.join(REF, "fea_test_sm_sym_sparse2.cu")])
     print("built", os.path.relpath(exe, HERE), "(unmodified reference program)")
+    build_atomicadd()
     return 0
 
 

@@ -85,3 +85,17 @@ def assemble_ell(prec, n_row, n_col, X, Y, gIdx, ell_len, ell_idx, iters=1):
     torch.cuda.synchronize()
     assert err == 0, f"reference ELL kernel: CUDA error {err}"
     return A, ms.value
+
+
+def atomic_variants(n=10_240_000, iters=3):   # a multiple of the 32x32x100 grid row: the staged variant reads no unset shared memory
+    """The reference's three accumulation variants (atomicadd.cu:73-129) on n ones: ms per launch and the sums
+    (fp32 naive / fp32 shared-memory staged / fp64 CAS loop).  The contention K5 suffers, as a micro-benchmark."""
+    path = os.path.join(_REF, "libref_atomicadd.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    ms = (C.c_float * 3)()
+    res = (C.c_double * 3)()
+    err = L.ref_atomic_variants(C.c_long(n), int(iters), ms, res)
+    names = ("naive_global_atomicAdd_f32", "smem_staged_block_sum_f32", "cas_loop_f64")
+    return {"n": n, "cuda_error": err, **{k: {"ms": ms[i], "sum": res[i], "GBps": n * (4 if i < 2 else 8) / (ms[i] * 1e-3) / 1e9} for i, k in enumerate(names)}}
