@@ -28,10 +28,13 @@ __global__ void spmv_k(const int2* __restrict__ rowinfo, const int* __restrict__
 // asynchronous copies (cp.async, all in flight at once); each thread then walks its own row out of
 // shared memory and only the x gathers go through L1/L2.  (Thread-per-row straight from global
 // memory reads each row with a 15-element stride between lanes.)
+// column offsets (column - own node) of the pattern's stencil class, passed by value
+struct spmv_cls { int len; int off[24]; };
+
 template <class T, int TILE>
 __global__ void __launch_bounds__(TILE) spmv_tile_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx,
                                                      int row0, int n_rows, const T* __restrict__ vals, const T* __restrict__ x,
-                                                     long long x_off, T* __restrict__ y) {
+                                                     long long x_off, T* __restrict__ y, const spmv_cls cls, int row_node0) {
   extern __shared__ __align__(16) unsigned char sm[];
   const int i0 = row0 + blockIdx.x * TILE;   // rows [row0, n_rows)
   const int nt = min(TILE, n_rows - i0);
@@ -40,24 +43,36 @@ __global__ void __launch_bounds__(TILE) spmv_tile_k(const int2* __restrict__ row
   T* s_v = reinterpret_cast<T*>(sm);
   int* s_c = reinterpret_cast<int*>(s_v + cnt + (cnt & 1));
   const unsigned vdst = (unsigned)__cvta_generic_to_shared(s_v), cdst = (unsigned)__cvta_generic_to_shared(s_c);
+  int lo = 0, len = 0;
+  bool in_cls = true;
+  if ((int)threadIdx.x < nt) {
+    const int2 r0 = rowinfo[i0 + threadIdx.x];
+    lo = r0.x - base;
+    len = rowinfo[i0 + threadIdx.x + 1].x - base - lo;
+    in_cls = cls.len > 0 && (r0.y & FEMX_ROW_SPEC);
+  }
+  // A tile made of stencil-class rows only (every interior tile of a structured mesh) needs no column list: the
+  // columns of a class row are its own node + the class's constant offsets — 8 instead of 12 bytes per nonzero.
+  const bool all_cls = __syncthreads_and(in_cls);
   for (int j = threadIdx.x; j < cnt; j += TILE) {
     if (sizeof(T) == 8)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(vdst + j * 8), "l"(vals + base + j) : "memory");
     else
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(vdst + j * 4), "l"(vals + base + j) : "memory");
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cdst + j * 4), "l"(col_idx + base + j) : "memory");
+    if (!all_cls) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cdst + j * 4), "l"(col_idx + base + j) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  int lo = 0, len = 0;
-  if ((int)threadIdx.x < nt) {
-    lo = rowinfo[i0 + threadIdx.x].x - base;
-    len = rowinfo[i0 + threadIdx.x + 1].x - base - lo;
-  }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   if ((int)threadIdx.x < nt) {
     double s = 0.0;
-    for (int p = 0; p < len; ++p) s += (double)s_v[lo + p] * (double)__ldg(x + ((long long)s_c[lo + p] - x_off));
+    if (all_cls) {
+      const T* xr = x + ((long long)(row_node0 + i0 + (int)threadIdx.x) - x_off);
+#pragma unroll 4
+      for (int p = 0; p < len; ++p) s += (double)s_v[lo + p] * (double)__ldg(xr + cls.off[p]);
+    } else {
+      for (int p = 0; p < len; ++p) s += (double)s_v[lo + p] * (double)__ldg(x + ((long long)s_c[lo + p] - x_off));
+    }
     y[i0 + threadIdx.x] = (T)s;
   }
 }
@@ -158,16 +173,22 @@ int femx_spmv_range(const femx_pattern* p, int dtype, const void* d_values, cons
   if (p->nd == 1 && smem <= 200 * 1024 && p->tile_nodes == 128) {
     // tile-staged kernel (128-row tiles)
     const unsigned blocks = (unsigned)((row_hi - row_lo + 127) / 128);
+    spmv_cls cls = {};
+    if (p->spec_np > 0 && p->spec_rlen <= 24) {
+      cls.len = p->spec_rlen;
+      for (int k = 0; k < p->spec_rlen; ++k) cls.off[k] = p->spec_off[k];
+    }
+    const int row_node0 = (int)p->row_begin;
     if (dtype == FEMX_F64) {
       if (smem > 48 * 1024) cudaFuncSetAttribute(spmv_tile_k<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       spmv_tile_k<double, 128><<<blocks, 128, smem, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)row_lo, (int)row_hi,
                                                                              (const double*)d_values, (const double*)d_x, xb,
-                                                                             (double*)d_y);
+                                                                             (double*)d_y, cls, row_node0);
     } else {
       if (smem > 48 * 1024) cudaFuncSetAttribute(spmv_tile_k<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       spmv_tile_k<float, 128><<<blocks, 128, smem, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)row_lo, (int)row_hi,
                                                                             (const float*)d_values, (const float*)d_x, xb,
-                                                                            (float*)d_y);
+                                                                            (float*)d_y, cls, row_node0);
     }
   } else if (dtype == FEMX_F64)
     spmv_k<double><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)row_lo, (int)row_hi, p->nd,

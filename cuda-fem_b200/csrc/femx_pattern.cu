@@ -606,16 +606,26 @@ __global__ void lattice_first_break(const int* __restrict__ conn, long long n, l
   if ((long long)conn[c * stride] - (long long)conn[0] != c * step) atomicMin(out, (int)c);
 }
 
+// every element against the template; V = 4: one 16-byte load per tetrahedron (conn 16-byte aligned), else scalar loads
+template <int V>
 __global__ void lattice_verify(const int* __restrict__ conn, long long n_elems, lat_desc d, int* __restrict__ bad) {
-  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_elems) return;
-  const long long c = e / d.P;
-  const int t = (int)(e - c * d.P);
-  const long long ci = c % d.cnx, cj = (c / d.cnx) % d.cny, ck = c / ((long long)d.cnx * d.cny);
-  const long long base = d.node0 + ci + cj * d.sy + ck * d.sz;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   bool ok = true;
-  for (int a = 0; a < d.nn; ++a) ok = ok && (long long)conn[e * d.nn + a] == base + d.off[t * d.nn + a];
-  if (!ok) atomicAdd(bad, 1);
+  if (e < n_elems) {
+    const unsigned c = (unsigned)(e / d.P);            // (n_elems * nn < 2^31: 32-bit cell arithmetic)
+    const int t = (int)(e - (long long)c * d.P);
+    const unsigned line = c / (unsigned)d.cnx, ci = c - line * (unsigned)d.cnx;
+    const unsigned ck = line / (unsigned)d.cny, cj = line - ck * (unsigned)d.cny;
+    const long long base = d.node0 + ci + cj * d.sy + ck * d.sz;
+    if (V == 4) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(conn) + e);
+      ok = v.x == base + d.off[t * 4] && v.y == base + d.off[t * 4 + 1] && v.z == base + d.off[t * 4 + 2] &&
+           v.w == base + d.off[t * 4 + 3];
+    } else {
+      for (int a = 0; a < d.nn; ++a) ok = ok && (long long)conn[e * d.nn + a] == base + d.off[t * d.nn + a];
+    }
+  }
+  if (__syncthreads_or(!ok) && threadIdx.x == 0) atomicAdd(bad, 1);
 }
 
 // check_class: the lattice is only recorded when the pattern's class rows are exactly its interior nodes
@@ -702,7 +712,8 @@ int detect_lattice(femx_ctx* ctx, femx_pattern* p, const int* d_conn, cudaStream
   if (b0 + cnx + cny * sy + cnz * sz >= p->n_nodes) return done(FEMX_OK);
   d.cnx = (int)cnx; d.cny = (int)cny;
   LT_CUDA(cudaMemsetAsync(d_tmp + 1, 0, sizeof(int), st));
-  lattice_verify<<<nblocks(ne, 256), 256, 0, st>>>(d_conn, ne, d, d_tmp + 1);
+  if (nn == 4 && (uintptr_t)d_conn % 16 == 0) lattice_verify<4><<<nblocks(ne, 256), 256, 0, st>>>(d_conn, ne, d, d_tmp + 1);
+  else lattice_verify<1><<<nblocks(ne, 256), 256, 0, st>>>(d_conn, ne, d, d_tmp + 1);
   LT_CUDA(cudaMemcpyAsync(h_tmp, d_tmp + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   LT_CUDA(cudaStreamSynchronize(st));
   LT_CUDA(cudaGetLastError());
