@@ -97,3 +97,76 @@ def test_dsl_tets_and_elasticity_match_oracle_on_gpu(ctx):
     ov = orc.assemble_csr(orc.ELASTICITY, 2, 2, conn, X, Y, None, drp, dci, params=(lam, mu))
     assert np.linalg.norm(v.cpu().numpy() - ov) <= 1e-12 * np.linalg.norm(ov)
     form.close(); pat.close()
+
+
+# ---------------------------------------------------------------- C++ front end (include/femx_weakform.hpp) ---
+CPP_PROBE = r'''
+#include <cstdio>
+#include "femx_weakform.hpp"
+using namespace femx::wf;
+int main() {
+  FunctionSpace fs(2);
+  Ex f = -2.0 * (fs.x * fs.x + fs.y * fs.y) + 36.0;
+  WeakForm wf(fs);
+  wf.build([&](Fn u, Fn v) { return dot(grad(u), grad(v)); }, [&](Fn v) { return f * v; });
+  femx_form_desc d = wf.desc(FEMX_F64, 0);
+  printf("%s@@\n", d.prologue);
+  for (int k = 0; k < 9; ++k) printf("%s@@\n", d.entries[k]);
+  for (int k = 0; k < 3; ++k) printf("%s@@\n", d.rhs_entries[k]);
+  return 0;
+}
+'''
+
+
+def test_cpp_weakform_front_end_generates_the_reference_entries(tmp_path):
+    """The C++ lambda front end (the reference's UX, fea_symbolic_nvrtc_sparse.cpp:494-503) on the host: its nine entry strings for
+    dot(grad u, grad v) and three load strings for f v, compiled through the OFFLINE NVRTC path and evaluated numerically,
+    equal the reference's recorded GiNaC output (golden fixture) on a jittered triangle."""
+    import ctypes
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "probe.cpp"
+    src.write_text(CPP_PROBE)
+    exe = tmp_path / "probe"
+    subprocess.check_call(["g++", "-std=c++11", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)]).decode().split("@@\n")
+    prologue, entries, rhs = out[0], out[1:10], out[10:13]
+    assert len(entries) == 9 and all(entries) and len(rhs) == 3
+    # numerical evaluation of the generated C text: compile it into a tiny host function
+    body = "typedef double real;\nextern \"C\" void ev(const double* p, double* o) {\n"
+    body += "  const double x1=p[0],x2=p[1],x3=p[2],y1=p[3],y2=p[4],y3=p[5],r=p[6],s=p[7],t=p[8]; (void)r;(void)s;(void)t;\n"
+    body += "  " + prologue.replace("\n", "\n  ") + "\n"
+    for k, e in enumerate(entries + rhs):
+        body += f"  o[{k}] = {e};\n"
+    body += "}\n"
+    (tmp_path / "ev.cpp").write_text(body)
+    so = tmp_path / "ev.so"
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-o", str(so), str(tmp_path / "ev.cpp")])
+    lib = ctypes.CDLL(str(so))
+    golden = json.load(open(os.path.join(root, "tests", "golden", "ref_integrand_strings.json")))
+    X = np.array([0.1, 1.3, 0.4]); Y = np.array([-0.2, 0.3, 1.1])
+    for (r, s) in ((0.2, 0.3), (0.6, 0.1)):
+        t = 1 - r - s
+        p = np.array([*X, *Y, r, s, t])
+        o = np.zeros(12)
+        lib.ev(p.ctypes.data_as(ctypes.c_void_p), o.ctypes.data_as(ctypes.c_void_p))
+        ns = dict(x1=X[0], x2=X[1], x3=X[2], y1=Y[0], y2=Y[1], y3=Y[2], r=r, s=s, t=t, pow=pow)
+        want = [eval(e.replace("powf", "pow").replace(".0f", ".0").replace("f)", ")"), dict(ns)) for e in golden["integrand"]]
+        assert np.allclose(o[:9], want, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.gpu
+def test_cpp_weakform_demo_program():
+    """examples/femx_weakform_demo: the reference's main() with the lambda front end, plain C++ against the C ABI (2-D and 3-D,
+    matrix against the built-in emitter to 1e-12, load vector against the exact integral of f)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "femx_weakform_demo")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(root, "examples")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok dim=") == 2, out.stdout
