@@ -849,6 +849,9 @@ int make_form(femx_ctx* ctx, const femx_form_desc* d, femx_form** out) {
     }
   }
   int st = compile_variant(f, f->nd == 1 ? "coo_e" : "coo", nullptr, ctx != nullptr);
+  // user strings are pasted into more than one kernel scope: compile the numeric-pass variant now as well, so that a
+  // name that collides with a kernel local fails HERE with the NVRTC log, not at the first femx_assemble_csr
+  if (st == FEMX_OK && f->builtin == FEMX_FORM_CUSTOM) st = compile_variant(f, "csr", nullptr, false);
   if (st != FEMX_OK) {
     if (ctx) ctx->err = f->err.empty() ? ctx->err : f->err;
     delete f;

@@ -274,8 +274,9 @@ __device__ __forceinline__ int femx_ldg_pinned(const int* p) {
 #define FEMX_SPEC_HDR (128 + ((FEMX_TILE_NODES * 4 + 127) / 128) * 128)
 
 // Scatter code of one incidence (row node = local node li of element e):
-//   bits  0-6, 7-13, 14-20 : positions in the row's column list of the OTHER vertices,
-//                            in cyclic order (li+1)%NN, (li+2)%NN, ...
+//   bits  0-6, 7-13, 14-20 : positions in the row's column list of the OTHER vertices, in the order
+//                            FEMX_OTH(li, j): cyclic (li+1+j)%3 for triangles, li ^ (j+1) for tetrahedra
+//                            (always an even permutation of the element: same signed Jacobian)
 //   bits 21-23             : first-touch flags of those positions (this incidence is the first of
 //                            the row to contribute there: store, do not add — the value image
 //                            needs no zero fill)

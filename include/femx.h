@@ -95,7 +95,10 @@ typedef struct femx_form_desc {
    * as a C expression over x1..x{nn}, y1.., z1.., and the quadrature point
    * r, s, t (and u in 3-D) — the names the reference's integrand() unpacks from
    * params[] (fea_symbolic_nvrtc_sparse.cpp:386-394).  Use the type `real`
-   * for casts; pow(x,2.0) is accepted. */
+   * for casts; pow(x,2.0) is accepted.  The strings (and the prologue) are pasted into kernel scopes: besides
+   * the names above, identifiers starting with femx_ / FEMX_ / lt_ / wf_ and the kernel locals e, e0, nodes, cx, cy,
+   * cz, out, code, sc, np, it, ps, po, more, srow, dacc, racc are reserved.  femx_form_compile compiles both the COO and
+   * the numeric-pass kernel for custom strings, so a clash fails there (FEMX_ERR_NVRTC + log), not at first use. */
   const char* const* entries;
   /* optional C statements evaluated once per element before the quadrature
    * loop (common sub-expressions such as the Jacobian); may be NULL. */
