@@ -157,7 +157,9 @@ SHIM_ATOMIC = r'''
 // ---- shim (not reference code): times the reference's three accumulation variants on n values ----------
 // (atomicadd.cu:73-129: naive global atomicAdd, shared-memory staged block sum + one atomicAdd per block, CAS-loop double add;
 //  its main() launches only the first on SIZE = 50)
-extern "C" int ref_atomic_variants(long n, int iters, float* ms3, double* results3) {
+// n_cas: the CAS-loop variant serialises completely (every resident thread retries until it wins: work ~ n x resident threads),
+// it is timed on a much smaller n
+extern "C" int ref_atomic_variants(long n, long n_cas, int iters, float* ms3, double* results3) {
   float* dIn = 0; double* dInD = 0; float* dRes = 0; double* dResD = 0;
   cudaMalloc(&dIn, n * sizeof(float)); cudaMalloc(&dInD, n * sizeof(double));
   cudaMalloc(&dRes, sizeof(float)); cudaMalloc(&dResD, sizeof(double));
@@ -167,10 +169,11 @@ extern "C" int ref_atomic_variants(long n, int iters, float* ms3, double* result
   cudaMemcpy(dInD, hd, n * sizeof(double), cudaMemcpyHostToDevice);
   dim3 blk(BLOCK_X_NAIVE, BLOCK_Y_NAIVE, 1);
   dim3 grd(BLOCK_COUNT_X, (unsigned)((n + (long)BLOCK_X_NAIVE * BLOCK_Y_NAIVE * BLOCK_COUNT_X - 1) / ((long)BLOCK_X_NAIVE * BLOCK_Y_NAIVE * BLOCK_COUNT_X)), 1);
-  ref_size = n;
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   for (int v = 0; v < 3; v++) {
     float best = 1e30f;
+    ref_size = v == 2 ? n_cas : n;
+    if (v == 2) grd.y = (unsigned)((n_cas + (long)BLOCK_X_NAIVE * BLOCK_Y_NAIVE * BLOCK_COUNT_X - 1) / ((long)BLOCK_X_NAIVE * BLOCK_Y_NAIVE * BLOCK_COUNT_X));
     for (int it = 0; it < iters; it++) {
       cudaMemset(dRes, 0, sizeof(float)); cudaMemset(dResD, 0, sizeof(double));
       cudaEventRecord(a);

@@ -87,7 +87,7 @@ def assemble_ell(prec, n_row, n_col, X, Y, gIdx, ell_len, ell_idx, iters=1):
     return A, ms.value
 
 
-def atomic_variants(n=10_240_000, iters=3):   # a multiple of the 32x32x100 grid row: the staged variant reads no unset shared memory
+def atomic_variants(n=10_240_000, n_cas=20_480, iters=3):   # n: a multiple of the 32x32x100 grid row (the staged variant reads no unset shared memory)
     """The reference's three accumulation variants (atomicadd.cu:73-129) on n ones: ms per launch and the sums
     (fp32 naive / fp32 shared-memory staged / fp64 CAS loop).  The contention K5 suffers, as a micro-benchmark."""
     path = os.path.join(_REF, "libref_atomicadd.so")
@@ -96,6 +96,8 @@ def atomic_variants(n=10_240_000, iters=3):   # a multiple of the 32x32x100 grid
     L = C.CDLL(path)
     ms = (C.c_float * 3)()
     res = (C.c_double * 3)()
-    err = L.ref_atomic_variants(C.c_long(n), int(iters), ms, res)
+    err = L.ref_atomic_variants(C.c_long(n), C.c_long(n_cas), int(iters), ms, res)
     names = ("naive_global_atomicAdd_f32", "smem_staged_block_sum_f32", "cas_loop_f64")
-    return {"n": n, "cuda_error": err, **{k: {"ms": ms[i], "sum": res[i], "GBps": n * (4 if i < 2 else 8) / (ms[i] * 1e-3) / 1e9} for i, k in enumerate(names)}}
+    sizes = (n, n, n_cas)
+    return {"cuda_error": err, **{k: {"n": sizes[i], "ms": ms[i], "sum": res[i], "values_per_s": sizes[i] / (ms[i] * 1e-3)}
+                                  for i, k in enumerate(names)}}
