@@ -22,6 +22,8 @@
 
 int femx_spmv_range(const femx_pattern* p, int dtype, const void* d_values, const void* d_x, int64_t x_base, void* d_y,
                     int64_t row_lo, int64_t row_hi, void* stream);
+int femx_spmv_range2(const femx_pattern* p, int dtype, const void* d_values, const void* d_x, int64_t x_base, void* d_y,
+                     int64_t row_lo, int64_t row_hi, int64_t row_lo2, int64_t row_hi2, void* stream);
 
 namespace {
 
@@ -286,9 +288,8 @@ int spmv_overlapped(femx_dist_op* op, void* ext, void* y, cudaStream_t st) {
   if (op->int_hi > op->int_lo) rc = femx_spmv_range(p, op->dtype, op->vals, ext, xb, y, op->int_lo, op->int_hi, st);
   if (rc != FEMX_OK) return rc;
   if (comm) FEMX_CUDA_OK(d->ctx, cudaStreamWaitEvent(st, d->e_halo, 0));
-  if (op->int_lo > 0) rc = femx_spmv_range(p, op->dtype, op->vals, ext, xb, y, 0, op->int_lo, st);
-  if (rc == FEMX_OK && op->int_hi < p->n_rows) rc = femx_spmv_range(p, op->dtype, op->vals, ext, xb, y, op->int_hi, p->n_rows, st);
-  return rc;
+  // the rows of the first and the last owned plane (they read the ghost zones): one launch
+  return femx_spmv_range2(p, op->dtype, op->vals, ext, xb, y, 0, op->int_lo, op->int_hi, p->n_rows, st);
 }
 
 // (gamma, delta) = ((r,r), (w,r)) summed over the ranks, then the CG scalars for the next update — ONE reduction per iteration

@@ -34,9 +34,14 @@ struct spmv_cls { int len; int off[24]; };
 template <class T, int TILE>
 __global__ void __launch_bounds__(TILE) spmv_tile_k(const int2* __restrict__ rowinfo, const int* __restrict__ col_idx,
                                                      int row0, int n_rows, const T* __restrict__ vals, const T* __restrict__ x,
-                                                     long long x_off, T* __restrict__ y, const spmv_cls cls, int row_node0) {
+                                                     long long x_off, T* __restrict__ y, const spmv_cls cls, int row_node0,
+                                                     int nblk_a, int row0_b, int n_rows_b) {
   extern __shared__ __align__(16) unsigned char sm[];
-  const int i0 = row0 + blockIdx.x * TILE;   // rows [row0, n_rows)
+  // rows [row0, n_rows) in the first nblk_a CTAs, rows [row0_b, n_rows_b) in the others (the two ghost-reading ends of a slab
+  // in ONE launch)
+  const bool second = (int)blockIdx.x >= nblk_a;
+  const int i0 = second ? row0_b + ((int)blockIdx.x - nblk_a) * TILE : row0 + blockIdx.x * TILE;
+  if (second) n_rows = n_rows_b;
   const int nt = min(TILE, n_rows - i0);
   const int base = rowinfo[i0].x;
   const int cnt = rowinfo[i0 + nt].x - base;
@@ -159,20 +164,32 @@ inline unsigned nb(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 // y[rows row_lo..row_hi) = A x for a range of NODE rows (the multi-GPU layer multiplies the rows that read no ghost
 // column while the halo is still travelling)
+int femx_spmv_range2(const femx_pattern* p, int dtype, const void* d_values, const void* d_x, int64_t x_base, void* d_y,
+                     int64_t row_lo, int64_t row_hi, int64_t row_lo2, int64_t row_hi2, void* stream);
+
 int femx_spmv_range(const femx_pattern* p, int dtype, const void* d_values, const void* d_x, int64_t x_base, void* d_y,
                     int64_t row_lo, int64_t row_hi, void* stream) {
+  return femx_spmv_range2(p, dtype, d_values, d_x, x_base, d_y, row_lo, row_hi, 0, 0, stream);
+}
+
+// two row ranges in one launch (either may be empty)
+int femx_spmv_range2(const femx_pattern* p, int dtype, const void* d_values, const void* d_x, int64_t x_base, void* d_y,
+                     int64_t row_lo, int64_t row_hi, int64_t row_lo2, int64_t row_hi2, void* stream) {
   if (!p || !d_values || !d_x || !d_y) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_spmv: NULL argument");
-  if (row_lo < 0 || row_hi > p->n_rows || row_lo > row_hi) return femx_fail(p->ctx, FEMX_ERR_INVALID, "femx_spmv: bad row range");
-  if (row_hi == row_lo) return FEMX_OK;
+  if (row_lo < 0 || row_hi > p->n_rows || row_lo > row_hi || row_lo2 < 0 || row_hi2 > p->n_rows || row_lo2 > row_hi2)
+    return femx_fail(p->ctx, FEMX_ERR_INVALID, "femx_spmv: bad row range");
+  if (row_hi == row_lo && row_hi2 == row_lo2) return FEMX_OK;
+  if (row_hi == row_lo) { row_lo = row_lo2; row_hi = row_hi2; row_lo2 = row_hi2 = 0; }
   FEMX_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
   const int64_t n = (row_hi - row_lo) * p->nd;
   const long long xb = (long long)x_base - (long long)p->nd * p->col_base;
   const size_t rs = dtype == FEMX_F64 ? 8 : 4;
   // (max_tile_nnz is taken over 128-row tiles starting at multiples of 128; a window that starts elsewhere lies in two of them)
-  const size_t smem = (size_t)(p->max_tile_nnz * (row_lo % 128 ? 2 : 1) + 2) * (rs + 4);
+  const size_t smem = (size_t)(p->max_tile_nnz * ((row_lo % 128 || row_lo2 % 128) ? 2 : 1) + 2) * (rs + 4);
   if (p->nd == 1 && smem <= 200 * 1024 && p->tile_nodes == 128) {
     // tile-staged kernel (128-row tiles)
-    const unsigned blocks = (unsigned)((row_hi - row_lo + 127) / 128);
+    const int nblk_a = (int)((row_hi - row_lo + 127) / 128), nblk_b = (int)((row_hi2 - row_lo2 + 127) / 128);
+    const unsigned blocks = (unsigned)(nblk_a + nblk_b);
     spmv_cls cls = {};
     if (p->spec_np > 0 && p->spec_rlen <= 24) {
       cls.len = p->spec_rlen;
@@ -183,12 +200,12 @@ int femx_spmv_range(const femx_pattern* p, int dtype, const void* d_values, cons
       if (smem > 48 * 1024) cudaFuncSetAttribute(spmv_tile_k<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       spmv_tile_k<double, 128><<<blocks, 128, smem, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)row_lo, (int)row_hi,
                                                                              (const double*)d_values, (const double*)d_x, xb,
-                                                                             (double*)d_y, cls, row_node0);
+                                                                             (double*)d_y, cls, row_node0, nblk_a, (int)row_lo2, (int)row_hi2);
     } else {
       if (smem > 48 * 1024) cudaFuncSetAttribute(spmv_tile_k<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       spmv_tile_k<float, 128><<<blocks, 128, smem, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)row_lo, (int)row_hi,
                                                                             (const float*)d_values, (const float*)d_x, xb,
-                                                                            (float*)d_y, cls, row_node0);
+                                                                            (float*)d_y, cls, row_node0, nblk_a, (int)row_lo2, (int)row_hi2);
     }
   } else if (dtype == FEMX_F64)
     spmv_k<double><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)row_lo, (int)row_hi, p->nd,
@@ -197,6 +214,8 @@ int femx_spmv_range(const femx_pattern* p, int dtype, const void* d_values, cons
     spmv_k<float><<<nb(n), 256, 0, (cudaStream_t)stream>>>(p->d_rowinfo, p->d_col_idx, (int)row_lo, (int)row_hi, p->nd,
                                                            (const float*)d_values, (const float*)d_x, xb, (float*)d_y);
   FEMX_CUDA_OK(p->ctx, cudaGetLastError());
+  if (!(p->nd == 1 && smem <= 200 * 1024 && p->tile_nodes == 128) && row_hi2 > row_lo2)
+    return femx_spmv_range2(p, dtype, d_values, d_x, x_base, d_y, row_lo2, row_hi2, 0, 0, stream);
   return FEMX_OK;
 }
 
