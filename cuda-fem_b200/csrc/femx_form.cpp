@@ -1123,17 +1123,33 @@ int femx_assemble_csr(femx_form* form, const femx_pattern* pat, const femx_mesh_
   bool lattice = false;
   std::string lat_key;
   if (cls && pat->lat.ok && pat->lat_rows > 0 && pat->lat_rows == pat->spec_rows && form->lt_ok && live.lattice != 0) {
-    std::string why;
-    femx_knobs kk = form->knobs;
-    kk.lt_tx = live.lt_tx; kk.lt_ty = live.lt_ty; kk.lt_kc = live.lt_kc; kk.lt_minb = live.lt_minb;
-    kk.lt_regs = live.lt_regs; kk.lt_pf = live.lt_pf; kk.lt_unroll = live.lt_unroll;
-    if (femx_lattice_plan_make(form, pat->lat, pat->spec_rlen, pat->spec_self, pat->spec_off, kk, &plan, &why)) {
-      lat_key = femx_lattice_key(pat->lat, plan);
-      if (!form->lt_failed.count(lat_key)) {
-        st = compile_variant(form, kname, &v, true, nullptr, 0, &pat->lat, &plan, lat_key);
-        if (st == FEMX_ERR_NVRTC || st == FEMX_ERR_UNSUPPORTED) form->lt_failed.insert(lat_key);  // stencil-class kernel instead
-        else if (st != FEMX_OK) return st;
-        else lattice = true;
+    // (plan and kernel are looked up per (pattern, lattice options): the launch path builds no strings / maps after the first call)
+    // (the key also names the lattice: a destroyed pattern's address may be reused by a different one)
+    char optkey[224];
+    snprintf(optkey, sizeof optkey, "%d,%d,%d,%d,%d,%d,%d|%lld|%d,%d,%d,%d,%lld,%lld,%lld,%d,%d,%s", live.lt_tx, live.lt_ty, live.lt_kc,
+             live.lt_minb, live.lt_regs, live.lt_pf, live.lt_unroll, (long long)pat->spec_rows, pat->lat.P, pat->lat.cn[0], pat->lat.cn[1],
+             pat->lat.cn[2], pat->lat.s[1], pat->lat.s[2], pat->lat.node0, pat->spec_rlen, pat->spec_self, pat->spec_key.c_str());
+    femx_lattice_cached& cc = form->lt_cache[pat];
+    if (cc.variant && cc.opts == optkey) {
+      plan = cc.plan;
+      v = cc.variant;
+      lattice = true;
+    } else {
+      std::string why;
+      femx_knobs kk = form->knobs;
+      kk.lt_tx = live.lt_tx; kk.lt_ty = live.lt_ty; kk.lt_kc = live.lt_kc; kk.lt_minb = live.lt_minb;
+      kk.lt_regs = live.lt_regs; kk.lt_pf = live.lt_pf; kk.lt_unroll = live.lt_unroll;
+      if (femx_lattice_plan_make(form, pat->lat, pat->spec_rlen, pat->spec_self, pat->spec_off, kk, &plan, &why)) {
+        lat_key = femx_lattice_key(pat->lat, plan);
+        if (!form->lt_failed.count(lat_key)) {
+          st = compile_variant(form, kname, &v, true, nullptr, 0, &pat->lat, &plan, lat_key);
+          if (st == FEMX_ERR_NVRTC || st == FEMX_ERR_UNSUPPORTED) form->lt_failed.insert(lat_key);  // stencil-class kernel instead
+          else if (st != FEMX_OK) return st;
+          else {
+            lattice = true;
+            cc.opts = optkey; cc.plan = plan; cc.variant = v;
+          }
+        }
       }
     }
   }

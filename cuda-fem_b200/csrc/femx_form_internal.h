@@ -50,8 +50,16 @@ bool femx_lattice_plan_make(const struct femx_form* f, const femx_lattice& L, in
 std::string femx_lattice_defines(const struct femx_form* f, const femx_lattice& L, femx_lattice_plan* plan);
 std::string femx_lattice_key(const femx_lattice& L, const femx_lattice_plan& plan);
 
+// what femx_assemble_csr worked out for (pattern, lattice options) on an earlier call: the hot call does not rebuild it
+struct femx_lattice_cached {
+  std::string opts;            // the option values the entry was made for
+  femx_lattice_plan plan;
+  femx_variant* variant = nullptr;
+};
+
 struct femx_form {
   femx_ctx* ctx = nullptr;
+  std::map<const void*, femx_lattice_cached> lt_cache;  // by pattern
   femx_knobs knobs;  // copied at compile time (from the context, or from the environment for offline forms)
   // element-once lattice pass (femx_lattice.cpp): available for the symmetric built-in scalar forms in 3-D;
   // K_ab = (d_a . d_b) lt_W / jac + lt_moff jac (a != b), diagonal = lt_cj * (sum of jac) - (off-diagonal row sum)
