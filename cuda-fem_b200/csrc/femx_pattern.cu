@@ -116,10 +116,11 @@ __global__ void scan_apply(const int* __restrict__ in, int64_t n, const long lon
 
 // out[0..n] = exclusive scan of in[0..n); *h_total = grand total (host)
 int exclusive_scan(femx_ctx* ctx, const int* d_in, int64_t n, int* d_out, long long* h_total,
-                   cudaStream_t st) {
+                   cudaStream_t st, long long* d_total = nullptr) {
   if (n == 0) {
     FEMX_CUDA_OK(ctx, cudaMemsetAsync(d_out, 0, sizeof(int), st));
-    *h_total = 0;
+    if (d_total) FEMX_CUDA_OK(ctx, cudaMemsetAsync(d_total, 0, sizeof(long long), st));
+    else *h_total = 0;
     return FEMX_OK;
   }
   int nt = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
@@ -129,8 +130,13 @@ int exclusive_scan(femx_ctx* ctx, const int* d_in, int64_t n, int* d_out, long l
   scan_tile_sums<<<nt, SCAN_THREADS, 0, st>>>(d_in, n, d_sums);
   scan_sums<<<1, SCAN_THREADS, 0, st>>>(d_sums, nt, d_sums + nt);
   scan_apply<<<nt, SCAN_THREADS, 0, st>>>(d_in, n, d_sums, d_out);
-  cudaError_t e = cudaMemcpyAsync(h_total, d_sums + nt, sizeof(long long), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaError_t e;
+  if (d_total) {  // the caller collects the total later, with its own synchronisation
+    e = cudaMemcpyAsync(d_total, d_sums + nt, sizeof(long long), cudaMemcpyDeviceToDevice, st);
+  } else {
+    e = cudaMemcpyAsync(h_total, d_sums + nt, sizeof(long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
   cudaFreeAsync(d_sums, st);
   FEMX_CUDA_OK(ctx, e);
   return FEMX_OK;
@@ -275,24 +281,6 @@ __global__ void slice_sizes(const int* __restrict__ pair_ptr, int n_rows, int n_
   if (s >= n_slices) return;
   int r = s * 32 + (threadIdx.x & 31);
   int np = r < n_rows ? pair_ptr[r + 1] - pair_ptr[r] : 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) np = max(np, __shfl_xor_sync(0xffffffffu, np, o));
-  if ((threadIdx.x & 31) == 0) size[s] = np * 32;
-}
-
-__global__ void row_len_max(const int* __restrict__ rowlen, int n_rows, int* __restrict__ out) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  int v = r < n_rows ? rowlen[r] : 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
-}
-
-__global__ void slice_sizes_cnt(const int* __restrict__ cnt, int n_rows, int n_slices, int* __restrict__ size) {
-  int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (s >= n_slices) return;
-  int r = s * 32 + (threadIdx.x & 31);
-  int np = r < n_rows ? cnt[r] : 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) np = max(np, __shfl_xor_sync(0xffffffffu, np, o));
   if ((threadIdx.x & 31) == 0) size[s] = np * 32;
@@ -598,34 +586,107 @@ struct lat_desc {
   int off[32];  // node offset of vertex a of element t from the cell's lower corner
 };
 
-// smallest c in [1, n) with conn[c * stride] - conn[0] != c * step  (n if there is none)
-__global__ void lattice_first_break(const int* __restrict__ conn, long long n, long long stride, long long step,
-                                    int* __restrict__ out) {
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1;
-  if (c >= n) return;
-  if ((long long)conn[c * stride] - (long long)conn[0] != c * step) atomicMin(out, (int)c);
+// The extents in one launch of one block: out[0] = cells per line = the smallest c in [1, nsx) with
+// conn[c * P * nn] - conn[0] != c (nsx if there is none); for tetrahedra, if that is a valid line length,
+// out[2] = lines per plane = the smallest c in [1, nsy) with conn[c * cnx * P * nn] - conn[0] != c * sy (nsy if none).
+// Both searches are bounded by the strides (a line has fewer cells than sy nodes, a plane fewer lines than sz / sy + 1).
+__global__ void lattice_extents(const int* __restrict__ conn, long long n_cells, int P, int nn, long long sy, long long sz,
+                                int dim, int* __restrict__ out) {
+  __shared__ int best;
+  const long long nsx = min(n_cells, sy);
+  if (threadIdx.x == 0) best = (int)nsx;
+  __syncthreads();
+  for (long long c = threadIdx.x + 1; c < nsx; c += blockDim.x)
+    if ((long long)conn[c * P * nn] - (long long)conn[0] != c) atomicMin(&best, (int)c);
+  __syncthreads();
+  const long long cnx = best;
+  __syncthreads();
+  if (threadIdx.x == 0) out[0] = (int)cnx;
+  if (dim != 3 || cnx < 2 || n_cells % cnx || cnx + 1 > sy) return;
+  const long long n_lines = n_cells / cnx, nsy = min(n_lines, sz / sy + 1);
+  if (threadIdx.x == 0) best = (int)nsy;
+  __syncthreads();
+  for (long long c = threadIdx.x + 1; c < nsy; c += blockDim.x)
+    if ((long long)conn[c * cnx * P * nn] - (long long)conn[0] != c * sy) atomicMin(&best, (int)c);
+  __syncthreads();
+  if (threadIdx.x == 0) out[2] = best;
 }
 
-// every element against the template; V = 4: one 16-byte load per tetrahedron (conn 16-byte aligned), else scalar loads
+// every element against the template; V = 4: one 16-byte load per tetrahedron (conn 16-byte aligned), else scalar loads.
+// 32-bit arithmetic throughout (n_elems * nn < 2^31, node ids < 2^31): a 64-bit division per thread made this kernel
+// instruction-bound at a third of the memory rate.
 template <int V>
-__global__ void lattice_verify(const int* __restrict__ conn, long long n_elems, lat_desc d, int* __restrict__ bad) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void lattice_verify(const int* __restrict__ conn, unsigned n_elems, lat_desc d, int* __restrict__ bad) {
+  constexpr int U = 4;                                   // elements per thread: all loads in flight before the first check
+  const unsigned e0 = blockIdx.x * (blockDim.x * U) + threadIdx.x;
+  int4 v[U];
+  if (V == 4) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned e = e0 + u * blockDim.x;
+      v[u] = e < n_elems ? __ldg(reinterpret_cast<const int4*>(conn) + e) : make_int4(0, 0, 0, 0);
+    }
+  }
   bool ok = true;
-  if (e < n_elems) {
-    const unsigned c = (unsigned)(e / d.P);            // (n_elems * nn < 2^31: 32-bit cell arithmetic)
-    const int t = (int)(e - (long long)c * d.P);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned e = e0 + u * blockDim.x;
+    if (e >= n_elems) break;
+    const unsigned c = e / (unsigned)d.P;
+    const int t = (int)(e - c * (unsigned)d.P);
     const unsigned line = c / (unsigned)d.cnx, ci = c - line * (unsigned)d.cnx;
     const unsigned ck = line / (unsigned)d.cny, cj = line - ck * (unsigned)d.cny;
-    const long long base = d.node0 + ci + cj * d.sy + ck * d.sz;
+    const int base = (int)((unsigned)d.node0 + ci + cj * (unsigned)d.sy + ck * (unsigned)d.sz);
     if (V == 4) {
-      const int4 v = __ldg(reinterpret_cast<const int4*>(conn) + e);
-      ok = v.x == base + d.off[t * 4] && v.y == base + d.off[t * 4 + 1] && v.z == base + d.off[t * 4 + 2] &&
-           v.w == base + d.off[t * 4 + 3];
+      ok = ok && v[u].x == base + d.off[t * 4] && v[u].y == base + d.off[t * 4 + 1] && v[u].z == base + d.off[t * 4 + 2] &&
+           v[u].w == base + d.off[t * 4 + 3];
     } else {
-      for (int a = 0; a < d.nn; ++a) ok = ok && (long long)conn[e * d.nn + a] == base + d.off[t * d.nn + a];
+      for (int a = 0; a < d.nn; ++a) ok = ok && conn[(size_t)e * d.nn + a] == base + d.off[t * d.nn + a];
     }
   }
   if (__syncthreads_or(!ok) && threadIdx.x == 0) atomicAdd(bad, 1);
+}
+
+// The same check for tetrahedra with one thread block per piece of a cell LINE: the line's position is decoded once per
+// block, the cell of an element by a multiplication (magic = ceil(2^34 / P), exact below 2^29 elements per line), the
+// template offsets sit in shared memory (indexed per thread, the kernel-parameter copy would serialise).  The generic
+// kernel above spends 3 integer divisions per element and runs at a third of the memory rate.
+template <int U>
+__global__ void lattice_verify_lines(const int4* __restrict__ conn, lat_desc d, unsigned line_elems, unsigned long long magic,
+                                     int* __restrict__ bad) {
+  __shared__ int off[32];
+  if (threadIdx.x < 32) off[threadIdx.x] = d.off[threadIdx.x];
+  const unsigned line = blockIdx.x;
+  const unsigned ck = line / (unsigned)d.cny, cj = line - ck * (unsigned)d.cny;
+  const int base = (int)((unsigned)d.node0 + cj * (unsigned)d.sy + ck * (unsigned)d.sz);
+  const int4* __restrict__ src = conn + (size_t)line * line_elems;
+  const unsigned x0 = blockIdx.y * (blockDim.x * U) + threadIdx.x;
+  int4 v[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned x = x0 + u * blockDim.x;
+    v[u] = x < line_elems ? __ldg(src + x) : make_int4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  bool ok = true;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned x = x0 + u * blockDim.x;
+    if (x < line_elems) {
+      const unsigned ci = (unsigned)(((unsigned long long)x * magic) >> 34);
+      const int t = (int)(x - ci * (unsigned)d.P), b = base + (int)ci;
+      ok = ok && v[u].x == b + off[t * 4] && v[u].y == b + off[t * 4 + 1] && v[u].z == b + off[t * 4 + 2] &&
+           v[u].w == b + off[t * 4 + 3];
+    }
+  }
+  if (__syncthreads_or(!ok) && threadIdx.x == 0) atomicAdd(bad, 1);
+}
+
+template <int U>
+void launch_verify_lines(const int* d_conn, const lat_desc& d, long long n_lines, unsigned line_elems, int* d_bad, cudaStream_t st) {
+  const unsigned long long magic = ((1ULL << 34) + d.P - 1) / d.P;
+  dim3 grid((unsigned)n_lines, (line_elems + 256 * U - 1) / (256 * U));
+  lattice_verify_lines<U><<<grid, 256, 0, st>>>(reinterpret_cast<const int4*>(d_conn), d, line_elems, magic, d_bad);
 }
 
 // check_class: the lattice is only recorded when the pattern's class rows are exactly its interior nodes
@@ -638,7 +699,7 @@ int detect_lattice(femx_ctx* ctx, femx_pattern* p, const int* d_conn, cudaStream
   int head[64];
   const int nh = (int)std::min<int64_t>(ne * nn, 64);
   int* d_tmp = nullptr;
-  int rc = tmp_alloc(ctx, &d_tmp, 2, st);
+  int rc = tmp_alloc(ctx, &d_tmp, 4, st);
   if (rc != FEMX_OK) return rc;
   auto done = [&](int code) { cudaFreeAsync(d_tmp, st); return code; };
 #define LT_CUDA(call)                                                                                  \
@@ -684,36 +745,46 @@ int detect_lattice(femx_ctx* ctx, femx_pattern* p, const int* d_conn, cudaStream
     }
   // extents
   const long long n_cells = ne / P;
-  int h_tmp[2] = {(int)std::min<long long>(n_cells, INT_MAX), 0};
-  LT_CUDA(cudaMemcpyAsync(d_tmp, h_tmp, sizeof h_tmp, cudaMemcpyHostToDevice, st));
-  // (a line has fewer cells than the y stride has nodes: the search never needs to look further)
-  const long long nsx = std::min<long long>(n_cells, sy);
-  h_tmp[0] = (int)nsx;
-  LT_CUDA(cudaMemcpyAsync(d_tmp, h_tmp, sizeof(int), cudaMemcpyHostToDevice, st));
-  lattice_first_break<<<nblocks(nsx, 256), 256, 0, st>>>(d_conn, nsx, (long long)P * nn, 1, d_tmp);
-  LT_CUDA(cudaMemcpyAsync(h_tmp, d_tmp, sizeof(int), cudaMemcpyDeviceToHost, st));
+  int h_tmp[4] = {0, 0, 0, 0};
+  LT_CUDA(cudaMemsetAsync(d_tmp, 0, sizeof(int) * 4, st));
+  lattice_extents<<<1, 1024, 0, st>>>(d_conn, n_cells, P, nn, sy, sz, dim, d_tmp);
+  LT_CUDA(cudaMemcpyAsync(h_tmp, d_tmp, sizeof h_tmp, cudaMemcpyDeviceToHost, st));
   LT_CUDA(cudaStreamSynchronize(st));
-  const long long cnx = h_tmp[0];   // (== nsx when no break was found below the bound: then the mesh is one line)
+  const long long cnx = h_tmp[0];   // (== the search bound when no break was found below it: then the mesh is one line)
   if (cnx < 2 || n_cells % cnx || cnx + 1 > sy) return done(FEMX_OK);
   const long long n_lines = n_cells / cnx;
   long long cny = n_lines, cnz = 1;
   if (dim == 3) {
     const long long nsy = std::min<long long>(n_lines, sz / sy + 1);
-    h_tmp[0] = (int)nsy;
-    LT_CUDA(cudaMemcpyAsync(d_tmp, h_tmp, sizeof(int), cudaMemcpyHostToDevice, st));
-    lattice_first_break<<<nblocks(nsy, 256), 256, 0, st>>>(d_conn, nsy, cnx * P * nn, sy, d_tmp);
-    LT_CUDA(cudaMemcpyAsync(h_tmp, d_tmp, sizeof(int), cudaMemcpyDeviceToHost, st));
-    LT_CUDA(cudaStreamSynchronize(st));
-    cny = h_tmp[0] == nsy && nsy < n_lines ? 0 : h_tmp[0];   // no break below the bound although lines remain: not a lattice
+    cny = h_tmp[2] == nsy && nsy < n_lines ? 0 : h_tmp[2];   // no break below the bound although lines remain: not a lattice
     if (cny < 1 || n_lines % cny || cny * sy + cnx + 1 > sz) return done(FEMX_OK);
     cnz = n_lines / cny;
   }
   L.cn[0] = (int)cnx; L.cn[1] = (int)cny; L.cn[2] = (int)cnz;
   if (b0 + cnx + cny * sy + cnz * sz >= p->n_nodes) return done(FEMX_OK);
   d.cnx = (int)cnx; d.cny = (int)cny;
-  LT_CUDA(cudaMemsetAsync(d_tmp + 1, 0, sizeof(int), st));
-  if (nn == 4 && (uintptr_t)d_conn % 16 == 0) lattice_verify<4><<<nblocks(ne, 256), 256, 0, st>>>(d_conn, ne, d, d_tmp + 1);
-  else lattice_verify<1><<<nblocks(ne, 256), 256, 0, st>>>(d_conn, ne, d, d_tmp + 1);
+  const long long line_elems = cnx * P;
+  if (nn == 4 && (uintptr_t)d_conn % 16 == 0 && line_elems >= 256 && line_elems < (1LL << 29) && P * nn <= 32 &&
+      (line_elems + 2047) / 2048 <= 65535) {
+    // elements per thread: the most that leaves the fewest idle threads in a line's last block
+    int U = 1;
+    long long waste = -1;
+    for (int u = 1; u <= 8; ++u) {
+      const long long w = (line_elems + 256 * u - 1) / (256 * u) * (256 * u) - line_elems;
+      if (waste < 0 || w <= waste) { waste = w; U = u; }
+    }
+    switch (U) {
+      case 1: launch_verify_lines<1>(d_conn, d, n_lines, (unsigned)line_elems, d_tmp + 1, st); break;
+      case 2: launch_verify_lines<2>(d_conn, d, n_lines, (unsigned)line_elems, d_tmp + 1, st); break;
+      case 3: launch_verify_lines<3>(d_conn, d, n_lines, (unsigned)line_elems, d_tmp + 1, st); break;
+      case 4: launch_verify_lines<4>(d_conn, d, n_lines, (unsigned)line_elems, d_tmp + 1, st); break;
+      case 5: launch_verify_lines<5>(d_conn, d, n_lines, (unsigned)line_elems, d_tmp + 1, st); break;
+      case 6: launch_verify_lines<6>(d_conn, d, n_lines, (unsigned)line_elems, d_tmp + 1, st); break;
+      case 7: launch_verify_lines<7>(d_conn, d, n_lines, (unsigned)line_elems, d_tmp + 1, st); break;
+      default: launch_verify_lines<8>(d_conn, d, n_lines, (unsigned)line_elems, d_tmp + 1, st); break;
+    }
+  } else if (nn == 4 && (uintptr_t)d_conn % 16 == 0) lattice_verify<4><<<nblocks(ne, 1024), 256, 0, st>>>(d_conn, (unsigned)ne, d, d_tmp + 1);
+  else lattice_verify<1><<<nblocks(ne, 1024), 256, 0, st>>>(d_conn, (unsigned)ne, d, d_tmp + 1);
   LT_CUDA(cudaMemcpyAsync(h_tmp, d_tmp + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   LT_CUDA(cudaStreamSynchronize(st));
   LT_CUDA(cudaGetLastError());
@@ -755,6 +826,7 @@ struct lat_row_tmpl {
   signed char cell[LT_MAX_NP][3];    // cell of incidence k relative to the node: (sx, sy, sz) in {-1, 0}
   unsigned char t[LT_MAX_NP], li[LT_MAX_NP];
   unsigned code[LT_MAX_NP];
+  int off[LT_MAX_RLEN];              // col[k] as a node offset of THIS lattice (filled by build_from_lattice)
 };
 struct lat_geom {
   int dim, P, nn;
@@ -765,67 +837,136 @@ struct lat_geom {
   int dom;  // dominant class (flagged FEMX_ROW_SPEC), -1 = none
 };
 
-__device__ __forceinline__ int lat_class_of(const lat_geom& g, long long node, int* ijk) {
-  long long q = node - g.node0;
-  if (q < 0) return -1;
-  long long k = 0, j, i;
-  if (g.dim == 3) { k = q / g.s[2]; q -= k * g.s[2]; }
-  j = q / g.s[1];
-  i = q - j * g.s[1];
-  if (i > g.cn[0] || j > g.cn[1] || k > g.cn[2]) return -1;
-  ijk[0] = (int)i; ijk[1] = (int)j; ijk[2] = (int)k;
-  const int ci = i == 0 ? 0 : (i == g.cn[0] ? 2 : 1), cj = j == 0 ? 0 : (j == g.cn[1] ? 2 : 1);
-  const int ck = g.dim == 3 ? (k == 0 ? 0 : (k == g.cn[2] ? 2 : 1)) : 0;
-  return ci + 3 * cj + 9 * ck;
+// Prefix sums of a per-class weight over the lattice's nodes in node order, in closed form: whole planes + whole lines
+// + the started line.  With w = row length this IS row_ptr, with w = [class == dominant] the rank of a row among the
+// rows outside the class — no length array, no device-wide scan.
+struct lat_pref {
+  long long line[9], plane[3], total, base;   // base: the prefix at row_begin (subtracted by the callers)
+  int w[27];
+};
+
+__host__ __device__ inline int lat_axis_class(long long pos, int cn) { return pos == 0 ? 0 : (pos == cn ? 2 : 1); }
+// number of positions below pos (0 <= pos <= cn + 1) whose class along the axis is cls
+__host__ __device__ inline long long lat_below(long long pos, int cn, int cls) {
+  if (cls == 0) return pos > 0;
+  if (cls == 2) return pos > cn;
+  const long long m = pos - 1 < 0 ? 0 : pos - 1;
+  return m > cn - 1 ? cn - 1 : m;
 }
 
-__global__ void lat_row_len_k(lat_geom g, const lat_row_tmpl* __restrict__ T, int* __restrict__ rowlen, int* __restrict__ npair,
-                              unsigned long long* __restrict__ tot_pairs, int* __restrict__ n_dom) {   // n_dom[1]: longest row
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  int np = 0, dom = 0, rl = 0;
-  if (r < g.n_rows) {
-    int ijk[3];
-    const int c = lat_class_of(g, (long long)g.row_begin + r, ijk);
-    rl = c < 0 ? 0 : T[c].rlen;
-    rowlen[r] = rl;
-    np = c < 0 ? 0 : T[c].np;
-    npair[r] = np;
-    dom = c >= 0 && c == g.dom;
+// node offset q = node - node0 -> clamped lattice position; returns the class (-1: not a lattice node)
+// (node ids and strides are below 2^31: 32-bit divisions on the device)
+__host__ __device__ inline int lat_locate(const lat_geom& g, long long q64, long long* ijk) {
+  if (q64 < 0) { ijk[0] = ijk[1] = ijk[2] = 0; return -1; }
+  unsigned q = (unsigned)q64, k = 0;
+  if (g.dim == 3) { k = q / (unsigned)g.s[2]; q -= k * (unsigned)g.s[2]; }
+  unsigned j = q / (unsigned)g.s[1], i = q - j * (unsigned)g.s[1];
+  bool in = true;
+  if (g.dim == 3 && k > (unsigned)g.cn[2]) { k = g.cn[2] + 1; j = 0; i = 0; in = false; }
+  if (j > (unsigned)g.cn[1]) { j = g.cn[1] + 1; i = 0; in = false; }
+  if (i > (unsigned)g.cn[0]) { i = g.cn[0] + 1; in = false; }
+  ijk[0] = i; ijk[1] = j; ijk[2] = k;
+  if (!in) return -1;
+  return lat_axis_class(i, g.cn[0]) + 3 * lat_axis_class(j, g.cn[1]) + (g.dim == 3 ? 9 * lat_axis_class(k, g.cn[2]) : 0);
+}
+
+// sum of w over the lattice nodes in front of the (clamped) position ijk
+__host__ __device__ inline long long lat_prefix(const lat_geom& g, const lat_pref& P, const long long* ijk) {
+  const long long i = ijk[0], j = ijk[1], k = ijk[2];
+  if (g.dim == 3 && k > g.cn[2]) return P.total;
+  const int ck = g.dim == 3 ? lat_axis_class(k, g.cn[2]) : 0;
+  long long s = 0;
+  if (g.dim == 3)
+    for (int c = 0; c < 3; ++c) s += lat_below(k, g.cn[2], c) * P.plane[c];
+  for (int c = 0; c < 3; ++c) s += lat_below(j, g.cn[1], c) * P.line[c + 3 * ck];
+  if (j <= g.cn[1]) {
+    const int cj = lat_axis_class(j, g.cn[1]);
+    for (int c = 0; c < 3; ++c) s += lat_below(i, g.cn[0], c) * P.w[c + 3 * cj + 9 * ck];
   }
-  // block totals
-  __shared__ int sh[256], sd[256], sm[256];
-  sh[threadIdx.x] = np; sd[threadIdx.x] = dom; sm[threadIdx.x] = rl;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      sh[threadIdx.x] += sh[threadIdx.x + o]; sd[threadIdx.x] += sd[threadIdx.x + o];
-      sm[threadIdx.x] = max(sm[threadIdx.x], sm[threadIdx.x + o]);
+  return s;
+}
+
+lat_pref lat_pref_make(const lat_geom& g, const int* w) {
+  lat_pref P = {};
+  auto cnt = [&](int d, int c) -> long long { return c == 1 ? g.cn[d] - 1 : 1; };
+  for (int c = 0; c < 27; ++c) P.w[c] = w[c];
+  for (int ck = 0; ck < 3; ++ck) {
+    for (int cj = 0; cj < 3; ++cj) {
+      long long l = 0;
+      for (int c = 0; c < 3; ++c) l += cnt(0, c) * w[c + 3 * cj + 9 * ck];
+      P.line[cj + 3 * ck] = l;
+      P.plane[ck] += cnt(1, cj) * l;
     }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) { atomicAdd(tot_pairs, (unsigned long long)sh[0]); atomicAdd(n_dom, sd[0]); atomicMax(n_dom + 1, sm[0]); }
+  P.total = P.plane[0];
+  if (g.dim == 3) P.total = cnt(2, 0) * P.plane[0] + cnt(2, 1) * P.plane[1] + cnt(2, 2) * P.plane[2];
+  long long ijk[3];
+  lat_locate(g, (long long)g.row_begin - g.node0, ijk);
+  P.base = lat_prefix(g, P, ijk);
+  return P;
 }
 
-__global__ void lat_row_fill_k(lat_geom g, const lat_row_tmpl* __restrict__ T, const int* __restrict__ row_ptr,
+// slice s of the padded scatter map: 32 x the largest incidence count among its 32 rows
+__global__ void lat_slice_sizes_k(lat_geom g, const lat_row_tmpl* __restrict__ T, int n_slices, int* __restrict__ size) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= n_slices) return;
+  const int r = s * 32 + (threadIdx.x & 31);
+  long long ijk[3];
+  const int c = r < g.n_rows ? lat_locate(g, (long long)g.row_begin + r - g.node0, ijk) : -1;
+  int np = c < 0 ? 0 : T[c].np;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) np = max(np, __shfl_xor_sync(0xffffffffu, np, o));
+  if ((threadIdx.x & 31) == 0) size[s] = np * 32;
+}
+
+__global__ void lat_row_fill_k(lat_geom g, lat_pref PL, lat_pref PD, const lat_row_tmpl* __restrict__ T,
                                const int* __restrict__ slice_ptr, int2* __restrict__ rowinfo, int* __restrict__ col_idx,
-                               unsigned* __restrict__ sell_code, int* __restrict__ sell_elem, int map_only) {
-  // map_only = 0: rowinfo + columns of every row, scatter map of the rows OUTSIDE the dominant class (the class rows'
-  // map is read by no kernel of the default path and is written on demand: femx_pattern_complete_map);
+                               unsigned* __restrict__ sell_code, int* __restrict__ sell_elem, int* __restrict__ other_rows,
+                               int map_only) {
+  // map_only = 0: rowinfo + columns of every row, the list of rows outside the dominant class and their scatter map
+  // (the class rows' map is read by no kernel of the default path and is written on demand: femx_pattern_complete_map);
   // map_only = 1: the scatter map of the class rows
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r > g.n_rows) return;
-  if (r == g.n_rows) { if (!map_only) rowinfo[r] = make_int2(row_ptr ? row_ptr[r] : 0, 0); return; }
-  int ijk[3];
-  const long long node = (long long)g.row_begin + r;
-  const int c = lat_class_of(g, node, ijk);
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int rc = min(r, g.n_rows);                                // (lanes behind the last row: zero-length rows at nnz)
+  const long long node = (long long)g.row_begin + rc;
+  long long ijk[3];
+  int c = lat_locate(g, node - g.node0, ijk);
+  if (r >= g.n_rows) c = -1;
   if (!map_only) {
-    const int rp = row_ptr[r];
-    if (c < 0) { rowinfo[r] = make_int2(rp, 0); return; }
-    const lat_row_tmpl& t0 = T[c];
-    rowinfo[r] = make_int2(rp, t0.np | (c == g.dom ? FEMX_ROW_SPEC : 0) | (t0.self << 24));
-    for (int k = 0; k < t0.rlen; ++k)
-      col_idx[rp + k] = (int)(node + t0.col[k][0] + t0.col[k][1] * g.s[1] + t0.col[k][2] * g.s[2]);
-    if (c == g.dom) return;
+    // rowinfo: one 8-byte store per row (row_ptr in closed form); columns: the 32 rows of a warp own ONE contiguous piece
+    // of col_idx, written 128 bytes per instruction (entry p belongs to the last row j of the warp with row_ptr[j] <= p)
+    const int rp = (int)(lat_prefix(g, PL, ijk) - PL.base);
+    if (r <= g.n_rows)
+      rowinfo[r] = make_int2(rp, c < 0 ? 0 : (T[c].np | (c == g.dom ? FEMX_ROW_SPEC : 0) | (T[c].self << 24)));
+    if (r < g.n_rows && c != g.dom && other_rows) other_rows[r - (int)(lat_prefix(g, PD, ijk) - PD.base)] = r;
+    const int p_begin = __shfl_sync(0xffffffffu, rp, 0);
+    const int p_end = __shfl_sync(0xffffffffu, rp + (c < 0 ? 0 : T[c].rlen), 31);
+    const int c0 = __shfl_sync(0xffffffffu, c, 0);
+    const int row0 = g.row_begin + (r - lane);
+    if (c0 >= 0 && T[c0].rlen > 1 && __all_sync(0xffffffffu, c == c0)) {
+      // 32 rows of one class (the usual warp): position -> (row, entry) by one multiplication
+      const int len = T[c0].rlen;
+      const unsigned magic = 0xffffffffu / (unsigned)len + 1u;     // floor(idx / len) = umulhi(idx, magic), idx < 32 * 27
+      const int* __restrict__ off = T[c0].off;
+      for (int idx = lane; idx < 32 * len; idx += 32) {
+        const int j = (int)__umulhi((unsigned)idx, magic);
+        col_idx[p_begin + idx] = row0 + j + off[idx - j * len];
+      }
+    } else {
+      for (int base = p_begin; base < p_end; base += 32) {
+        const int p = base + lane;
+        int j = 0;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+          const int v = __shfl_sync(0xffffffffu, rp, j + s);
+          if (v <= p) j += s;
+        }
+        const int rpj = __shfl_sync(0xffffffffu, rp, j), cj = __shfl_sync(0xffffffffu, c, j);
+        if (p < p_end && cj >= 0) col_idx[p] = row0 + j + T[cj].off[p - rpj];
+      }
+    }
+    if (c < 0 || c == g.dom) return;
   } else if (c < 0 || c != g.dom) {
     return;
   }
@@ -937,73 +1078,99 @@ int build_from_lattice(femx_ctx* ctx, femx_pattern* p, cudaStream_t st) {
   for (int d = 0; d < 3; ++d) { g.cn[d] = L.cn[d]; g.s[d] = L.s[d]; }
   g.node0 = L.node0; g.row_begin = (int)p->row_begin; g.n_rows = (int)nr;
   g.dom = want_class ? dom : -1;
-  lat_row_tmpl* d_T = nullptr;
-  int *d_rowlen = nullptr, *d_np = nullptr, *d_row_ptr = nullptr, *d_ssize = nullptr, *d_flags = nullptr;
-  unsigned long long* d_tot = nullptr;
-  int rc = FEMX_OK;
-  auto cleanup = [&]() {
-    cudaFreeAsync(d_T, st); cudaFreeAsync(d_rowlen, st); cudaFreeAsync(d_np, st); cudaFreeAsync(d_row_ptr, st);
-    cudaFreeAsync(d_ssize, st); cudaFreeAsync(d_flags, st); cudaFreeAsync(d_tot, st);
+  // everything the general pass gets from scans and reductions follows from the class counts of the row range
+  long long cnt[27], nnz = 0, tot_pairs = 0, n_dom = 0;
+  int max_row = 0, max_other = 0;
+  auto count_classes = [&]() {
+    long long e_ijk[3];
+    lat_locate(g, (long long)g.row_begin + nr - g.node0, e_ijk);
+    for (int c = 0; c < 27; ++c) {
+      int w[27] = {};
+      w[c] = 1;
+      const lat_pref P = lat_pref_make(g, w);
+      cnt[c] = T[c].np ? lat_prefix(g, P, e_ijk) - P.base : 0;
+    }
   };
+  count_classes();
+  if (want_class && cnt[dom] * 4 < nr) g.dom = -1;   // (the general pass wants a quarter of its sample rows)
+  for (int c = 0; c < 27; ++c) {
+    if (cnt[c] <= 0) continue;
+    nnz += cnt[c] * T[c].rlen;
+    tot_pairs += cnt[c] * T[c].np;
+    max_row = std::max(max_row, T[c].rlen);
+    if (c == g.dom) n_dom = cnt[c];
+    else max_other = std::max(max_other, T[c].rlen);
+  }
+  if (nnz >= (1LL << 31) - 1 || tot_pairs >= (1LL << 31) - 1)
+    return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: %lld node-level nonzeros / %lld incidences exceed 32-bit offsets", nnz, tot_pairs);
+  int w_len[27], w_dom[27];
+  for (int c = 0; c < 27; ++c) { w_len[c] = T[c].rlen; w_dom[c] = c == g.dom; }
+  const lat_pref PL = lat_pref_make(g, w_len), PD = lat_pref_make(g, w_dom);
+  for (auto& t : T)
+    for (int k = 0; k < t.rlen; ++k) t.off[k] = (int)(t.col[k][0] + t.col[k][1] * L.s[1] + t.col[k][2] * L.s[2]);
+
+  lat_row_tmpl* d_T = nullptr;
+  int *d_ssize = nullptr, *d_flags = nullptr;
+  long long* d_tot = nullptr;
+  int rc = FEMX_OK;
+  auto cleanup = [&]() { cudaFreeAsync(d_T, st); cudaFreeAsync(d_ssize, st); cudaFreeAsync(d_flags, st); cudaFreeAsync(d_tot, st); };
 #define LB_TRY(x) do { rc = (x); if (rc != FEMX_OK) { cleanup(); return rc; } } while (0)
 #define LB_CUDA(call)                                                                                   \
   do {                                                                                                  \
     cudaError_t e__ = (call);                                                                           \
     if (e__ != cudaSuccess) { cleanup(); return femx_fail(ctx, FEMX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); } \
   } while (0)
+  const int64_t n_slices = (nr + 31) / 32;
   LB_TRY(tmp_alloc(ctx, &d_T, 27, st));
-  LB_TRY(tmp_alloc(ctx, &d_rowlen, nr + 1, st));
-  LB_TRY(tmp_alloc(ctx, &d_np, nr + 1, st));
-  LB_TRY(tmp_alloc(ctx, &d_row_ptr, nr + 1, st));
   LB_TRY(tmp_alloc(ctx, &d_flags, 4, st));
+  LB_TRY(tmp_alloc(ctx, &d_ssize, n_slices + 1, st));
   LB_TRY(tmp_alloc(ctx, &d_tot, 1, st));
   LB_CUDA(cudaMemcpyAsync(d_T, T.data(), sizeof(lat_row_tmpl) * 27, cudaMemcpyHostToDevice, st));
   LB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, st));
-  LB_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long), st));
-  if (nr > 0) lat_row_len_k<<<nblocks(nr, 256), 256, 0, st>>>(g, d_T, d_rowlen, d_np, d_tot, d_flags);
-  long long nnz = 0;
-  LB_TRY(exclusive_scan(ctx, d_rowlen, nr, d_row_ptr, &nnz, st));
-  unsigned long long tot_pairs = 0;
-  int h_flags[4];
-  LB_CUDA(cudaMemcpyAsync(&tot_pairs, d_tot, sizeof tot_pairs, cudaMemcpyDeviceToHost, st));
-  LB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
-  LB_CUDA(cudaStreamSynchronize(st));
-  if (nnz >= (1LL << 31) - 1 || tot_pairs >= (1ULL << 31) - 1) {
-    cleanup();
-    return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: %lld node-level nonzeros / %llu incidences exceed 32-bit offsets", nnz, tot_pairs);
-  }
-  long long n_dom = h_flags[0];
-  p->max_row = h_flags[1];
-  if (want_class && n_dom * 4 < nr) { g.dom = -1; n_dom = 0; }  // (the general pass wants a quarter of its sample rows)
+  p->max_row = max_row;
   p->n_pairs = (int64_t)tot_pairs;
   p->nnz_node = nnz;
+  const long long n_other = g.dom >= 0 && n_dom > 0 ? nr - n_dom : 0;
+  LB_TRY(dev_alloc(ctx, &p->d_slice_ptr, n_slices + 1, &p->bytes, st));
+  // the padded scatter map is allocated by its bound (every slice as long as the longest row's incidence list: on a
+  // lattice that is what all but the boundary slices are); the exact size arrives with the final synchronisation
+  int max_np = 0;
+  for (int c = 0; c < 27; ++c)
+    if (cnt[c] > 0) max_np = std::max(max_np, T[c].np);
+  long long n_sell = n_slices * 32 * max_np;
+  if (n_sell >= (1LL << 31) - 1)
+    return (cleanup(), femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: padded scatter map (%lld) exceeds 32-bit offsets", n_sell));
+  if (n_slices > 0) lat_slice_sizes_k<<<nblocks(n_slices, 8), 256, 0, st>>>(g, d_T, (int)n_slices, d_ssize);
+  LB_TRY(exclusive_scan(ctx, d_ssize, n_slices, p->d_slice_ptr, nullptr, st, d_tot));
   LB_TRY(dev_alloc(ctx, &p->d_rowinfo, nr + 1, &p->bytes, st));
   LB_TRY(dev_alloc(ctx, &p->d_col_idx, nnz + 8, &p->bytes, st));
   LB_CUDA(cudaMemsetAsync(p->d_col_idx + nnz, 0, sizeof(int) * 8, st));
-  const int64_t n_slices = (nr + 31) / 32;
-  LB_TRY(tmp_alloc(ctx, &d_ssize, n_slices + 1, st));
-  LB_TRY(dev_alloc(ctx, &p->d_slice_ptr, n_slices + 1, &p->bytes, st));
-  long long n_sell = 0;
-  if (n_slices > 0) slice_sizes_cnt<<<nblocks(n_slices, 8), 256, 0, st>>>(d_np, (int)nr, (int)n_slices, d_ssize);
-  LB_TRY(exclusive_scan(ctx, d_ssize, n_slices, p->d_slice_ptr, &n_sell, st));
-  if (n_sell >= (1LL << 31) - 1) {
-    cleanup();
-    return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: padded scatter map (%lld) exceeds 32-bit offsets", n_sell);
-  }
-  p->n_sell = n_sell;
   LB_TRY(dev_alloc(ctx, &p->d_sell_code, n_sell, &p->bytes, st));
   LB_TRY(dev_alloc(ctx, &p->d_sell_elem, n_sell, &p->bytes, st));
+  if (n_other > 0) LB_TRY(dev_alloc(ctx, &p->d_other_rows, n_other, &p->bytes, st));
   // (no zero fill: the padding of a slice is copied by the generic pass's bulk loads but never used)
-  lat_row_fill_k<<<nblocks(nr + 1, 128), 128, 0, st>>>(g, d_T, d_row_ptr, p->d_slice_ptr, p->d_rowinfo, p->d_col_idx,
-                                                       p->d_sell_code, p->d_sell_elem, 0);
-  LB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, st));
+  lat_row_fill_k<<<nblocks(nr + 1, 128), 128, 0, st>>>(g, PL, PD, d_T, p->d_slice_ptr, p->d_rowinfo, p->d_col_idx,
+                                                       p->d_sell_code, p->d_sell_elem, n_other > 0 ? p->d_other_rows : nullptr, 0);
   if (nr > 0) {
     int64_t ntiles = (nr + p->tile_nodes - 1) / p->tile_nodes;
     tile_max<<<nblocks(ntiles, 128), 128, 0, st>>>(p->d_rowinfo, p->d_slice_ptr, (int)nr, p->tile_nodes, d_flags + 2);
   }
+  // the scatter map of the class rows is completed on demand (femx_pattern_complete_map); keep what that needs
+  p->map_complete = !(g.dom >= 0 && n_dom > 0);
+  if (!p->map_complete) {
+    rc = dev_alloc(ctx, (lat_row_tmpl**)&p->d_lat_tmpl, 27, &p->bytes, st);
+    if (rc != FEMX_OK) { cleanup(); return rc; }
+    LB_CUDA(cudaMemcpyAsync(p->d_lat_tmpl, d_T, sizeof(lat_row_tmpl) * 27, cudaMemcpyDeviceToDevice, st));   // (stream-ordered before d_T is freed)
+    p->lat_dom = g.dom;
+  }
+  int h_flags[4];
+  long long sell_exact = 0;
   LB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+  LB_CUDA(cudaMemcpyAsync(&sell_exact, d_tot, sizeof sell_exact, cudaMemcpyDeviceToHost, st));
   LB_CUDA(cudaStreamSynchronize(st));
   LB_CUDA(cudaGetLastError());
+  if (sell_exact > n_sell) { cleanup(); return femx_fail(ctx, FEMX_ERR_CUDA, "lattice pass: scatter map %lld above its bound %lld", sell_exact, n_sell); }
+  p->n_sell = sell_exact;
   p->max_tile_nnz = h_flags[2];
   p->max_tile_codes = h_flags[3];
   if (g.dom >= 0 && n_dom > 0) {
@@ -1017,21 +1184,13 @@ int build_from_lattice(femx_ctx* ctx, femx_pattern* p, cudaStream_t st) {
     char key[96];
     snprintf(key, sizeof key, "%016llx_%d_%d_%d", kh, D.np, D.rlen, D.self);
     p->spec_key = key;
-    LB_TRY(build_other_rows(ctx, p, n_dom, st));
+    p->n_other = n_other;
+    p->max_row_other = max_other;
     // the element-once numeric pass takes the class rows only when they are the lattice-interior nodes
     const int interior = dim == 3 ? 13 : 4;
     p->lat_rows = g.dom == interior ? n_dom : 0;
   } else {
     p->lat_rows = 0;
-  }
-  // the scatter map of the class rows is completed on demand (femx_pattern_complete_map); keep what that needs
-  p->map_complete = !(g.dom >= 0 && n_dom > 0);
-  if (!p->map_complete) {
-    rc = dev_alloc(ctx, (lat_row_tmpl**)&p->d_lat_tmpl, 27, &p->bytes, st);
-    if (rc != FEMX_OK) { cleanup(); return rc; }
-    LB_CUDA(cudaMemcpyAsync(p->d_lat_tmpl, d_T, sizeof(lat_row_tmpl) * 27, cudaMemcpyDeviceToDevice, st));
-    p->lat_dom = g.dom;
-    LB_CUDA(cudaStreamSynchronize(st));
   }
   cleanup();
   return FEMX_OK;
@@ -1055,8 +1214,9 @@ int femx_pattern_complete_map(const femx_pattern* cp, void* stream) {
   for (int d = 0; d < 3; ++d) { g.cn[d] = L.cn[d]; g.s[d] = L.s[d]; }
   g.node0 = L.node0; g.row_begin = (int)p->row_begin; g.n_rows = (int)p->n_rows;
   g.dom = p->lat_dom;
-  lat_row_fill_k<<<nblocks(p->n_rows + 1, 128), 128, 0, (cudaStream_t)stream>>>(g, (const lat_row_tmpl*)p->d_lat_tmpl, nullptr, p->d_slice_ptr,
-                                                                                  p->d_rowinfo, p->d_col_idx, p->d_sell_code, p->d_sell_elem, 1);
+  const lat_pref none = {};
+  lat_row_fill_k<<<nblocks(p->n_rows + 1, 128), 128, 0, (cudaStream_t)stream>>>(g, none, none, (const lat_row_tmpl*)p->d_lat_tmpl, p->d_slice_ptr,
+                                                                                  p->d_rowinfo, p->d_col_idx, p->d_sell_code, p->d_sell_elem, nullptr, 1);
   FEMX_CUDA_OK(p->ctx, cudaGetLastError());
   p->map_complete = true;
   return FEMX_OK;
