@@ -629,7 +629,10 @@ def main():
             cg = {"iterations": 100, "its_per_s": 100.0 / (cg_ms * 1e-3), "ms_total": cg_ms, "spmv_ms": spmv_ms,
                   "spmv_nnz_per_s": nnz_global / (spmv_ms * 1e-3),
                   "residual@0": float(res[0]), "residual@100": float(res[100]), "rms_error_vs_exact_solution_1": err1,
-                  "collectives_per_iteration": {"ncclSend/ncclRecv (grouped, halo of r)": 2 if world > 1 else 0,
+                  "collectives_per_iteration": {"ncclSend/ncclRecv (grouped, halo of r)": 2 if (world > 1 and not op.peer_halo) else 0,
+                                                "halo_path": ("none (1 rank)" if world == 1 else
+                                                              ("NVLink peer memory: the update kernel stores the boundary entries of r into the neighbours' ghost zones"
+                                                               if op.peer_halo else "ncclSend/ncclRecv on a second stream, overlapped with the interior rows")),
                                                 "reduction of 2 doubles": (0 if world == 1 else 1),
                                                 "reduction_path": ("none (1 rank)" if world == 1 else
                                                                    ("NVLink peer memory, fused into the kernel that finishes the dot products and advances alpha/beta"

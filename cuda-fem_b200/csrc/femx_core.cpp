@@ -36,6 +36,7 @@ const knob_entry kKnobs[] = {
     {"FEMX_LT_MINB", "lt_minb", &femx_knobs::lt_minb}, {"FEMX_LT_REGS", "lt_regs", &femx_knobs::lt_regs}, {"FEMX_LT_PF", "lt_pf", &femx_knobs::lt_pf}, {"FEMX_LT_UNROLL", "lt_unroll", &femx_knobs::lt_unroll},
     {"FEMX_LT_SIDE", "lt_side", &femx_knobs::lt_side},
     {"FEMX_DIST_GRAPH", "dist_graph", &femx_knobs::dist_graph}, {"FEMX_DIST_P2P", "dist_p2p", &femx_knobs::dist_p2p},
+    {"FEMX_DIST_PUSH", "dist_push", &femx_knobs::dist_push},
 };
 }  // namespace
 

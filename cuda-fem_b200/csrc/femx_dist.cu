@@ -106,7 +106,17 @@ struct femx_dist_op {
   cudaGraphExec_t graph = nullptr;
   const void* graph_x = nullptr;
   int use_graph = 1;
+  // peer-memory halo of the CG: r_ext sits behind a header {flag_from_lo, flag_from_hi, cnt_lo, cnt_hi, err} in ONE allocation
+  // that the two slab neighbours map through CUDA IPC; the update kernel stores its boundary entries of r into their ghost
+  // zones and raises their flag, the boundary rows' SpMV waits for the own flags (no NCCL call, no second stream)
+  char* halo_base = nullptr;
+  void *peer_lo = nullptr, *peer_hi = nullptr;   // mapped allocations of rank - 1 / rank + 1
+  void *push_lo_dst = nullptr, *push_hi_dst = nullptr;
+  unsigned long long *push_lo_flag = nullptr, *push_hi_flag = nullptr;
+  bool push = false;
 };
+
+#define FEMX_HALO_HDR 256
 
 namespace {
 
@@ -249,6 +259,68 @@ __global__ void cg_update_k(int64_t n, const double* __restrict__ sc, T* __restr
   r[i] = (T)((double)r[i] - alpha * sn);
 }
 
+// The update kernel of the peer-memory halo: the same arithmetic; the threads of the first send_lo / last send_hi entries
+// also store the new r into the neighbour's ghost zone (remote stores over NVLink), fence, and the LAST of the CTAs that touched
+// a zone (local counter) raises the neighbour's flag to the sequence number of this iteration (= reductions done so far: the
+// same number on every rank, monotone over solves).
+template <class T>
+__global__ void __launch_bounds__(256) cg_update_push_k(int64_t n, const double* __restrict__ sc, T* __restrict__ r, const T* __restrict__ w,
+                                                        T* __restrict__ p, T* __restrict__ s, T* __restrict__ x, int64_t send_lo,
+                                                        int64_t send_hi, T* __restrict__ dst_lo, T* __restrict__ dst_hi,
+                                                        unsigned long long* flag_lo, unsigned long long* flag_hi,
+                                                        unsigned* __restrict__ cnt, const unsigned long long* __restrict__ seq_counter,
+                                                        unsigned n_cta_lo, unsigned n_cta_hi) {
+  const double alpha = sc[4], beta = sc[5];
+  const int64_t b0 = (int64_t)blockIdx.x * blockDim.x, i = b0 + threadIdx.x;
+  bool remote = false;
+  if (i < n) {
+    const double pn = (double)r[i] + beta * (double)p[i];
+    const double sn = (double)w[i] + beta * (double)s[i];
+    p[i] = (T)pn;
+    s[i] = (T)sn;
+    x[i] = (T)((double)x[i] + alpha * pn);
+    const T rn = (T)((double)r[i] - alpha * sn);
+    r[i] = rn;
+    if (i < send_lo) { dst_lo[i] = rn; remote = true; }
+    if (i >= n - send_hi) { dst_hi[i - (n - send_hi)] = rn; remote = true; }
+  }
+  const int64_t b1 = min(b0 + (int64_t)blockDim.x, n) - 1;
+  const bool cta_lo = b0 < send_lo, cta_hi = send_hi > 0 && b1 >= n - send_hi;
+  if (cta_lo || cta_hi) {                      // (block-uniform)
+    if (remote) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned long long seq = *seq_counter;
+      if (cta_lo && atomicAdd(cnt, 1u) == n_cta_lo - 1) {
+        *cnt = 0;
+        __threadfence_system();
+        *(volatile unsigned long long*)flag_lo = seq;
+      }
+      if (cta_hi && atomicAdd(cnt + 1, 1u) == n_cta_hi - 1) {
+        cnt[1] = 0;
+        __threadfence_system();
+        *(volatile unsigned long long*)flag_hi = seq;
+      }
+    }
+  }
+}
+
+// waits until both neighbours have delivered this iteration's ghost entries (bounded: a lost peer raises err instead of
+// hanging the device)
+__global__ void halo_wait_k(const unsigned long long* flags, int need_lo, int need_hi, const unsigned long long* __restrict__ seq_counter,
+                            int* __restrict__ err) {
+  const unsigned long long seq = *seq_counter;
+  const int t = threadIdx.x;
+  if ((t == 0 && need_lo) || (t == 1 && need_hi)) {
+    const volatile unsigned long long* f = flags + t;
+    const long long t0 = clock64();
+    while (*f < seq) {
+      if (clock64() - t0 > (1LL << 33)) { *err = 1; break; }
+    }
+  }
+  __threadfence_system();
+}
+
 inline unsigned nb256(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 // ghost zones of `ext` (layout [ghost_lo | owned | ghost_hi]) from the neighbours, on the comm stream
@@ -319,6 +391,34 @@ int cg_iteration(femx_dist_op* op, void* x, cudaStream_t st) {
   const int64_t n = op->n_owned;
   const size_t es = esize(op->dtype);
   void* r = (char*)op->r_ext + op->ghost_lo * es;
+  if (op->push) {
+    // peer-memory halo: update + push, interior rows, wait for the neighbours' flags, boundary rows — one stream, no NCCL
+    const femx_pattern* p = op->pat;
+    const int64_t xb = (int64_t)p->col_base * p->nd;
+    unsigned long long* hdr = (unsigned long long*)op->halo_base;
+    unsigned* cnt = (unsigned*)(hdr + 2);
+    int* err = (int*)(hdr + 4);
+    const unsigned nb = nb256(n);
+    const unsigned c_lo = (unsigned)((op->send_lo + 255) / 256);
+    const unsigned c_hi = op->send_hi > 0 ? nb - (unsigned)((n - op->send_hi) / 256) : 0;
+    if (op->dtype == FEMX_F64)
+      cg_update_push_k<double><<<nb, 256, 0, st>>>(n, op->d_sc, (double*)r, (const double*)op->w, (double*)op->p, (double*)op->s, (double*)x,
+                                                   op->send_lo, op->send_hi, (double*)op->push_lo_dst, (double*)op->push_hi_dst,
+                                                   op->push_lo_flag, op->push_hi_flag, cnt, d->d_seq, c_lo, c_hi);
+    else
+      cg_update_push_k<float><<<nb, 256, 0, st>>>(n, op->d_sc, (float*)r, (const float*)op->w, (float*)op->p, (float*)op->s, (float*)x,
+                                                  op->send_lo, op->send_hi, (float*)op->push_lo_dst, (float*)op->push_hi_dst,
+                                                  op->push_lo_flag, op->push_hi_flag, cnt, d->d_seq, c_lo, c_hi);
+    FEMX_CUDA_OK(d->ctx, cudaGetLastError());
+    int rc = FEMX_OK;
+    if (op->int_hi > op->int_lo) rc = femx_spmv_range(p, op->dtype, op->vals, op->r_ext, xb, op->w, op->int_lo, op->int_hi, st);
+    if (rc != FEMX_OK) return rc;
+    halo_wait_k<<<1, 32, 0, st>>>(hdr, op->ghost_lo > 0 && d->rank > 0, op->ghost_hi > 0 && d->rank < d->world - 1, d->d_seq, err);
+    FEMX_CUDA_OK(d->ctx, cudaGetLastError());
+    rc = femx_spmv_range2(p, op->dtype, op->vals, op->r_ext, xb, op->w, 0, op->int_lo, op->int_hi, p->n_rows, st);
+    if (rc != FEMX_OK) return rc;
+    return reduce2(op, r, op->w, st);
+  }
   if (op->dtype == FEMX_F64)
     cg_update_k<double><<<nb256(n), 256, 0, st>>>(n, op->d_sc, (double*)r, (const double*)op->w, (double*)op->p, (double*)op->s, (double*)x);
   else
@@ -329,6 +429,62 @@ int cg_iteration(femx_dist_op* op, void* x, cudaStream_t st) {
   return reduce2(op, r, op->w, st);
 }
 
+// Peer mapping of the CG's residual buffers (collective: every rank of the communicator calls it from femx_dist_op_create).
+// One ncclAllGather carries {IPC handle, ghost_lo, n_owned, ghost_hi, ok} of every rank; a rank maps its two neighbours;
+// an all-reduce (MIN) makes the outcome unanimous.
+struct halo_record { cudaIpcMemHandle_t h; long long ghost_lo, n_owned, ghost_hi, ok; };
+
+void dist_setup_push(femx_dist_op* op) {
+  femx_dist* d = op->d;
+  const nccl_api* nc = get_nccl();
+  const int world = d->world;
+  const size_t es = esize(op->dtype);
+  bool ok = true;
+  halo_record mine = {};
+  mine.ghost_lo = op->ghost_lo; mine.n_owned = op->n_owned; mine.ghost_hi = op->ghost_hi;
+  if (cudaIpcGetMemHandle(&mine.h, op->halo_base) != cudaSuccess) ok = false;
+  mine.ok = ok ? 1 : 0;
+  std::vector<halo_record> all(world);
+  halo_record* d_all = nullptr;
+  if (cudaMalloc((void**)&d_all, sizeof(halo_record) * world + 16) != cudaSuccess) { (void)cudaGetLastError(); d_all = nullptr; }
+  // (from here on every rank makes the same collective calls whatever its own state)
+  if (d_all) cudaMemcpy(d_all + d->rank, &mine, sizeof mine, cudaMemcpyHostToDevice);
+  ncclResult_t r = d_all ? nc->AllGather(d_all + d->rank, d_all, sizeof mine, ncclUint8, d->comm, d->s_comm) : ncclSuccess;
+  if (!d_all || r != ncclSuccess || cudaStreamSynchronize(d->s_comm) != cudaSuccess) ok = false;
+  if (ok) cudaMemcpy(all.data(), d_all, sizeof(halo_record) * world, cudaMemcpyDeviceToHost);
+  for (int q = 0; q < world && ok; ++q) ok = all[q].ok == 1;
+  auto open = [&](int q, void** out) {
+    if (cudaIpcOpenMemHandle(out, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { *out = nullptr; ok = false; }
+  };
+  if (ok && d->rank > 0 && op->send_lo > 0) {
+    open(d->rank - 1, &op->peer_lo);
+    if (ok && all[d->rank - 1].ghost_hi != op->send_lo) ok = false;
+    if (ok) {
+      op->push_lo_dst = (char*)op->peer_lo + FEMX_HALO_HDR + (all[d->rank - 1].ghost_lo + all[d->rank - 1].n_owned) * es;
+      op->push_lo_flag = (unsigned long long*)op->peer_lo + 1;        // its flag_from_hi
+    }
+  }
+  if (ok && d->rank < world - 1 && op->send_hi > 0) {
+    open(d->rank + 1, &op->peer_hi);
+    if (ok && all[d->rank + 1].ghost_lo != op->send_hi) ok = false;
+    if (ok) {
+      op->push_hi_dst = (char*)op->peer_hi + FEMX_HALO_HDR;
+      op->push_hi_flag = (unsigned long long*)op->peer_hi;            // its flag_from_lo
+    }
+  }
+  (void)cudaGetLastError();
+  double flag = ok ? 1.0 : 0.0, *d_flag = (double*)(d_all + world);
+  if (d_all) {
+    cudaMemcpy(d_flag, &flag, sizeof flag, cudaMemcpyHostToDevice);
+    r = nc->AllReduce(d_flag, d_flag, 1, ncclDouble, ncclMin, d->comm, d->s_comm);
+    if (r == ncclSuccess && cudaStreamSynchronize(d->s_comm) == cudaSuccess) cudaMemcpy(&flag, d_flag, sizeof flag, cudaMemcpyDeviceToHost);
+    else flag = 0.0;
+    cudaFree(d_all);
+  } else {
+    flag = 0.0;
+  }
+  op->push = flag == 1.0;
+}
 
 // Peer buffers of the fused reduction: every rank allocates 2 x world slots, the IPC handles travel over one ncclAllGather,
 // every rank maps the others' buffers (NVLink peer access).  All ranks agree on success through an all-reduce (MIN), so either
@@ -480,7 +636,8 @@ int femx_dist_op_create(femx_dist* d, const femx_pattern* pat, int dtype, const 
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes ? bytes : 8); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes ? bytes : 8); } };
   alloc(&op->x_ext, n_ext * es);
-  alloc(&op->r_ext, n_ext * es);
+  alloc((void**)&op->halo_base, FEMX_HALO_HDR + n_ext * es);
+  if (e == cudaSuccess) op->r_ext = op->halo_base + FEMX_HALO_HDR;
   alloc(&op->w, op->n_owned * es);
   alloc(&op->p, op->n_owned * es);
   alloc(&op->s, op->n_owned * es);
@@ -540,6 +697,8 @@ int femx_dist_op_create(femx_dist* d, const femx_pattern* pat, int dtype, const 
       femx_dist_op_destroy(op);
       return femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_dist_op_create: a neighbour's ghost zone is larger than this rank's owned range");
     }
+    // (d->p2p and the option are the same on every rank: either all ranks make the collective calls below or none)
+    if (d->p2p && ctx->knobs.dist_push != 0) dist_setup_push(op);
   }
   *out = op;
   return FEMX_OK;
@@ -548,7 +707,9 @@ int femx_dist_op_create(femx_dist* d, const femx_pattern* pat, int dtype, const 
 void femx_dist_op_destroy(femx_dist_op* op) {
   if (!op) return;
   if (op->graph) cudaGraphExecDestroy(op->graph);
-  cudaFree(op->x_ext); cudaFree(op->r_ext); cudaFree(op->w); cudaFree(op->p); cudaFree(op->s);
+  if (op->peer_lo) cudaIpcCloseMemHandle(op->peer_lo);
+  if (op->peer_hi) cudaIpcCloseMemHandle(op->peer_hi);
+  cudaFree(op->x_ext); cudaFree(op->halo_base); cudaFree(op->w); cudaFree(op->p); cudaFree(op->s);
   cudaFree(op->d_sc); cudaFree(op->d_it); cudaFree(op->d_part); cudaFree(op->d_hist);
   delete op;
 }
@@ -569,6 +730,12 @@ int femx_dist_op_info(const femx_dist_op* op, int64_t* n_owned, int64_t* ghost_l
   if (ghost_hi) *ghost_hi = op->ghost_hi;
   if (interior_lo) *interior_lo = op->int_lo;
   if (interior_hi) *interior_hi = op->int_hi;
+  return FEMX_OK;
+}
+
+int femx_dist_op_peer_halo(const femx_dist_op* op, int* peer_halo) {
+  if (!op || !peer_halo) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_dist_op_peer_halo: NULL argument");
+  *peer_halo = op->push ? 1 : 0;
   return FEMX_OK;
 }
 
@@ -649,8 +816,14 @@ int femx_dist_cg(femx_dist_op* op, const void* d_b_owned, void* d_x_owned, int i
   }
   CG_CUDA(cudaEventRecord(t1, st));
   std::vector<double> hist(iters + 1);
+  int halo_err = 0;
   CG_CUDA(cudaMemcpyAsync(hist.data(), op->d_hist, sizeof(double) * (iters + 1), cudaMemcpyDeviceToHost, st));
+  if (op->push) CG_CUDA(cudaMemcpyAsync(&halo_err, op->halo_base + 32, sizeof(int), cudaMemcpyDeviceToHost, st));
   CG_CUDA(cudaStreamSynchronize(st));
+  if (halo_err) {
+    cudaMemsetAsync(op->halo_base + 32, 0, sizeof(int), st);
+    return fail(femx_fail(ctx, FEMX_ERR_CUDA, "femx_dist_cg: a neighbour's ghost entries did not arrive (peer-memory halo timed out)"));
+  }
   if (h_residuals)
     for (int k = 0; k <= iters; ++k) h_residuals[k] = std::sqrt(std::max(hist[k], 0.0));
   if (h_ms) cudaEventElapsedTime(h_ms, t0, t1);

@@ -28,6 +28,7 @@ struct femx_knobs {
   int lt_tx = 0, lt_ty = 0, lt_kc = 0, lt_minb = 0, lt_regs = 0, lt_pf = 0, lt_unroll = 2, lt_side = 1;  // FEMX_LT_*: tile shape / k-chunk / occupancy of that pass
   int dist_p2p = 1;     // FEMX_DIST_P2P    CG reduction over NVLink peer memory, fused with the dot products and the CG scalars (0: ncclAllReduce)
   int dist_graph = 1;   // FEMX_DIST_GRAPH  the CG iteration of femx_dist_cg is replayed from a CUDA graph
+  int dist_push = 1;    // FEMX_DIST_PUSH   CG halo: the update kernel stores the boundary entries of r straight into the neighbours' ghost zones (NVLink peer memory) instead of ncclSend/Recv
   std::string jit_dump; // FEMX_JIT_DUMP  directory that receives the generated sources
   std::string key() const;
 };

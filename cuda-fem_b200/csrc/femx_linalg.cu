@@ -1,6 +1,7 @@
 // Validation layer: CSR SpMV on the pattern's native layout and the fused
 // vector kernels of an unpreconditioned CG (no reference counterpart).
 // All reductions use a fixed grid and a fixed tree → bitwise reproducible.
+#include <algorithm>
 #include "femx_internal.h"
 
 namespace {
@@ -184,8 +185,12 @@ int femx_spmv_range2(const femx_pattern* p, int dtype, const void* d_values, con
   const int64_t n = (row_hi - row_lo) * p->nd;
   const long long xb = (long long)x_base - (long long)p->nd * p->col_base;
   const size_t rs = dtype == FEMX_F64 ? 8 : 4;
-  // (max_tile_nnz is taken over 128-row tiles starting at multiples of 128; a window that starts elsewhere lies in two of them)
-  const size_t smem = (size_t)(p->max_tile_nnz * ((row_lo % 128 || row_lo2 % 128) ? 2 : 1) + 2) * (rs + 4);
+  // (max_tile_nnz is taken over 128-row tiles starting at multiples of 128; a window that starts elsewhere lies in two of
+  // them — but never holds more than 128 of the longest rows, which on a structured slab is the smaller bound: twice the
+  // shared memory halved the resident CTAs of every rank whose first interior row is not a multiple of 128)
+  const size_t win_nnz = (row_lo % 128 || row_lo2 % 128) ? std::min<size_t>((size_t)p->max_tile_nnz * 2, (size_t)p->max_row * 128)
+                                                         : (size_t)p->max_tile_nnz;
+  const size_t smem = (win_nnz + 2) * (rs + 4);
   if (p->nd == 1 && smem <= 200 * 1024 && p->tile_nodes == 128) {
     // tile-staged kernel (128-row tiles)
     const int nblk_a = (int)((row_hi - row_lo + 127) / 128), nblk_b = (int)((row_hi2 - row_lo2 + 127) / 128);

@@ -682,6 +682,37 @@ __global__ void lattice_verify_lines(const int4* __restrict__ conn, lat_desc d, 
   if (__syncthreads_or(!ok) && threadIdx.x == 0) atomicAdd(bad, 1);
 }
 
+// ... and for any element type (triangles; unaligned connectivity): one thread per 32-bit word of a line
+template <int U>
+__global__ void lattice_verify_words(const int* __restrict__ conn, lat_desc d, unsigned line_words, unsigned long long magic_nn,
+                                     unsigned long long magic_p, int* __restrict__ bad) {
+  __shared__ int off[32];
+  if (threadIdx.x < 32) off[threadIdx.x] = d.off[threadIdx.x];
+  const unsigned line = blockIdx.x;
+  const unsigned ck = line / (unsigned)d.cny, cj = line - ck * (unsigned)d.cny;
+  const int base = (int)((unsigned)d.node0 + cj * (unsigned)d.sy + ck * (unsigned)d.sz);
+  const int* __restrict__ src = conn + (size_t)line * line_words;
+  const unsigned x0 = blockIdx.y * (blockDim.x * U) + threadIdx.x;
+  int v[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned x = x0 + u * blockDim.x;
+    v[u] = x < line_words ? __ldg(src + x) : 0;
+  }
+  __syncthreads();
+  bool ok = true;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned x = x0 + u * blockDim.x;
+    if (x < line_words) {
+      const unsigned e = (unsigned)(((unsigned long long)x * magic_nn) >> 34), a = x - e * (unsigned)d.nn;
+      const unsigned ci = (unsigned)(((unsigned long long)e * magic_p) >> 34), t = e - ci * (unsigned)d.P;
+      ok = ok && v[u] == base + (int)ci + off[t * d.nn + a];
+    }
+  }
+  if (__syncthreads_or(!ok) && threadIdx.x == 0) atomicAdd(bad, 1);
+}
+
 template <int U>
 void launch_verify_lines(const int* d_conn, const lat_desc& d, long long n_lines, unsigned line_elems, int* d_bad, cudaStream_t st) {
   const unsigned long long magic = ((1ULL << 34) + d.P - 1) / d.P;
@@ -783,6 +814,11 @@ int detect_lattice(femx_ctx* ctx, femx_pattern* p, const int* d_conn, cudaStream
       case 7: launch_verify_lines<7>(d_conn, d, n_lines, (unsigned)line_elems, d_tmp + 1, st); break;
       default: launch_verify_lines<8>(d_conn, d, n_lines, (unsigned)line_elems, d_tmp + 1, st); break;
     }
+  } else if (line_elems * nn >= 256 && line_elems * nn < (1LL << 29) && P * nn <= 32 && (line_elems * nn + 2047) / 2048 <= 65535) {
+    const unsigned words = (unsigned)(line_elems * nn);
+    const unsigned long long m_nn = ((1ULL << 34) + nn - 1) / nn, m_p = ((1ULL << 34) + P - 1) / P;
+    dim3 grid((unsigned)n_lines, (words + 2047) / 2048);
+    lattice_verify_words<8><<<grid, 256, 0, st>>>(d_conn, d, words, m_nn, m_p, d_tmp + 1);
   } else if (nn == 4 && (uintptr_t)d_conn % 16 == 0) lattice_verify<4><<<nblocks(ne, 1024), 256, 0, st>>>(d_conn, (unsigned)ne, d, d_tmp + 1);
   else lattice_verify<1><<<nblocks(ne, 1024), 256, 0, st>>>(d_conn, (unsigned)ne, d, d_tmp + 1);
   LT_CUDA(cudaMemcpyAsync(h_tmp, d_tmp + 1, sizeof(int), cudaMemcpyDeviceToHost, st));

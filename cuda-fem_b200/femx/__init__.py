@@ -52,7 +52,7 @@ SYMBOLS = [
     "femx_dist_unique_id", "femx_dist_create", "femx_dist_info",
     "femx_partition_extract", "femx_part_destroy", "femx_part_info", "femx_part_arrays", "femx_part_copy", "femx_part_gather",
     "femx_pattern_export_csr_mapped", "femx_dist_destroy", "femx_dist_slab", "femx_dist_allreduce",
-    "femx_dist_op_create", "femx_dist_op_destroy", "femx_dist_op_info", "femx_dist_spmv", "femx_dist_cg", "femx_spmv_rows",
+    "femx_dist_op_create", "femx_dist_op_destroy", "femx_dist_op_info", "femx_dist_op_peer_halo", "femx_dist_spmv", "femx_dist_cg", "femx_spmv_rows",
     "femx_form_compile", "femx_form_compile_offline", "femx_form_destroy", "femx_form_source",
     "femx_form_log", "femx_form_entry", "femx_form_prologue", "femx_form_cubin",
     "femx_mesh_rectangle", "femx_mesh_expand", "femx_mesh_box",
@@ -583,6 +583,9 @@ class DistOp:
         v = [C.c_int64() for _ in range(5)]
         dist.ctx.check(lib().femx_dist_op_info(self.h, *[C.byref(x) for x in v]))
         self.n_owned, self.ghost_lo, self.ghost_hi, self.interior_lo, self.interior_hi = (x.value for x in v)
+        ph = C.c_int()
+        dist.ctx.check(lib().femx_dist_op_peer_halo(self.h, C.byref(ph)))
+        self.peer_halo = bool(ph.value)   # the CG's halo goes through NVLink peer memory (no NCCL call in the iteration)
 
     def spmv(self, x, y=None, stream=None):
         import torch

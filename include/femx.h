@@ -361,6 +361,11 @@ void femx_dist_op_destroy(femx_dist_op* op);
  * ghost column (their SpMV overlaps the halo exchange). */
 int femx_dist_op_info(const femx_dist_op* op, int64_t* n_owned, int64_t* ghost_lo, int64_t* ghost_hi, int64_t* interior_lo,
                       int64_t* interior_hi);
+/* *peer_halo = 1 when femx_dist_cg moves its halo through NVLink peer memory: the update kernel stores the first / last owned
+ * entries of the new residual straight into the two neighbours' ghost zones (their buffers mapped through CUDA IPC) and raises
+ * a flag the boundary rows' SpMV waits for — no ncclSend/ncclRecv and no second stream inside the iteration.  0 = NCCL halo
+ * (peer mapping unavailable, option dist_push = 0, or world == 1).  The option must be the same on every rank. */
+int femx_dist_op_peer_halo(const femx_dist_op* op, int* peer_halo);
 /* y_owned = A[owned rows] x, x given by its owned part on every rank (device pointers, n_owned entries each). */
 int femx_dist_spmv(femx_dist_op* op, const void* d_x_owned, void* d_y_owned, void* stream);
 /* `iters` steps of unpreconditioned CG from x0 = 0 (Chronopoulos-Gear form: one SpMV, one fused update kernel and

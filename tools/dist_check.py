@@ -65,7 +65,7 @@ def main():
         print(json.dumps({"world": world, "n": n, "slab_rows_bitwise": bool(ok[0]), "dist_spmv_bitwise": bool(ok[1]),
                           "cg_history_rel_diff_vs_1_rank": rel, "cg_history_ok": bool(ok[2]),
                           "residual@0": float(resn[0]), "residual@100": float(resn[100]), "cg_ms": ms,
-                          "lattice": ps.lattice() is not None, "p2p_reduction": dd.p2p_reduction}))
+                          "lattice": ps.lattice() is not None, "p2p_reduction": dd.p2p_reduction, "peer_halo": op.peer_halo}))
     op.close(); dd.close(); o1.close(); d1.close()
     if world > 1:
         dist.destroy_process_group()
