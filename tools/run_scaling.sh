@@ -1,3 +1,6 @@
+#!/bin/bash
+# One strong-scaling point of the headline benchmark under torchrun:  bash tools/run_scaling.sh N   (N = 2, 4, 8; e.g. gpurun --gpus N)
+# writes gpurun_out/r02_bench_cfg3_nN.json and prints the headline fields
 cd /root/repo
 N=$1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29561"
