@@ -23,6 +23,9 @@
 
 namespace {
 
+// (cudaFreeAsync(NULL) is an error that would stay behind as the last error: clean-up paths free what exists)
+inline void free_async(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+
 // ------------------------------------------------------------------ scan ---
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
@@ -137,7 +140,7 @@ int exclusive_scan(femx_ctx* ctx, const int* d_in, int64_t n, int* d_out, long l
     e = cudaMemcpyAsync(h_total, d_sums + nt, sizeof(long long), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   }
-  cudaFreeAsync(d_sums, st);
+  free_async(d_sums, st);
   FEMX_CUDA_OK(ctx, e);
   return FEMX_OK;
 }
@@ -485,9 +488,9 @@ int build_other_rows(femx_ctx* ctx, femx_pattern* p, long long class_rows, cudaS
     p->n_other = n_other;
     p->max_row_other = mx;
   }
-  cudaFreeAsync(d_flag, st);
-  cudaFreeAsync(d_pos, st);
-  cudaFreeAsync(d_count, st);
+  free_async(d_flag, st);
+  free_async(d_pos, st);
+  free_async(d_count, st);
   return rc;
 }
 
@@ -501,8 +504,8 @@ int detect_stencil_class(femx_ctx* ctx, femx_pattern* p, const int* d_pair_ptr, 
   int rc = tmp_alloc(ctx, &d_hash, nr, st);
   if (rc == FEMX_OK) rc = tmp_alloc(ctx, &d_count, 1, st);
   auto done = [&](int code) {
-    cudaFreeAsync(d_hash, st);
-    cudaFreeAsync(d_count, st);
+    free_async(d_hash, st);
+    free_async(d_count, st);
     return code;
   };
   if (rc != FEMX_OK) return done(rc);
@@ -522,13 +525,13 @@ int detect_stencil_class(femx_ctx* ctx, femx_pattern* p, const int* d_pair_ptr, 
     int* d_sr = nullptr;
     rc = tmp_alloc(ctx, &d_sh, S, st);
     if (rc == FEMX_OK) rc = tmp_alloc(ctx, &d_sr, S, st);
-    if (rc != FEMX_OK) { cudaFreeAsync(d_sh, st); cudaFreeAsync(d_sr, st); return done(rc); }
+    if (rc != FEMX_OK) { free_async(d_sh, st); free_async(d_sr, st); return done(rc); }
     sample_rows<<<nblocks(S, 128), 128, 0, st>>>(d_hash, (long long)nr, S, d_sh, d_sr);
     cudaError_t e1 = cudaMemcpyAsync(hs.data(), d_sh, sizeof(unsigned long long) * S, cudaMemcpyDeviceToHost, st);
     cudaError_t e2 = cudaMemcpyAsync(hrow.data(), d_sr, sizeof(int) * S, cudaMemcpyDeviceToHost, st);
     cudaError_t e3 = cudaStreamSynchronize(st);
-    cudaFreeAsync(d_sh, st);
-    cudaFreeAsync(d_sr, st);
+    free_async(d_sh, st);
+    free_async(d_sr, st);
     SC_CUDA(e1); SC_CUDA(e2); SC_CUDA(e3);
   }
   int best = -1, best_cnt = 0;
@@ -732,7 +735,7 @@ int detect_lattice(femx_ctx* ctx, femx_pattern* p, const int* d_conn, cudaStream
   int* d_tmp = nullptr;
   int rc = tmp_alloc(ctx, &d_tmp, 4, st);
   if (rc != FEMX_OK) return rc;
-  auto done = [&](int code) { cudaFreeAsync(d_tmp, st); return code; };
+  auto done = [&](int code) { free_async(d_tmp, st); return code; };
 #define LT_CUDA(call)                                                                                  \
   do {                                                                                                 \
     cudaError_t e__ = (call);                                                                          \
@@ -1149,7 +1152,7 @@ int build_from_lattice(femx_ctx* ctx, femx_pattern* p, cudaStream_t st) {
   int *d_ssize = nullptr, *d_flags = nullptr;
   long long* d_tot = nullptr;
   int rc = FEMX_OK;
-  auto cleanup = [&]() { cudaFreeAsync(d_T, st); cudaFreeAsync(d_ssize, st); cudaFreeAsync(d_flags, st); cudaFreeAsync(d_tot, st); };
+  auto cleanup = [&]() { free_async(d_T, st); free_async(d_ssize, st); free_async(d_flags, st); free_async(d_tot, st); };
 #define LB_TRY(x) do { rc = (x); if (rc != FEMX_OK) { cleanup(); return rc; } } while (0)
 #define LB_CUDA(call)                                                                                   \
   do {                                                                                                  \
@@ -1307,8 +1310,8 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
   unsigned* d_pair_code = nullptr;
   int st_code = FEMX_OK;
   auto cleanup = [&]() {
-    cudaFreeAsync(d_cnt, st); cudaFreeAsync(d_pair_ptr, st); cudaFreeAsync(d_row_ptr, st); cudaFreeAsync(d_flags, st);
-    cudaFreeAsync(d_pair_elem, st); cudaFreeAsync(d_pair_code, st);
+    free_async(d_cnt, st); free_async(d_pair_ptr, st); free_async(d_row_ptr, st); free_async(d_flags, st);
+    free_async(d_pair_elem, st); free_async(d_pair_code, st);
   };
 #define PB_TRY(x)                                   \
   do {                                              \
@@ -1404,7 +1407,7 @@ int femx_pattern_build(femx_ctx* ctx, int nn, int nd, int64_t n_nodes, int64_t n
       if (n_slices > 0) slice_sizes<<<nblocks(n_slices, 8), 256, 0, st>>>(d_pair_ptr, (int)nr, (int)n_slices, d_ssize);
       st_code = exclusive_scan(ctx, d_ssize, n_slices, p->d_slice_ptr, &n_sell, st);
     }
-    cudaFreeAsync(d_ssize, st);
+    free_async(d_ssize, st);
     if (st_code != FEMX_OK) { cleanup(); femx_pattern_destroy(p); return st_code; }
     if (n_sell >= (1LL << 31) - 1) {
       cleanup(); femx_pattern_destroy(p);
