@@ -222,10 +222,14 @@ __global__ void __launch_bounds__(256) cg_reduce_p2p_k(const double* __restrict_
       __threadfence_system();
       dst->seq = seq;
       volatile p2p_slot* src = peers[rank] + par * world + r;      // rank r's contribution, in my buffer
-      while (src->seq != seq) { }
+      const long long t0 = clock64();
+      bool lost = false;                                            // (bounded: a lost peer poisons the scalars instead of hanging the device)
+      while (src->seq != seq) {
+        if (clock64() - t0 > (1LL << 34)) { lost = true; break; }
+      }
       __threadfence_system();
-      sh0[r] = src->v[0];
-      sh1[r] = src->v[1];
+      sh0[r] = lost ? __longlong_as_double(0x7ff8000000000000LL) : src->v[0];
+      sh1[r] = lost ? __longlong_as_double(0x7ff8000000000000LL) : src->v[1];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
