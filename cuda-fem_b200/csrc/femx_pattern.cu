@@ -874,6 +874,7 @@ struct lat_geom {
   long long node0;
   int row_begin, n_rows;
   int dom;  // dominant class (flagged FEMX_ROW_SPEC), -1 = none
+  int w32;  // the prefix sums of the whole lattice fit 32 bits (device: lat_prefix32)
 };
 
 // Prefix sums of a per-class weight over the lattice's nodes in node order, in closed form: whole planes + whole lines
@@ -925,6 +926,29 @@ __host__ __device__ inline long long lat_prefix(const lat_geom& g, const lat_pre
   return s;
 }
 
+// the same sum in 32-bit arithmetic (the caller has checked that P.total fits): a third of the integer multiplies
+__device__ __forceinline__ int lat_below32(int pos, int cn, int cls) {
+  return cls == 0 ? (pos > 0) : (cls == 2 ? (pos > cn) : min(max(pos - 1, 0), cn - 1));
+}
+__device__ __forceinline__ int lat_prefix32(const lat_geom& g, const lat_pref& P, const long long* ijk) {
+  const int i = (int)ijk[0], j = (int)ijk[1], k = (int)ijk[2];
+  if (g.dim == 3 && k > g.cn[2]) return (int)P.total;
+  const int ck = g.dim == 3 ? lat_axis_class(k, g.cn[2]) : 0;
+  int s = 0;
+  if (g.dim == 3) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s += lat_below32(k, g.cn[2], c) * (int)P.plane[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) s += lat_below32(j, g.cn[1], c) * (int)P.line[c + 3 * ck];
+  if (j <= g.cn[1]) {
+    const int cj = lat_axis_class(j, g.cn[1]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s += lat_below32(i, g.cn[0], c) * P.w[c + 3 * cj + 9 * ck];
+  }
+  return s;
+}
+
 lat_pref lat_pref_make(const lat_geom& g, const int* w) {
   lat_pref P = {};
   auto cnt = [&](int d, int c) -> long long { return c == 1 ? g.cn[d] - 1 : 1; };
@@ -945,17 +969,28 @@ lat_pref lat_pref_make(const lat_geom& g, const int* w) {
   return P;
 }
 
-// slice s of the padded scatter map: 32 x the largest incidence count among its 32 rows
+// slice s of the padded scatter map: 32 x the largest incidence count among its 32 rows.  One thread per slice: a slice
+// that lies inside one lattice line (all but cn[0] / 32 of them) has at most three classes, known from its two ends.
 __global__ void lat_slice_sizes_k(lat_geom g, const lat_row_tmpl* __restrict__ T, int n_slices, int* __restrict__ size) {
-  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slices) return;
-  const int r = s * 32 + (threadIdx.x & 31);
+  const int r0 = s * 32, r1 = min(r0 + 32, g.n_rows);
   long long ijk[3];
-  const int c = r < g.n_rows ? lat_locate(g, (long long)g.row_begin + r - g.node0, ijk) : -1;
-  int np = c < 0 ? 0 : T[c].np;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) np = max(np, __shfl_xor_sync(0xffffffffu, np, o));
-  if ((threadIdx.x & 31) == 0) size[s] = np * 32;
+  const int c0 = lat_locate(g, (long long)g.row_begin + r0 - g.node0, ijk);
+  int np = 0;
+  if (c0 >= 0 && ijk[0] + (r1 - r0 - 1) <= g.cn[0]) {
+    const int i0 = (int)ijk[0], i1 = i0 + (r1 - r0 - 1);
+    const int base = c0 - lat_axis_class(i0, g.cn[0]);   // 3 cj + 9 ck
+    if (i0 == 0) np = max(np, T[base].np);
+    if (i1 == g.cn[0]) np = max(np, T[base + 2].np);
+    if (max(i0, 1) <= min(i1, g.cn[0] - 1)) np = max(np, T[base + 1].np);
+  } else {
+    for (int r = r0; r < r1; ++r) {
+      const int c = lat_locate(g, (long long)g.row_begin + r - g.node0, ijk);
+      if (c >= 0) np = max(np, T[c].np);
+    }
+  }
+  size[s] = np * 32;
 }
 
 __global__ void lat_row_fill_k(lat_geom g, lat_pref PL, lat_pref PD, const lat_row_tmpl* __restrict__ T,
@@ -975,10 +1010,11 @@ __global__ void lat_row_fill_k(lat_geom g, lat_pref PL, lat_pref PD, const lat_r
   if (!map_only) {
     // rowinfo: one 8-byte store per row (row_ptr in closed form); columns: the 32 rows of a warp own ONE contiguous piece
     // of col_idx, written 128 bytes per instruction (entry p belongs to the last row j of the warp with row_ptr[j] <= p)
-    const int rp = (int)(lat_prefix(g, PL, ijk) - PL.base);
+    const int rp = g.w32 ? lat_prefix32(g, PL, ijk) - (int)PL.base : (int)(lat_prefix(g, PL, ijk) - PL.base);
     if (r <= g.n_rows)
       rowinfo[r] = make_int2(rp, c < 0 ? 0 : (T[c].np | (c == g.dom ? FEMX_ROW_SPEC : 0) | (T[c].self << 24)));
-    if (r < g.n_rows && c != g.dom && other_rows) other_rows[r - (int)(lat_prefix(g, PD, ijk) - PD.base)] = r;
+    if (r < g.n_rows && c != g.dom && other_rows)
+      other_rows[r - (g.w32 ? lat_prefix32(g, PD, ijk) - (int)PD.base : (int)(lat_prefix(g, PD, ijk) - PD.base))] = r;
     const int p_begin = __shfl_sync(0xffffffffu, rp, 0);
     const int p_end = __shfl_sync(0xffffffffu, rp + (c < 0 ? 0 : T[c].rlen), 31);
     const int c0 = __shfl_sync(0xffffffffu, c, 0);
@@ -1145,6 +1181,7 @@ int build_from_lattice(femx_ctx* ctx, femx_pattern* p, cudaStream_t st) {
   int w_len[27], w_dom[27];
   for (int c = 0; c < 27; ++c) { w_len[c] = T[c].rlen; w_dom[c] = c == g.dom; }
   const lat_pref PL = lat_pref_make(g, w_len), PD = lat_pref_make(g, w_dom);
+  g.w32 = PL.total < (1LL << 31) - 1 && PD.total < (1LL << 31) - 1;
   for (auto& t : T)
     for (int k = 0; k < t.rlen; ++k) t.off[k] = (int)(t.col[k][0] + t.col[k][1] * L.s[1] + t.col[k][2] * L.s[2]);
 
@@ -1179,7 +1216,7 @@ int build_from_lattice(femx_ctx* ctx, femx_pattern* p, cudaStream_t st) {
   long long n_sell = n_slices * 32 * max_np;
   if (n_sell >= (1LL << 31) - 1)
     return (cleanup(), femx_fail(ctx, FEMX_ERR_UNSUPPORTED, "femx_pattern_build: padded scatter map (%lld) exceeds 32-bit offsets", n_sell));
-  if (n_slices > 0) lat_slice_sizes_k<<<nblocks(n_slices, 8), 256, 0, st>>>(g, d_T, (int)n_slices, d_ssize);
+  if (n_slices > 0) lat_slice_sizes_k<<<nblocks(n_slices, 256), 256, 0, st>>>(g, d_T, (int)n_slices, d_ssize);
   LB_TRY(exclusive_scan(ctx, d_ssize, n_slices, p->d_slice_ptr, nullptr, st, d_tot));
   LB_TRY(dev_alloc(ctx, &p->d_rowinfo, nr + 1, &p->bytes, st));
   LB_TRY(dev_alloc(ctx, &p->d_col_idx, nnz + 8, &p->bytes, st));
