@@ -43,24 +43,28 @@ __global__ void box_nodes(double x0, double y0, double z0, double hx, double hy,
 
 // Kuhn split, one thread per tet; permutation table and orientation fix as in
 // DESIGN.md (even permutations swap their two middle vertices).
-__constant__ int c_perm[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
-__constant__ int c_odd[6] = {0, 1, 1, 0, 0, 1};
 
-__global__ void box_cells(int64_t nx, int64_t ny, int64_t n_tets, int* __restrict__ conn) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_tets) return;
-  int64_t cell = t / 6;
-  int p = (int)(t - cell * 6);
-  int64_t c[3] = {cell % nx, (cell / nx) % ny, cell / (nx * ny)};
+// one thread per tetrahedron, one 16-byte store; 32-bit arithmetic (the caller has checked 4 * n_tets < 2^31) and the
+// permutation table packed into an immediate (a constant-memory table indexed per thread serialises)
+__global__ void box_cells(int64_t nx64, int64_t ny64, int64_t n_tets, int* __restrict__ conn) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)n_tets) return;
+  const unsigned nx = (unsigned)nx64, ny = (unsigned)ny64;
+  const unsigned cell = t / 6u, p = t - cell * 6u;
+  const unsigned line = cell / nx, cz = line / ny;
+  unsigned c[3] = {cell - line * nx, line - cz * ny, cz};
+  // axis order of Kuhn tetrahedron p, 2 bits per step: {0,1,2} {0,2,1} {1,0,2} {1,2,0} {2,0,1} {2,1,0}; odd permutations: p = 1, 2, 5
+  const unsigned long long kPerm = 0x24ull | (0x18ull << 6) | (0x21ull << 12) | (0x09ull << 18) | (0x12ull << 24) | (0x06ull << 30);
+  const unsigned perm = (unsigned)(kPerm >> (6 * p)) & 63u;
   int v[4];
   v[0] = (int)((c[2] * (ny + 1) + c[1]) * (nx + 1) + c[0]);
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    int ax = c_perm[p][a];
-    if (ax == 0) c[0] += 1; else if (ax == 1) c[1] += 1; else c[2] += 1;
+    const unsigned ax = (perm >> (2 * a)) & 3u;
+    c[0] += ax == 0; c[1] += ax == 1; c[2] += ax == 2;
     v[a + 1] = (int)((c[2] * (ny + 1) + c[1]) * (nx + 1) + c[0]);
   }
-  if (!c_odd[p]) { int tmp = v[1]; v[1] = v[2]; v[2] = tmp; }
+  if (!((0x26u >> p) & 1u)) { int tmp = v[1]; v[1] = v[2]; v[2] = tmp; }
   reinterpret_cast<int4*>(conn)[t] = make_int4(v[0], v[1], v[2], v[3]);
 }
 
