@@ -246,8 +246,6 @@ __global__ void __launch_bounds__(256) cg_reduce_p2p_k(const double* __restrict_
 
 __global__ void cg_scalars_k(double* __restrict__ sc, double* __restrict__ hist, int* __restrict__ it) { cg_scalars(sc, hist, it); }
 
-__global__ void cg_final_k(const double* __restrict__ sc, double* __restrict__ hist, const int* __restrict__ it) { hist[*it] = sc[0]; }
-
 // p = r + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s
 template <class T>
 __global__ void cg_update_k(int64_t n, const double* __restrict__ sc, T* __restrict__ r, const T* __restrict__ w,

@@ -103,11 +103,10 @@ int femx_partition_extract(femx_ctx* ctx, int nn, int64_t n_nodes, int64_t n_ele
     // 3. local connectivity: rank of each node in the sorted list
     if (ne > 0) thrust::lower_bound(pol, p->d_l2g, p->d_l2g + nl, p->d_conn, p->d_conn + ne * nn, p->d_conn);
     // 4. the owned range in local numbering (contiguous: every owned node is in the list)
-    int32_t bounds[2] = {(int32_t)node_lo, (int32_t)node_hi}, *d_b = d_sel;   // (d_sel is free again: >= 2 ints when n_elems >= 2)
+    int32_t bounds[2] = {(int32_t)node_lo, (int32_t)node_hi};
     int32_t h_pos[2] = {0, 0};
     int32_t* d_q = nullptr;
     if (cudaMalloc((void**)&d_q, 4 * sizeof(int32_t)) != cudaSuccess) return fail(femx_fail(ctx, FEMX_ERR_NOMEM, "femx_partition_extract: out of memory"));
-    (void)d_b;
     cudaMemcpyAsync(d_q, bounds, sizeof bounds, cudaMemcpyHostToDevice, st);
     thrust::lower_bound(pol, p->d_l2g, p->d_l2g + nl, d_q, d_q + 2, d_q + 2);
     cudaMemcpyAsync(h_pos, d_q + 2, sizeof h_pos, cudaMemcpyDeviceToHost, st);
