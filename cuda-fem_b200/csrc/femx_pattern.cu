@@ -1534,6 +1534,27 @@ int femx_pattern_lattice(const femx_pattern* p, int* n_per_cell, int64_t* h_cell
   return FEMX_OK;
 }
 
+int femx_lattice_prefix(int dim, const int32_t* h_cells, const int64_t* h_strides, int64_t node0, const int32_t* h_weights,
+                        int64_t n, const int64_t* h_nodes, int64_t* h_out) {
+  if ((dim != 2 && dim != 3) || !h_cells || !h_strides || !h_weights || (n > 0 && (!h_nodes || !h_out)))
+    return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_lattice_prefix: bad argument");
+  lat_geom g = {};
+  g.dim = dim;
+  for (int d = 0; d < 3; ++d) { g.cn[d] = d < dim ? h_cells[d] : 1; g.s[d] = d < dim ? h_strides[d] : 0; }
+  g.node0 = node0;
+  if (g.cn[0] < 1 || g.cn[1] < 1 || g.cn[2] < 1 || g.s[0] != 1 || g.s[1] < g.cn[0] + 1 ||
+      (dim == 3 && g.s[2] < (long long)g.cn[1] * g.s[1] + g.cn[0] + 1))
+    return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_lattice_prefix: strides narrower than the lattice");
+  const lat_pref P = lat_pref_make(g, h_weights);
+  for (int64_t i = 0; i < n; ++i) {
+    if (h_nodes[i] - node0 >= (1LL << 31)) return femx_fail(nullptr, FEMX_ERR_UNSUPPORTED, "femx_lattice_prefix: node ids beyond 32 bits");
+    long long ijk[3];
+    lat_locate(g, h_nodes[i] - node0, ijk);
+    h_out[i] = lat_prefix(g, P, ijk);
+  }
+  return FEMX_OK;
+}
+
 int femx_pattern_export_csr(const femx_pattern* p, int64_t* d_rp64, int32_t* d_rp32, int32_t* d_col,
                             void* stream) {
   if (!p) return femx_fail(nullptr, FEMX_ERR_INVALID, "femx_pattern_export_csr: pattern is NULL");

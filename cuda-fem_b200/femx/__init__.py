@@ -52,7 +52,7 @@ SYMBOLS = [
     "femx_dist_unique_id", "femx_dist_create", "femx_dist_info",
     "femx_partition_extract", "femx_part_destroy", "femx_part_info", "femx_part_arrays", "femx_part_copy", "femx_part_gather",
     "femx_pattern_export_csr_mapped", "femx_dist_destroy", "femx_dist_slab", "femx_dist_allreduce",
-    "femx_dist_op_create", "femx_dist_op_destroy", "femx_dist_op_info", "femx_dist_op_peer_halo", "femx_dist_spmv", "femx_dist_cg", "femx_spmv_rows",
+    "femx_dist_op_create", "femx_dist_op_destroy", "femx_dist_op_info", "femx_dist_op_peer_halo", "femx_lattice_prefix", "femx_dist_spmv", "femx_dist_cg", "femx_spmv_rows",
     "femx_form_compile", "femx_form_compile_offline", "femx_form_destroy", "femx_form_source",
     "femx_form_log", "femx_form_entry", "femx_form_prologue", "femx_form_cubin",
     "femx_mesh_rectangle", "femx_mesh_expand", "femx_mesh_box",
@@ -610,6 +610,22 @@ class DistOp:
             lib().femx_dist_op_destroy.argtypes = [C.c_void_p]
             lib().femx_dist_op_destroy(self.h)
             self.h = C.c_void_p()
+
+
+def lattice_prefix(cells, strides, node0, weights, nodes):
+    """Closed-form prefix sums over the nodes of a lattice (femx_lattice_prefix; host only): numpy int64 array."""
+    import numpy as np
+    dim = len(cells)
+    c = (C.c_int32 * dim)(*[int(v) for v in cells])
+    s_ = (C.c_int64 * dim)(*[int(v) for v in strides])
+    w = (C.c_int32 * 27)(*[int(v) for v in weights])
+    q = np.ascontiguousarray(nodes, np.int64)
+    out = np.empty(len(q), np.int64)
+    st = lib().femx_lattice_prefix(dim, c, s_, _i64(node0), w, _i64(len(q)), q.ctypes.data_as(C.c_void_p),
+                                   out.ctypes.data_as(C.c_void_p))
+    if st:
+        raise FemxError(st, lib().femx_last_error(None).decode())
+    return out
 
 
 def read_gmsh(path):

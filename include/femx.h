@@ -270,6 +270,14 @@ int femx_form_cubin_stencil(femx_form* form, int n_incid, int row_len, int self_
  * h_cells / h_strides: 3 entries each; h_corners: 8*nn entries; any pointer may be NULL. */
 int femx_pattern_lattice(const femx_pattern* pat, int* n_per_cell, int64_t* h_cells, int64_t* h_strides,
                          int64_t* node0, int32_t* h_corners);
+/* Host utility (no device): the closed form the lattice symbolic pass evaluates per row.  Lattice node (i, j, k),
+ * 0 <= i <= h_cells[0] ..., is node node0 + i + j h_strides[1] + k h_strides[2] (strides may be wider than the lattice:
+ * the nodes in between carry nothing); its class is ci + 3 cj + 9 ck with c = 0 / 1 / 2 for the low face / interior / high
+ * face along an axis.  h_out[q] = sum of h_weights[class] over the lattice nodes whose id is below h_nodes[q] — with
+ * weights = row length per class this is the CSR row pointer of that node, with weights = 1 for one class the number of
+ * rows of that class in front of it.  (femx_pattern.cu: lat_prefix; dim = 2: h_cells / h_strides have 2 entries.) */
+int femx_lattice_prefix(int dim, const int32_t* h_cells, const int64_t* h_strides, int64_t node0, const int32_t* h_weights,
+                        int64_t n, const int64_t* h_nodes, int64_t* h_out);
 /* Diagnostic: NVRTC-compiles the element-once lattice pass for an explicitly given lattice cell (n_per_cell
  * elements, h_corners as above), node strides and stencil class (row_len sorted column offsets h_offsets, own
  * position self_pos); no device needed with a form from femx_form_compile_offline.  h_info (6 ints, may be NULL)
