@@ -127,3 +127,15 @@ def test_offline_jit_rhs_kernel(golden_dir):
     f = femx.Form(None, 3, femx.ELASTICITY, nd=3, params=(1.0, 0.5), rhs_vec=(0.0, 0.0, -9.81), offline=True)
     assert f.cubin("rhs")[:4] == b"\x7fELF"
     f.close()
+
+
+def test_cxx_clients_build_and_link():
+    """examples/: plain C++ clients of the C ABI (the reference's main(), the weak-form front end, the multi-GPU CG) compile
+    against include/femx.h and link against libfemx.so only; without arguments the multi-GPU client prints its usage."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "examples")])
+    for exe in ("femx_sparse2", "femx_weakform_demo", "femx_dist_cg"):
+        assert os.access(os.path.join(root, "examples", exe), os.X_OK), exe
+    r = subprocess.run([os.path.join(root, "examples", "femx_dist_cg")], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
